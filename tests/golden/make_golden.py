@@ -1,0 +1,337 @@
+"""Generate golden input/output vectors from the UNMODIFIED reference.
+
+Run in the build container only (it imports /root/reference, which does not
+exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference's arithmetic lives in PyTorch/ATen (torch 2.11.0+cu128, CPU,
+this container); viz-only modules that are not installed (matplotlib,
+tensorboardX) are stubbed, and ``.cuda()`` is made the identity so that
+``HeatModel`` (which calls ``.cuda()`` unconditionally,
+models/heat_model.py:19,38-42,98-102) runs on the CPU.  Nothing else in the
+reference is touched.  Seeds follow utils/build.py:18-21 (666).
+
+Outputs: tests/golden/*.npz (small; committed).
+"""
+import argparse
+import os
+import sys
+import types
+
+os.environ.setdefault("HOME", "/root")
+os.environ["CUDA_VISIBLE_DEVICES"] = ""
+for _name in ("matplotlib", "matplotlib.pyplot", "tensorboardX"):
+    sys.modules[_name] = types.ModuleType(_name)
+sys.modules["matplotlib"].use = lambda *a, **k: None
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+sys.modules["tensorboardX"].SummaryWriter = object
+sys.path.insert(0, "/root/reference")
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.nn.Module.cuda = lambda self, *a, **k: self
+
+import utils  # noqa: E402  (reference)
+from models.get_iterator import get_iterator  # noqa: E402
+from models.heat_model import HeatModel  # noqa: E402
+from models.iterators import (ConvIterator, JacobiIterator, MultigridIterator,  # noqa: E402
+                              UNetIterator)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def seed(s=666):
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def npy(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def heat_source(N, B):
+    """generation.py:101-115 get_heat_source."""
+    out = []
+    for _ in range(B):
+        scale = np.random.uniform(3, 3.5) / (N ** 2)
+        f = -utils.gaussian(N - 2) * scale
+        f = torch.Tensor(f).unsqueeze(0)
+        out.append(utils.pad_boundary(f, torch.zeros(1, 4)))
+    return torch.cat(out, dim=0)
+
+
+def square_problem(B, N, poisson):
+    bc = torch.rand(B, 4)
+    if poisson:
+        bc = bc * 0.75
+    x = utils.set_boundary(torch.rand(B, N, N), bc)
+    f = heat_source(N, B) if poisson else None
+    return x, bc, f
+
+
+def mask_problem(B, N, geometry):
+    x, v, m = utils.get_geometry(geometry, N, B, 1)
+    bc = torch.Tensor(np.stack([v, m], axis=1))
+    x = utils.initialize(torch.Tensor(x), bc, "random")
+    return x, bc, None
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **{k: v for k, v in arrs.items() if v is not None})
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
+# --------------------------------------------------------------------------
+def gen_ops():
+    """Grid operators of utils/heat_utils.py on both bc encodings."""
+    for tag, maker in (("square17", lambda: square_problem(3, 17, True)),
+                       ("square33", lambda: square_problem(3, 33, True)),
+                       ("square65", lambda: square_problem(2, 65, False)),
+                       ("cyl33", lambda: mask_problem(3, 33, "cylinders")),
+                       ("lshape33", lambda: mask_problem(3, 33, "Lshape")),
+                       ("cyl65", lambda: mask_problem(2, 65, "cylinders"))):
+        seed()
+        x, bc, f = maker()
+        B, N, _ = x.shape
+        gt = torch.rand(B, N, N)
+        out = dict(x=npy(x), bc=npy(bc), gt=npy(gt))
+        if f is not None:
+            out["f"] = npy(f)
+            out["fd_step_f"] = npy(utils.fd_step(x.clone(), bc, f))
+            out["fd_error_max_f"] = npy(utils.fd_error(x, bc, f, "max"))
+            out["fd_error_mean_f"] = npy(utils.fd_error(x, bc, f, "mean"))
+        out["fd_step"] = npy(utils.fd_step(x.clone(), bc, None))
+        out["fd_error_max"] = npy(utils.fd_error(x, bc, None, "max"))
+        out["fd_error_mean"] = npy(utils.fd_error(x, bc, None, "mean"))
+        out["l2_error"] = npy(utils.l2_error(x, gt))
+        out["set_boundary"] = npy(utils.set_boundary(gt.clone(), bc))
+        out["pad_boundary"] = npy(utils.pad_boundary(gt[:, 1:-1, 1:-1].clone(), bc))
+        # chained Jacobi: 25 steps
+        y = x.clone()
+        for _ in range(25):
+            y = utils.fd_step(y, bc, f)
+        out["jacobi25"] = npy(y)
+        out["jacobi25_fd_error"] = npy(utils.fd_error(y, bc, f, "max"))
+        # transfer operators
+        M = (N - 1) // 2 + 1
+        if bc.dim() == 4:
+            bc_sub = utils.subsample(bc.view(B * 2, N, N)).view(B, 2, M, M)
+        else:
+            bc_sub = bc
+        out["subsample"] = npy(utils.subsample(x))
+        out["bc_sub"] = npy(bc_sub)
+        out["restriction"] = npy(utils.restriction(x, bc_sub))
+        xs = torch.rand(B, M, M)
+        out["xs"] = npy(xs)
+        out["interpolation"] = npy(utils.interpolation(xs, bc))
+        save("ops_" + tag, **out)
+
+
+def rand_conv_weights(it, scale=0.15):
+    with torch.no_grad():
+        for p in it.parameters():
+            p.copy_((torch.rand_like(p) - 0.5) * 2 * scale)
+
+
+def gen_conv():
+    """ConvIterator forward / H / chained steps (models/iterators/conv_iterator.py)."""
+    cases = [("square17_L1_clamp", 3, 17, "square", 1, "clamp", True),
+             ("square33_L3_clamp", 3, 33, "square", 3, "clamp", False),
+             ("square33_L3_none_f", 3, 33, "square", 3, "none", True),
+             ("square65_L2_sigmoid", 2, 65, "square", 2, "sigmoid", False),
+             ("cyl33_L3_clamp", 3, 33, "cylinders", 3, "clamp", False),
+             ("lshape33_L4_none", 2, 33, "Lshape", 4, "none", False),
+             ("square17_L5_none", 2, 17, "square", 5, "none", False),
+             ("square33_L3_clamp_B1", 1, 33, "square", 3, "clamp", False)]
+    for tag, B, N, geom, L, act, poisson in cases:
+        seed()
+        x, bc, f = square_problem(B, N, poisson) if geom == "square" else mask_problem(B, N, geom)
+        it = ConvIterator(act, L)
+        it.is_bc_mask = geom != "square"
+        rand_conv_weights(it)
+        w = np.stack([npy(l.weight)[0, 0] for l in it.layers])
+        with torch.no_grad():
+            y1 = it(x, bc, f)
+            r = torch.rand(B, 1, N - 2, N - 2) - 0.5
+            h = it.H(r, bc)
+            y = x
+            for _ in range(10):
+                y = it(y, bc, f)
+        save("conv_" + tag, x=npy(x), bc=npy(bc), f=None if f is None else npy(f), w=w,
+             step1=npy(y1), r=npy(r[:, 0]), H=npy(h[:, 0]), step10=npy(y),
+             meta=np.array([L, {"none": 0, "clamp": 1, "sigmoid": 2}[act], int(geom != "square")]))
+
+
+def gen_multigrid():
+    """MultigridIterator.forward (models/iterators/jacobi_iterator.py:23-78)."""
+    cases = [("square17_2_1_1", 3, 17, "square", (2, 1, 1), True),
+             ("square33_3_2_2", 3, 33, "square", (3, 2, 2), True),
+             ("square65_4_2_1", 2, 65, "square", (4, 2, 1), False),
+             ("square129_3_2_2", 2, 129, "square", (3, 2, 2), False),
+             ("cyl33_3_2_2", 3, 33, "cylinders", (3, 2, 2), False),
+             ("lshape65_3_1_2", 2, 65, "Lshape", (3, 1, 2), False)]
+    for tag, B, N, geom, (nl, pre, post), poisson in cases:
+        seed()
+        x, bc, f = square_problem(B, N, poisson) if geom == "square" else mask_problem(B, N, geom)
+        it = MultigridIterator(nl, pre, post)
+        it.is_bc_mask = geom != "square"
+        y1 = it(x, bc, f)
+        y3 = it(it(y1, bc, f), bc, f)
+        save("mg_" + tag, x=npy(x), bc=npy(bc), f=None if f is None else npy(f), step1=npy(y1),
+             step3=npy(y3), meta=np.array([nl, pre, post, int(geom != "square")]))
+
+
+def unet_weights(it):
+    g = lambda ml: (np.stack([npy(l.weight)[0, 0] for l in ml]) if len(ml) else
+                    np.zeros((0, 3, 3), np.float32))
+    return g(it.first_layers), g(it.pooling_layers), g(it.second_layers)
+
+
+def gen_unet():
+    """UNetIterator forward / H (models/iterators/unet_iterator.py)."""
+    cases = [("square17_2_1_1_clamp", 3, 17, "square", (2, 1, 1), "clamp", False),
+             ("square33_3_2_2_clamp", 3, 33, "square", (3, 2, 2), "clamp", True),
+             ("square65_3_2_2_none", 2, 65, "square", (3, 2, 2), "none", False),
+             ("square129_2_1_2_clamp", 2, 129, "square", (2, 1, 2), "clamp", False),
+             ("cyl33_3_2_2_clamp", 3, 33, "cylinders", (3, 2, 2), "clamp", False),
+             ("lshape65_3_1_1_none", 2, 65, "Lshape", (3, 1, 1), "none", False),
+             ("square33_1_2_2_none", 2, 33, "square", (1, 2, 2), "none", False)]
+    for tag, B, N, geom, (nl, pre, post), act, poisson in cases:
+        seed()
+        x, bc, f = square_problem(B, N, poisson) if geom == "square" else mask_problem(B, N, geom)
+        it = UNetIterator(act, nl, pre, post)
+        it.is_bc_mask = geom != "square"
+        rand_conv_weights(it, 0.2)
+        wf, wp, ws = unet_weights(it)
+        with torch.no_grad():
+            y1 = it(x, bc, f)
+            r = torch.rand(B, 1, N - 2, N - 2) - 0.5
+            h = it.H(r, bc)
+            y = x
+            for _ in range(5):
+                y = it(y, bc, f)
+        save("unet_" + tag, x=npy(x), bc=npy(bc), f=None if f is None else npy(f), w_first=wf,
+             w_pool=wp, w_second=ws, step1=npy(y1), r=npy(r[:, 0]), H=npy(h[:, 0]), step5=npy(y),
+             meta=np.array([nl, pre, post, {"none": 0, "clamp": 1, "sigmoid": 2}[act],
+                            int(geom != "square")]))
+
+
+def gen_backward():
+    """Autograd through ONE reference step with the reference loss
+    (models/heat_model.py:52-53: nn.MSELoss over all B*N*N entries)."""
+    for kind in ("conv", "unet"):
+        for geom in ("square", "cylinders"):
+            for act in ("none", "clamp", "sigmoid"):
+                seed()
+                B, N = 3, 33
+                x, bc, f = (square_problem(B, N, True) if geom == "square"
+                            else mask_problem(B, N, geom))
+                gt = torch.rand(B, N, N)
+                if kind == "conv":
+                    it = ConvIterator(act, 3)
+                    rand_conv_weights(it)
+                else:
+                    it = UNetIterator(act, 3, 2, 1)
+                    rand_conv_weights(it, 0.2)
+                it.is_bc_mask = geom != "square"
+                if act == "clamp":  # make the clamp gate bite on some cells
+                    x = x * 1.6 - 0.3
+                    x = utils.set_boundary(x, bc)
+                xg = x.clone().requires_grad_(True)
+                y = it(xg, bc, f)
+                loss = torch.nn.MSELoss()(y, gt)
+                loss.backward()
+                out = dict(x=npy(x), bc=npy(bc), f=None if f is None else npy(f), gt=npy(gt),
+                           y=npy(y), loss=np.float32(loss.item()), gx=npy(xg.grad))
+                if kind == "conv":
+                    out["w"] = np.stack([npy(l.weight)[0, 0] for l in it.layers])
+                    out["gw"] = np.stack([npy(l.weight.grad)[0, 0] for l in it.layers])
+                    out["meta"] = np.array([3, {"none": 0, "clamp": 1, "sigmoid": 2}[act],
+                                            int(geom != "square")])
+                else:
+                    wf, wp, ws = unet_weights(it)
+                    gg = lambda ml: np.stack([npy(l.weight.grad)[0, 0] for l in ml])
+                    out.update(w_first=wf, w_pool=wp, w_second=ws, gw_first=gg(it.first_layers),
+                               gw_pool=gg(it.pooling_layers), gw_second=gg(it.second_layers),
+                               meta=np.array([3, 2, 1, {"none": 0, "clamp": 1, "sigmoid": 2}[act],
+                                              int(geom != "square")]))
+                save("bwd_%s_%s_%s" % (kind, geom, act), **out)
+
+
+def make_opt(**kw):
+    d = dict(iterator="conv", activation="clamp", conv_n_layers=3, mg_n_layers=3,
+             mg_pre_smoothing=2, mg_post_smoothing=2, cg_n_iters=4, geometry="square",
+             is_train=True, optimizer="adam", lr_init=1e-3, max_iter_steps=6,
+             max_iter_steps_from_gt=4, lambda_gt=0.0)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def gen_drivers():
+    """Loop drivers: calculate_errors / HeatModel.evaluate / HeatModel.train /
+    get_iterator (utils/heat_utils.py:163-181, models/heat_model.py:31-128)."""
+    # ---- evaluate (conv vs Jacobi) on a small square problem
+    seed()
+    B, N = 4, 17
+    x, bc, f = square_problem(B, N, False)
+    gt = x.clone()
+    for _ in range(600):
+        gt = utils.fd_step(gt, bc, None)
+    x = utils.initialize(x, bc, "avg")
+    model = HeatModel(make_opt(is_train=False))
+    rand_conv_weights(model.iterator, 0.05)
+    w = np.stack([npy(l.weight)[0, 0] for l in model.iterator.layers])
+    results, xf = model.evaluate(x.clone(), gt, bc, None, 60)
+    save("driver_evaluate_conv17", x=npy(x), bc=npy(bc), gt=npy(gt), w=w,
+         jacobi_errors=npy(results["Jacobi errors"]), model_errors=npy(results["model errors"]),
+         x_final=npy(xf))
+
+    # ---- train: three optimiser steps, both loss terms active
+    for tag, opt in (("conv_adam", make_opt(lambda_gt=0.3)),
+                     ("conv_sgd", make_opt(optimizer="sgd", lr_init=1e-2)),
+                     ("unet_adam", make_opt(iterator="unet", mg_n_layers=2, lambda_gt=0.0))):
+        seed()
+        x, bc, f = square_problem(4, 17, True)
+        gt = x.clone()
+        for _ in range(600):
+            gt = utils.fd_step(gt, bc, f)
+        x = utils.initialize(x, bc, "random")
+        model = HeatModel(opt)
+        rand_conv_weights(model.iterator, 0.05)
+        sd0 = {k: npy(v) for k, v in model.iterator.state_dict().items()}
+        np.random.seed(1234)  # the step counts N, M are drawn from numpy's global RNG (heat_model.py:46,59)
+        losses = []
+        for _ in range(3):
+            out = model.train(x.clone(), gt, bc, f)
+            losses.append([out["loss"].get("loss_x", np.nan), out["loss"].get("loss_gt", np.nan)])
+        sd1 = {k: npy(v) for k, v in model.iterator.state_dict().items()}
+        arrs = dict(x=npy(x), bc=npy(bc), f=npy(f), gt=npy(gt), losses=np.array(losses, np.float64))
+        for k, v in sd0.items():
+            arrs["w0/" + k] = v
+        for k, v in sd1.items():
+            arrs["w1/" + k] = v
+        save("driver_train_" + tag, **arrs)
+
+    # ---- get_iterator contract
+    rows = []
+    for itname in ("jacobi", "multigrid", "conv", "unet"):
+        for geom in ("square", "Lshape"):
+            it, cmp_, ratio, is_train = get_iterator(make_opt(iterator=itname, geometry=geom))
+            rows.append((itname, geom, it.name(), "" if cmp_ is None else cmp_.name(), float(ratio),
+                         bool(is_train), bool(it.is_bc_mask), float(it.n_operations)))
+    np.save(os.path.join(HERE, "get_iterator_contract.npy"), np.array(rows, dtype=object),
+            allow_pickle=True)
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    gen_ops()
+    gen_conv()
+    gen_multigrid()
+    gen_unet()
+    gen_backward()
+    gen_drivers()
