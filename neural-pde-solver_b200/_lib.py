@@ -1,0 +1,115 @@
+"""ctypes binding of libnpde_b200.so -- the C ABI declared in include/npde.h.
+
+There is exactly one implementation of every operator: the CUDA library.  If it
+has not been built, importing any operator raises; there is no CPU or PyTorch
+fallback.  (tests/ can point the binding at the host-compiled SIMT emulator of
+the same sources with ``_use_emulator`` -- test infrastructure, never used by
+the package itself.)
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnpde_b200.so")
+
+OK = 0
+BC_SQUARE, BC_MASK = 0, 1
+ACT = {"none": 0, "clamp": 1, "sigmoid": 2}
+AGG = {"max": 0, "mean": 1}
+IT_JACOBI, IT_CONV, IT_MULTIGRID, IT_UNET = 0, 1, 2, 3
+WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_ITERATE = 0, 1, 2, 3, 4, 5, 16
+MAX_CONV_LAYERS = 8
+
+_c_float_p = ctypes.c_void_p  # raw device pointers
+_int = ctypes.c_int
+_size = ctypes.c_size_t
+_vp = ctypes.c_void_p
+
+
+class IterateDesc(ctypes.Structure):
+    """struct npde_iterate_desc (include/npde.h)."""
+    _fields_ = [
+        ("iterator", _int), ("B", _int), ("N", _int), ("bc_kind", _int), ("n_layers", _int),
+        ("pre", _int), ("post", _int), ("act", _int), ("k", _int), ("temporal_depth", _int),
+        ("x_in", _vp), ("x_out", _vp), ("bc", _vp), ("f", _vp), ("w", _vp), ("w_host", _vp),
+        ("gt", _vp), ("err_l2", _vp), ("err_fd", _vp), ("workspace", _vp), ("workspace_bytes", _size),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/npde.h
+PROTOTYPES = {
+    "npde_version": (_int, []),
+    "npde_strerror": (ctypes.c_char_p, [_int]),
+    "npde_workspace_bytes": (_size, [_int] * 8),
+    "npde_set_boundary": (_int, [_vp, _vp, _int, _int, _int, _vp]),
+    "npde_pad_boundary": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),
+    "npde_fd_step": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp]),
+    "npde_fd_error": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_l2_error": (_int, [_vp, _vp, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_conv_H": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_conv_step_fwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_conv_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_subsample": (_int, [_vp, _vp, _int, _int, _vp]),
+    "npde_restrict": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),
+    "npde_prolong": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),
+    "npde_mg_step": (_int, [_vp, _vp, _int, _vp, _int, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_unet_H": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_unet_step_fwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _int, _int,
+                                  _vp, _size, _vp]),
+    "npde_unet_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp,
+                                  _vp, _int, _int, _vp, _size, _vp]),
+    "npde_iterate": (_int, [ctypes.POINTER(IterateDesc), _vp]),
+}
+
+_lib = None
+_emulated = False
+
+
+class NpdeError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        msg = lib().npde_strerror(code)
+        super().__init__("%s failed: %s (code %d)" % (where, msg.decode() if msg else "?", code))
+
+
+def _bind(path):
+    handle = ctypes.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(handle, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return handle
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libnpde_b200.so is not built (%s). Build it with `python neural-pde-solver_b200/build.py` "
+                "(needs nvcc); there is no CPU fallback." % LIB_PATH)
+        _lib = _bind(LIB_PATH)
+    return _lib
+
+
+def is_emulated():
+    return _emulated
+
+
+def _use_emulator(path):
+    """TESTS ONLY: bind the host-compiled SIMT emulator build of the same CUDA sources
+    (tests/emu).  It takes host pointers, so CPU tensors are accepted while it is active."""
+    global _lib, _emulated
+    _lib = _bind(path)
+    _emulated = True
+
+
+def _use_cuda_library():
+    global _lib, _emulated
+    _lib = None
+    _emulated = False
+
+
+def check(code, where):
+    if code != OK:
+        raise NpdeError(code, where)

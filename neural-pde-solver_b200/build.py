@@ -1,0 +1,85 @@
+"""Builds libnpde_b200.so (sm_100a) in-tree with nvcc.
+
+The shared library is the product: hand-written CUDA kernels plus the C ABI of
+include/npde.h.  There is no JIT and no fallback: if the library is missing the
+package refuses to work (see _lib.py).
+
+    python neural-pde-solver_b200/build.py            # build if sources changed
+    python neural-pde-solver_b200/build.py --force
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
+LIB = os.path.join(HERE, "libnpde_b200.so")
+SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_api.cu"]
+HEADERS = [os.path.join(CSRC, "npde_common.cuh"), os.path.join(CSRC, "npde_internal.h"),
+           os.path.join(ROOT, "include", "npde.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--fmad=false"]  # no implicit contraction: every fused multiply-add is written as one
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = []
+    for src in SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(o, [s] + HEADERS):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", "-o", o, s])
+
+    def run(cmd):
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(run, jobs))
+    objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    if force or jobs or _stale(LIB, objs):
+        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+    return LIB
+
+
+def build_emulator(force=False):
+    """TEST INFRASTRUCTURE: the same .cu sources compiled for the host against
+    tests/emu/cuda_emu.h (a SIMT emulator) -> tests/emu/_build/libnpde_emu.so.
+    Used by the CPU test-suite to check index logic without a GPU; never loaded
+    by the product path."""
+    emu_dir = os.path.join(ROOT, "tests", "emu")
+    out = os.path.join(emu_dir, "_build", "libnpde_emu.so")
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    if force or _stale(out, srcs + HEADERS + [os.path.join(emu_dir, "cuda_emu.h")]):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-DNPDE_EMU", "-ffp-contract=off", "-fPIC", "-shared",
+               "-I" + emu_dir, "-x", "c++"] + srcs + ["-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emulator build failed:\n" + r.stderr)
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

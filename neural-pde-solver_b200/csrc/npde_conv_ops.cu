@@ -1,0 +1,347 @@
+// npde_conv_ops.cu -- layer-by-layer building blocks of the learned iterators:
+// masked 3x3 cross-correlation (stride 1 / stride 2), the Psi/residual shell,
+// the act+pad+G epilogue, the UNet's pad->bilinear->crop, and the backward
+// pieces (weight-gradient reductions, transposed convs).  The UNet, conv stacks
+// deeper than the fused kernel supports, and the whole backward path are
+// compositions of these; the k-step Jacobi/Conv hot loop uses npde_stream.cu.
+#include "npde_common.cuh"
+#include "npde_internal.h"
+
+namespace {
+
+constexpr int TX = 32, TY = 8;
+inline dim3 grid2d(int W, int H, int B) { return dim3((W + TX - 1) / TX, (H + TY - 1) / TY, B); }
+
+__device__ __forceinline__ float ldz(const float *__restrict__ p, int H, int i, int j) {
+  return (i < 0 || j < 0 || i >= H || j >= H) ? 0.0f : __ldg(p + (size_t)i * H + j);
+}
+
+// foreground multiplier of cell (i,j) of an S x S interior: 1 - mask[(i+1),(j+1)]
+// with mask the (S+2) x (S+2) level mask  (conv_iterator.py:24, unet_iterator.py:43-48).
+__device__ __forceinline__ float fg_at(const float *__restrict__ mask, int S, int i, int j) {
+  return __fsub_rn(1.0f, __ldg(mask + (size_t)(i + 1) * (S + 2) + (j + 1)));
+}
+
+// out = conv3x3(in) [* fg]: row-major fmaf chain, first tap a plain product.
+__global__ void k_conv3x3(const float *__restrict__ in, int Hi, const float *__restrict__ w, int stride,
+                          int pad, const float *__restrict__ mask, size_t mask_bstride,
+                          float *__restrict__ out, int Ho) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= Ho || j >= Ho) return;
+  const float *p = in + (size_t)b * Hi * Hi;
+  int i0 = i * stride - pad, j0 = j * stride - pad;
+  float acc = __fmul_rn(__ldg(w + 0), ldz(p, Hi, i0, j0));
+  acc = __fmaf_rn(__ldg(w + 1), ldz(p, Hi, i0, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 2), ldz(p, Hi, i0, j0 + 2), acc);
+  acc = __fmaf_rn(__ldg(w + 3), ldz(p, Hi, i0 + 1, j0), acc);
+  acc = __fmaf_rn(__ldg(w + 4), ldz(p, Hi, i0 + 1, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 5), ldz(p, Hi, i0 + 1, j0 + 2), acc);
+  acc = __fmaf_rn(__ldg(w + 6), ldz(p, Hi, i0 + 2, j0), acc);
+  acc = __fmaf_rn(__ldg(w + 7), ldz(p, Hi, i0 + 2, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 8), ldz(p, Hi, i0 + 2, j0 + 2), acc);
+  if (mask) acc = __fmul_rn(acc, fg_at(mask + (size_t)b * mask_bstride, Ho, i, j));
+  out[((size_t)b * Ho + i) * Ho + j] = acc;
+}
+
+// adjoint of k_conv3x3 w.r.t. its input: out[p,q] = sum_{a,c} w[a,c] * g[(p+pad-a)/s, (q+pad-c)/s]
+__global__ void k_conv3x3_transpose(const float *__restrict__ g, int Hg, const float *__restrict__ w,
+                                    int stride, int pad, float *__restrict__ out, int Ho) {
+  int q = blockIdx.x * TX + threadIdx.x, p = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (p >= Ho || q >= Ho) return;
+  const float *gb = g + (size_t)b * Hg * Hg;
+  float acc = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int ii = p + pad - a, jj = q + pad - c;
+      if (ii < 0 || jj < 0 || (ii % stride) || (jj % stride)) continue;
+      ii /= stride;
+      jj /= stride;
+      if (ii >= Hg || jj >= Hg) continue;
+      acc = __fmaf_rn(__ldg(w + a * 3 + c), __ldg(gb + (size_t)ii * Hg + jj), acc);
+    }
+  out[((size_t)b * Ho + p) * Ho + q] = acc;
+}
+
+__global__ void k_mul_fg(float *r, const float *__restrict__ mask, size_t mask_bstride, int S) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= S || j >= S) return;
+  size_t o = ((size_t)b * S + i) * S + j;
+  r[o] = __fmul_rn(r[o], fg_at(mask + (size_t)b * mask_bstride, S, i, j));
+}
+
+__global__ void k_add_inplace(float *a, const float *__restrict__ b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = __fadd_rn(a[i], __ldg(b + i));
+}
+
+// conv_iterator.py:38-43 / unet_iterator.py:92-98: y = Psi_valid(x) - f ; r0 = (y - x_int) [* fg]
+__global__ void k_psi_residual(const float *__restrict__ x, const float *__restrict__ f,
+                               const float *__restrict__ mask, size_t mask_bstride, float *__restrict__ y_int,
+                               float *__restrict__ r0, int N) {
+  int S = N - 2;
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= S || j >= S) return;
+  const float *p = x + ((size_t)b * N + (i + 1)) * N + (j + 1);
+  float y = npde_psi(__ldg(p - N), __ldg(p - 1), __ldg(p + 1), __ldg(p + N));
+  if (f) y = __fsub_rn(y, __ldg(f + ((size_t)b * N + (i + 1)) * N + (j + 1)));
+  float r = __fsub_rn(y, __ldg(p));
+  if (mask) r = __fmul_rn(r, fg_at(mask + (size_t)b * mask_bstride, S, i, j));
+  size_t o = ((size_t)b * S + i) * S + j;
+  y_int[o] = y;
+  r0[o] = r;
+}
+
+// conv_iterator.py:46-50: out = G(pad(act(y + h)))
+__global__ void k_combine(const float *__restrict__ y_int, const float *__restrict__ h, BcView bc, int act,
+                          float *__restrict__ out, int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  int S = N - 2;
+  float v = 0.0f;
+  if (i >= 1 && i <= N - 2 && j >= 1 && j <= N - 2) {
+    size_t o = ((size_t)b * S + (i - 1)) * S + (j - 1);
+    v = npde_act(__fadd_rn(__ldg(y_int + o), __ldg(h + o)), act);
+  }
+  out[((size_t)b * N + i) * N + j] = npde_apply_G(v, bc, b, i, j, N);
+}
+
+// value of zero_pad_1(r) at padded coordinates (I,J), r is s x s
+__device__ __forceinline__ float padded_at(const float *__restrict__ r, int s, int I, int J) {
+  return (I >= 1 && I <= s && J >= 1 && J <= s) ? __ldg(r + (size_t)(I - 1) * s + (J - 1)) : 0.0f;
+}
+
+// unet_iterator.py:78-83: zero-pad 1, bilinear x2 (align_corners), crop 1, [* fg of the finer level]
+__global__ void k_pad_up_crop(const float *__restrict__ r, int s, const float *__restrict__ mask_out,
+                              size_t mask_bstride, float *__restrict__ out, int nested) {
+  int so = 2 * s + 1;
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= so || j >= so) return;
+  const float *rb = r + (size_t)b * s * s;
+  int ii = i + 1, jj = j + 1;  // coordinates in the (2M-1)^2 upsampled padded image, M = s+2
+  int I = ii >> 1, J = jj >> 1;
+  float v;
+  if (!(ii & 1) && !(jj & 1)) v = padded_at(rb, s, I, J);
+  else if (!(ii & 1)) v = __fmul_rn(0.5f, __fadd_rn(padded_at(rb, s, I, J), padded_at(rb, s, I, J + 1)));
+  else if (!(jj & 1)) v = __fmul_rn(0.5f, __fadd_rn(padded_at(rb, s, I, J), padded_at(rb, s, I + 1, J)));
+  else {
+    float a = padded_at(rb, s, I, J), bq = padded_at(rb, s, I, J + 1);
+    float c = padded_at(rb, s, I + 1, J), d = padded_at(rb, s, I + 1, J + 1);
+    float sum = nested ? __fadd_rn(__fadd_rn(a, bq), __fadd_rn(c, d))
+                       : __fadd_rn(__fadd_rn(__fadd_rn(a, bq), c), d);
+    v = __fmul_rn(0.25f, sum);
+  }
+  if (mask_out) v = __fmul_rn(v, fg_at(mask_out + (size_t)b * mask_bstride, so, i, j));
+  out[((size_t)b * so + i) * so + j] = v;
+}
+
+// adjoint of k_pad_up_crop (without the mask multiply): g is (2s+1)^2, out is s^2
+__global__ void k_pad_up_crop_transpose(const float *__restrict__ g, int s, float *__restrict__ out) {
+  int so = 2 * s + 1;
+  int J = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (I >= s || J >= s) return;
+  const float *gb = g + (size_t)b * so * so;
+  // padded coarse coords (I+1,J+1) <-> upsampled coords (2I+2, 2J+2) <-> cropped coords (2I+1, 2J+1)
+  int ci = 2 * I + 1, cj = 2 * J + 1;
+  float acc = 0.0f;
+#pragma unroll
+  for (int di = -1; di <= 1; ++di)
+#pragma unroll
+    for (int dj = -1; dj <= 1; ++dj) {
+      int i = ci + di, j = cj + dj;
+      if (i < 0 || j < 0 || i >= so || j >= so) continue;
+      float wgt = (di == 0 ? 1.0f : 0.5f) * (dj == 0 ? 1.0f : 0.5f);
+      acc = __fmaf_rn(wgt, __ldg(gb + (size_t)i * so + j), acc);
+    }
+  out[((size_t)b * s + I) * s + J] = acc;
+}
+
+// gz = crop(gout * (1 - m)) * act'(y + rL)      
+__global__ void k_bwd_gz(const float *__restrict__ gout, const float *__restrict__ y_int,
+                         const float *__restrict__ rL, const float *__restrict__ mask, size_t mask_bstride,
+                         int act, float *__restrict__ gz, int N) {
+  int S = N - 2;
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= S || j >= S) return;
+  size_t o = ((size_t)b * S + i) * S + j;
+  float go = __ldg(gout + ((size_t)b * N + (i + 1)) * N + (j + 1));
+  if (mask) go = __fmul_rn(go, fg_at(mask + (size_t)b * mask_bstride, S, i, j));
+  float z = __fadd_rn(__ldg(y_int + o), __ldg(rL + o));
+  gz[o] = __fmul_rn(go, npde_act_grad(z, act));
+}
+
+// dL/dx = Psi_valid^T(gz + g0) - embed(g0)        (Appendix B step 3)
+__global__ void k_bwd_gx(const float *__restrict__ gz, const float *__restrict__ g0, float *__restrict__ gx,
+                         int N) {
+  int S = N - 2;
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  const float *a = gz + (size_t)b * S * S, *c = g0 + (size_t)b * S * S;
+  auto gy = [&](int I, int J) -> float {  // interior coords of the fine grid
+    if (I < 1 || J < 1 || I > N - 2 || J > N - 2) return 0.0f;
+    size_t o = (size_t)(I - 1) * S + (J - 1);
+    return __fadd_rn(__ldg(a + o), __ldg(c + o));
+  };
+  float acc = __fmul_rn(0.25f, gy(i + 1, j));
+  acc = __fmaf_rn(0.25f, gy(i, j + 1), acc);
+  acc = __fmaf_rn(0.25f, gy(i, j - 1), acc);
+  acc = __fmaf_rn(0.25f, gy(i - 1, j), acc);
+  if (i >= 1 && j >= 1 && i <= N - 2 && j <= N - 2) acc = __fsub_rn(acc, __ldg(c + (size_t)(i - 1) * S + (j - 1)));
+  gx[((size_t)b * N + i) * N + j] = acc;
+}
+
+// 9 weight-gradient sums, fp64 accumulation, deterministic two-stage reduction.
+constexpr int WG_THREADS = 256;
+__global__ void __launch_bounds__(WG_THREADS)
+k_weight_grad(const float *__restrict__ g, int Hg, const float *__restrict__ r, int Hr, int stride, int pad,
+              float *gw9, double *part, unsigned *counter, int rows_per_block, int blocks_per_img) {
+  int b = blockIdx.x / blocks_per_img, chunk = blockIdx.x % blocks_per_img;
+  const float *gb = g + (size_t)b * Hg * Hg, *rb = r + (size_t)b * Hr * Hr;
+  int i0 = chunk * rows_per_block, i1 = min(i0 + rows_per_block, Hg);
+  double acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.0;
+  for (int idx = threadIdx.x; idx < (i1 - i0) * Hg; idx += WG_THREADS) {
+    int i = i0 + idx / Hg, j = idx % Hg;
+    float gv = __ldg(gb + (size_t)i * Hg + j);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        acc[a * 3 + c] += (double)gv * (double)ldz(rb, Hr, i * stride + a - pad, j * stride + c - pad);
+  }
+  __shared__ double sh[WG_THREADS / 32][9];
+  __shared__ bool last;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    double v = npde_warp_sum(acc[t]);
+    if (lane == 0) sh[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    double v = 0.0;
+    for (int w = 0; w < WG_THREADS / 32; ++w) v += sh[w][threadIdx.x];
+    part[(size_t)blockIdx.x * 9 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned done = atomicAdd(counter, 1u);
+    last = (done == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 9) {
+    __threadfence();
+    volatile double *p = part;
+    double v = 0.0;
+    for (unsigned k = 0; k < gridDim.x; ++k) v += p[(size_t)k * 9 + threadIdx.x];
+    gw9[threadIdx.x] = (float)v;
+  }
+}
+
+inline int wg_rows_per_block(int Hg) {
+  int rows = 32768 / (Hg > 0 ? Hg : 1);
+  return rows < 1 ? 1 : rows;
+}
+
+}  // namespace
+
+namespace npde {
+
+int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const float *mask,
+            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
+  NPDE_LAUNCH(k_conv3x3, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, in, Hi, w9, stride, pad, mask, mask_bstride,
+              out, Ho);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int conv3x3_transpose(const float *g, int Hg, const float *w9, int stride, int pad, float *out, int Ho, int B,
+                      cudaStream_t st) {
+  NPDE_LAUNCH(k_conv3x3_transpose, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, g, Hg, w9, stride, pad, out, Ho);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int mul_fg(float *r, const float *mask, size_t mask_bstride, int S, int B, cudaStream_t st) {
+  NPDE_LAUNCH(k_mul_fg, grid2d(S, S, B), dim3(TX, TY), 0, st, r, mask, mask_bstride, S);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int add_inplace(float *a, const float *b, size_t n, cudaStream_t st) {
+  NPDE_LAUNCH(k_add_inplace, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, b, n);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int psi_residual(const float *x, const float *f, const float *mask, size_t mask_bstride, float *y_int,
+                 float *r0, int B, int N, cudaStream_t st) {
+  NPDE_LAUNCH(k_psi_residual, grid2d(N - 2, N - 2, B), dim3(TX, TY), 0, st, x, f, mask, mask_bstride, y_int, r0,
+              N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int combine(const float *y_int, const float *h, const float *bc, int bc_kind, int act, float *out, int B, int N,
+            cudaStream_t st) {
+  BcView v{bc, bc_kind};
+  NPDE_LAUNCH(k_combine, grid2d(N, N, B), dim3(TX, TY), 0, st, y_int, h, v, act, out, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int pad_up_crop(const float *r, int s, const float *mask_out, size_t mask_bstride, float *out, int B,
+                cudaStream_t st) {
+  int M = s + 2, so = 2 * s + 1;
+  int nested = ((long)M * M > 1024) ? 1 : 0;
+  NPDE_LAUNCH(k_pad_up_crop, grid2d(so, so, B), dim3(TX, TY), 0, st, r, s, mask_out, mask_bstride, out, nested);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int pad_up_crop_transpose(const float *g, int s, float *out, int B, cudaStream_t st) {
+  NPDE_LAUNCH(k_pad_up_crop_transpose, grid2d(s, s, B), dim3(TX, TY), 0, st, g, s, out);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int bwd_gz(const float *gout, const float *y_int, const float *rL, const float *mask, size_t mask_bstride,
+           int act, float *gz, int B, int N, cudaStream_t st) {
+  NPDE_LAUNCH(k_bwd_gz, grid2d(N - 2, N - 2, B), dim3(TX, TY), 0, st, gout, y_int, rL, mask, mask_bstride, act,
+              gz, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+size_t weight_grad_ws_bytes(int B, int Hg) {
+  int rpb = wg_rows_per_block(Hg);
+  int bpi = (Hg + rpb - 1) / rpb;
+  return npde_align_up(sizeof(double) * 9 * (size_t)B * bpi, 256) + 256;
+}
+
+int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int pad, float *gw9, int B,
+                void *ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ((uintptr_t)ws & 255) || ws_bytes < weight_grad_ws_bytes(B, Hg)) return NPDE_ERR_WORKSPACE;
+  int rpb = wg_rows_per_block(Hg);
+  int bpi = (Hg + rpb - 1) / rpb;
+  double *part = reinterpret_cast<double *>(ws);
+  unsigned *counter =
+      reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + npde_align_up(sizeof(double) * 9 * (size_t)B * bpi, 256));
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return (int)e;
+  NPDE_LAUNCH(k_weight_grad, dim3(B * bpi), dim3(WG_THREADS), 0, st, g, Hg, r, Hr, stride, pad, gw9, part,
+              counter, rpb, bpi);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream_t st) {
+  NPDE_LAUNCH(k_bwd_gx, grid2d(N, N, B), dim3(TX, TY), 0, st, gz, g0, gx, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+}  // namespace npde

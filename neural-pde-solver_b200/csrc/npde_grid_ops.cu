@@ -1,0 +1,342 @@
+// npde_grid_ops.cu -- the grid operators of utils/heat_utils.py as one fused
+// kernel each: G (set_boundary / pad_boundary), Psi+G (fd_step, single step on
+// the reference layout), the error norms (fd_error, l2_error) and the multigrid
+// transfer operators (subsample, restriction+G, interpolation+G).
+//
+// These are HBM-bound elementwise / 5-point kernels: one thread per output
+// cell, x fastest so every warp reads and writes whole 128-byte lines; the
+// neighbour reuse is served by L1.  The k-step hot loop does not use them --
+// see npde_stream.cu for the temporally blocked register-streaming kernels.
+#include "npde_common.cuh"
+#include "npde_internal.h"
+
+namespace {
+
+constexpr int TX = 32, TY = 8;
+
+inline dim3 grid2d(int W, int H, int B) { return dim3((W + TX - 1) / TX, (H + TY - 1) / TY, B); }
+
+// ---------------------------------------------------------------- G -------
+__global__ void k_set_boundary_mask(float *x, BcView bc, int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  size_t o = ((size_t)b * N + i) * N + j;
+  x[o] = npde_apply_G(x[o], bc, b, i, j, N);
+}
+
+// square: one thread per ring cell; rows skip the corner columns (columns win).
+__global__ void k_set_boundary_square(float *x, BcView bc, int N) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (t >= 4 * N) return;
+  int side = t / N, p = t - side * N;
+  const float *c = bc.bc + (size_t)b * 4;
+  float *xb = x + (size_t)b * N * N;
+  if (side == 0) { if (p > 0 && p < N - 1) xb[p] = __ldg(c + 0); }
+  else if (side == 1) { if (p > 0 && p < N - 1) xb[(size_t)(N - 1) * N + p] = __ldg(c + 1); }
+  else if (side == 2) xb[(size_t)p * N] = __ldg(c + 2);
+  else xb[(size_t)p * N + N - 1] = __ldg(c + 3);
+}
+
+__global__ void k_pad_boundary(const float *__restrict__ xin, BcView bc, float *__restrict__ y, int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  int S = N - 2;
+  bool interior = i >= 1 && i <= N - 2 && j >= 1 && j <= N - 2;
+  float v = interior ? __ldg(xin + ((size_t)b * S + (i - 1)) * S + (j - 1)) : 0.0f;
+  y[((size_t)b * N + i) * N + j] = npde_apply_G(v, bc, b, i, j, N);
+}
+
+// ------------------------------------------------------------ Psi + G -----
+__global__ void k_fd_step(const float *__restrict__ x, BcView bc, const float *__restrict__ f,
+                          float *__restrict__ y, int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  const float *xb = x + (size_t)b * N * N;
+  size_t o = (size_t)i * N + j;
+  float u = i > 0 ? __ldg(xb + o - N) : 0.0f;
+  float l = j > 0 ? __ldg(xb + o - 1) : 0.0f;
+  float r = j < N - 1 ? __ldg(xb + o + 1) : 0.0f;
+  float d = i < N - 1 ? __ldg(xb + o + N) : 0.0f;
+  float v = npde_psi(u, l, r, d);
+  if (f) v = __fsub_rn(v, __ldg(f + (size_t)b * N * N + o));
+  y[(size_t)b * N * N + o] = npde_apply_G(v, bc, b, i, j, N);
+}
+
+// -------------------------------------------------------- reductions ------
+// grid (chunks, B); every CTA reduces a band of rows, writes one partial, and
+// the last CTA of each problem folds the partials in index order, so the
+// result is deterministic (no floating-point atomics).
+struct ReduceWs {
+  double *part;       // (B, chunks)
+  unsigned *counter;  // (B), zeroed by the host wrapper
+};
+
+constexpr int RED_THREADS = 256;
+
+template <bool IS_MAX>
+__device__ __forceinline__ void block_reduce_finish(double v, ReduceWs ws, int chunks, float *err, int b,
+                                                    double denom, bool take_sqrt) {
+  __shared__ double sh[RED_THREADS / 32];
+  __shared__ bool last;
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (IS_MAX) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(NPDE_FULL_MASK, v, o));
+  } else {
+    v = npde_warp_sum(v);
+  }
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = sh[0];
+    for (int w = 1; w < RED_THREADS / 32; ++w) t = IS_MAX ? fmax(t, sh[w]) : t + sh[w];
+    ws.part[(size_t)b * chunks + blockIdx.x] = t;
+    __threadfence();
+    unsigned done = atomicAdd(ws.counter + b, 1u);
+    last = (done == (unsigned)chunks - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    volatile double *p = ws.part + (size_t)b * chunks;
+    double t = p[0];
+    for (int c = 1; c < chunks; ++c) t = IS_MAX ? fmax(t, p[c]) : t + p[c];
+    if (IS_MAX) err[b] = (float)t;
+    else err[b] = take_sqrt ? sqrtf((float)(t / denom)) : (float)(t / denom);
+  }
+}
+
+template <bool IS_MAX>
+__global__ void __launch_bounds__(RED_THREADS)
+k_fd_error(const float *__restrict__ x, BcView bc, const float *__restrict__ f, float *err, ReduceWs ws,
+           int N, int rows_per_chunk) {
+  int b = blockIdx.y, chunks = gridDim.x;
+  const float *xb = x + (size_t)b * N * N;
+  const float *fb = f ? f + (size_t)b * N * N : nullptr;
+  const bool mask = bc.kind == NPDE_BC_MASK;
+  const float *m = mask ? bc.bc + ((size_t)b * 2 + 1) * N * N : nullptr;
+  int lo = mask ? 0 : 1, hi = mask ? N : N - 1;  // heat_utils.py:113-121
+  int r0 = lo + blockIdx.x * rows_per_chunk, r1 = min(r0 + rows_per_chunk, hi);
+  double acc = 0.0;
+  int W = hi - lo;
+  for (int idx = threadIdx.x; idx < (r1 - r0) * W; idx += RED_THREADS) {
+    int i = r0 + idx / W, j = lo + idx % W;
+    size_t o = (size_t)i * N + j;
+    float u = i > 0 ? __ldg(xb + o - N) : 0.0f;
+    float l = j > 0 ? __ldg(xb + o - 1) : 0.0f;
+    float c = __ldg(xb + o);
+    float r = j < N - 1 ? __ldg(xb + o + 1) : 0.0f;
+    float d = i < N - 1 ? __ldg(xb + o + N) : 0.0f;
+    float v = npde_residual(u, l, c, r, d);
+    if (fb) v = __fsub_rn(v, __ldg(fb + o));
+    if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + o)));
+    double a = (double)fabsf(v);
+    acc = IS_MAX ? fmax(acc, a) : acc + a;
+  }
+  block_reduce_finish<IS_MAX>(acc, ws, chunks, err, b, (double)W * (double)W, false);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+k_l2_error(const float *__restrict__ x, const float *__restrict__ gt, float *err, ReduceWs ws, int N,
+           int cells_per_chunk) {
+  int b = blockIdx.y, chunks = gridDim.x;
+  size_t n = (size_t)N * N;
+  size_t c0 = (size_t)blockIdx.x * cells_per_chunk;
+  size_t c1 = c0 + cells_per_chunk < n ? c0 + cells_per_chunk : n;
+  const float *xb = x + (size_t)b * n, *gb = gt + (size_t)b * n;
+  double acc = 0.0;
+  for (size_t o = c0 + threadIdx.x; o < c1; o += RED_THREADS) {
+    float d = __fsub_rn(__ldg(xb + o), __ldg(gb + o));
+    acc += (double)__fmul_rn(d, d);
+  }
+  block_reduce_finish<false>(acc, ws, chunks, err, b, (double)n, true);
+}
+
+__global__ void k_copy_field(const float *__restrict__ src, int sp, long sb, float *__restrict__ dst, int dp, long db,
+                             int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  dst[(size_t)b * db + (size_t)i * dp + j] = __ldg(src + (size_t)b * sb + (size_t)i * sp + j);
+}
+
+// ------------------------------------------------------ transfer ops ------
+// y[I,J] = scale * x[2I,2J]   (subsample; scale 4 gives f_sub, jacobi_iterator.py:47)
+__global__ void k_subsample(const float *__restrict__ x, size_t x_bstride, float *__restrict__ y, int N, int M,
+                            float scale) {
+  int J = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (I >= M || J >= M) return;
+  float v = __ldg(x + (size_t)b * x_bstride + (size_t)2 * I * N + 2 * J);
+  y[((size_t)b * M + I) * M + J] = scale == 1.0f ? v : __fmul_rn(scale, v);
+}
+
+__global__ void k_restrict(const float *__restrict__ x, BcView bc_sub, float *__restrict__ y, int N, int M) {
+  int J = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (I >= M || J >= M) return;
+  float v = 0.0f;
+  if (I >= 1 && I <= M - 2 && J >= 1 && J <= M - 2) {
+    const float *p = x + ((size_t)b * N + 2 * I) * N + 2 * J;
+    v = __fmul_rn(0.125f, __ldg(p - N));
+    v = __fmaf_rn(0.125f, __ldg(p - 1), v);
+    v = __fmaf_rn(0.5f, __ldg(p), v);
+    v = __fmaf_rn(0.125f, __ldg(p + 1), v);
+    v = __fmaf_rn(0.125f, __ldg(p + N), v);
+  }
+  y[((size_t)b * M + I) * M + J] = npde_apply_G(v, bc_sub, b, I, J, M);
+}
+
+// bilinear x2, align_corners=True, from an M x M image with row pitch `pitch`
+// (element (I,J) at src[I*pitch+J]); see DESIGN.md for the two centre orders.
+__device__ __forceinline__ float bilinear_up_at(const float *__restrict__ src, int pitch, int i, int j,
+                                                bool nested) {
+  int I = i >> 1, J = j >> 1;
+  const float *p = src + (size_t)I * pitch + J;
+  if (!(i & 1) && !(j & 1)) return __ldg(p);
+  if (!(i & 1)) return __fmul_rn(0.5f, __fadd_rn(__ldg(p), __ldg(p + 1)));
+  if (!(j & 1)) return __fmul_rn(0.5f, __fadd_rn(__ldg(p), __ldg(p + pitch)));
+  float a = __ldg(p), bq = __ldg(p + 1), c = __ldg(p + pitch), d = __ldg(p + pitch + 1);
+  float s = nested ? __fadd_rn(__fadd_rn(a, bq), __fadd_rn(c, d))
+                   : __fadd_rn(__fadd_rn(__fadd_rn(a, bq), c), d);
+  return __fmul_rn(0.25f, s);
+}
+
+__global__ void k_prolong(const float *__restrict__ x, BcView bc, float *__restrict__ y, int M, int N,
+                          int nested) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  float v = bilinear_up_at(x + (size_t)b * M * M, M, i, j, nested != 0);
+  y[((size_t)b * N + i) * N + j] = npde_apply_G(v, bc, b, i, j, N);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------ host side ----
+namespace npde {
+
+int check_common(const void *a, const void *b, int B, int N) {
+  if (!a || !b) return NPDE_ERR_NULL;
+  if (B < 1 || N < 3) return NPDE_ERR_SIZE;
+  return NPDE_OK;
+}
+
+int check_bc(const float *bc, int bc_kind) {
+  if (bc_kind != NPDE_BC_SQUARE && bc_kind != NPDE_BC_MASK) return NPDE_ERR_BC;
+  if (!bc) return NPDE_ERR_NULL;
+  return NPDE_OK;
+}
+
+int reduce_chunks(int N) {
+  long cells = (long)N * N;
+  int c = (int)((cells + 32767) / 32768);
+  return c < 1 ? 1 : (c > 1024 ? 1024 : c);
+}
+
+size_t reduce_ws_bytes(int B, int N) {
+  return npde_align_up(sizeof(double) * (size_t)B * reduce_chunks(N), 256) +
+         npde_align_up(sizeof(unsigned) * (size_t)B, 256);
+}
+
+static int reduce_ws_carve(void *ws, size_t ws_bytes, int B, int N, ReduceWs *out, cudaStream_t st) {
+  if (!ws || ((uintptr_t)ws & 255)) return NPDE_ERR_WORKSPACE;
+  if (ws_bytes < reduce_ws_bytes(B, N)) return NPDE_ERR_WORKSPACE;
+  size_t part_bytes = npde_align_up(sizeof(double) * (size_t)B * reduce_chunks(N), 256);
+  out->part = reinterpret_cast<double *>(ws);
+  out->counter = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + part_bytes);
+  cudaError_t e = cudaMemsetAsync(out->counter, 0, sizeof(unsigned) * (size_t)B, st);
+  return e == cudaSuccess ? NPDE_OK : (int)e;
+}
+
+int set_boundary(float *x, const float *bc, int bc_kind, int B, int N, cudaStream_t st) {
+  BcView v{bc, bc_kind};
+  if (bc_kind == NPDE_BC_MASK) {
+    NPDE_LAUNCH(k_set_boundary_mask, grid2d(N, N, B), dim3(TX, TY), 0, st, x, v, N);
+  } else {
+    NPDE_LAUNCH(k_set_boundary_square, dim3((4 * N + 127) / 128, B), dim3(128), 0, st, x, v, N);
+  }
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int pad_boundary(const float *xin, const float *bc, int bc_kind, float *y, int B, int N, cudaStream_t st) {
+  BcView v{bc, bc_kind};
+  NPDE_LAUNCH(k_pad_boundary, grid2d(N, N, B), dim3(TX, TY), 0, st, xin, v, y, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int fd_step_simple(const float *x, const float *bc, int bc_kind, const float *f, float *y, int B, int N,
+                   cudaStream_t st) {
+  BcView v{bc, bc_kind};
+  NPDE_LAUNCH(k_fd_step, grid2d(N, N, B), dim3(TX, TY), 0, st, x, v, f, y, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int aggregate, float *err, int B,
+             int N, void *ws, size_t ws_bytes, cudaStream_t st) {
+  ReduceWs r;
+  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
+  if (rc) return rc;
+  BcView v{bc, bc_kind};
+  int chunks = reduce_chunks(N);
+  int rows = (bc_kind == NPDE_BC_MASK) ? N : N - 2;
+  int rpc = (rows + chunks - 1) / chunks;
+  chunks = (rows + rpc - 1) / rpc;  // no empty trailing chunks
+  if (aggregate == NPDE_AGG_MAX) {
+    NPDE_LAUNCH(k_fd_error<true>, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, v, f, err, r, N, rpc);
+  } else {
+    NPDE_LAUNCH(k_fd_error<false>, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, v, f, err, r, N, rpc);
+  }
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
+             cudaStream_t st) {
+  ReduceWs r;
+  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
+  if (rc) return rc;
+  int chunks = reduce_chunks(N);
+  long n = (long)N * N;
+  int cpc = (int)((n + chunks - 1) / chunks);
+  chunks = (int)((n + cpc - 1) / cpc);
+  NPDE_LAUNCH(k_l2_error, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, gt, err, r, N, cpc);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int subsample_strided(const float *x, size_t x_bstride, float *y, int B, int N, float scale, cudaStream_t st) {
+  int M = (N - 1) / 2 + 1;
+  NPDE_LAUNCH(k_subsample, grid2d(M, M, B), dim3(TX, TY), 0, st, x, x_bstride, y, N, M, scale);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t st) {
+  return subsample_strided(x, (size_t)N * N, y, B, N, scale, st);
+}
+
+int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st) {
+  NPDE_LAUNCH(k_copy_field, grid2d(N, N, B), dim3(TX, TY), 0, st, src.p, src.pitch, src.bstride, dst.p, dst.pitch,
+              dst.bstride, N);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int restrict_(const float *x, const float *bc_sub, int bc_kind, float *y, int B, int N, cudaStream_t st) {
+  int M = (N - 1) / 2 + 1;
+  BcView v{bc_sub, bc_kind};
+  NPDE_LAUNCH(k_restrict, grid2d(M, M, B), dim3(TX, TY), 0, st, x, v, y, N, M);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int prolong(const float *x, const float *bc, int bc_kind, float *y, int B, int M, cudaStream_t st) {
+  int N = 2 * M - 1;
+  BcView v{bc, bc_kind};
+  int nested = ((long)M * M > 1024) ? 1 : 0;  // ATen CPU bilinear order switch, see DESIGN.md
+  NPDE_LAUNCH(k_prolong, grid2d(N, N, B), dim3(TX, TY), 0, st, x, v, y, M, N, nested);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+}  // namespace npde

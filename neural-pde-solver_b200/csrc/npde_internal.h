@@ -1,0 +1,80 @@
+// npde_internal.h -- host-side entry points shared between the translation units
+// of libnpde_b200.  All functions enqueue on `st` and return NPDE_OK / error.
+#pragma once
+#include "npde_common.cuh"
+
+namespace npde {
+
+int check_common(const void *a, const void *b, int B, int N);
+int check_bc(const float *bc, int bc_kind);
+
+// npde_grid_ops.cu
+int reduce_chunks(int N);
+size_t reduce_ws_bytes(int B, int N);
+int set_boundary(float *x, const float *bc, int bc_kind, int B, int N, cudaStream_t st);
+int pad_boundary(const float *xin, const float *bc, int bc_kind, float *y, int B, int N, cudaStream_t st);
+int fd_step_simple(const float *x, const float *bc, int bc_kind, const float *f, float *y, int B, int N,
+                   cudaStream_t st);
+int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int aggregate, float *err, int B,
+             int N, void *ws, size_t ws_bytes, cudaStream_t st);
+int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
+             cudaStream_t st);
+int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t st);
+// same, input images `x_bstride` floats apart (the mask plane of a (B,2,N,N) bc tensor)
+int subsample_strided(const float *x, size_t x_bstride, float *y, int B, int N, float scale, cudaStream_t st);
+int restrict_(const float *x, const float *bc_sub, int bc_kind, float *y, int B, int N, cudaStream_t st);
+int prolong(const float *x, const float *bc, int bc_kind, float *y, int B, int M, cudaStream_t st);
+
+// npde_conv_ops.cu -- layer-by-layer building blocks (UNet, deep conv stacks, backward)
+// mask: level mask (B, S+2, S+2) with batch stride mask_bstride floats, or NULL.
+int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const float *mask,
+            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st);
+int conv3x3_transpose(const float *g, int Hg, const float *w9, int stride, int pad, float *out, int Ho, int B,
+                      cudaStream_t st);
+int mul_fg(float *r, const float *mask, size_t mask_bstride, int S, int B, cudaStream_t st);
+int add_inplace(float *a, const float *b, size_t n, cudaStream_t st);
+int psi_residual(const float *x, const float *f, const float *mask, size_t mask_bstride, float *y_int,
+                 float *r0, int B, int N, cudaStream_t st);
+int combine(const float *y_int, const float *h, const float *bc, int bc_kind, int act, float *out, int B, int N,
+            cudaStream_t st);
+int pad_up_crop(const float *r, int s, const float *mask_out, size_t mask_bstride, float *out, int B,
+                cudaStream_t st);
+int pad_up_crop_transpose(const float *g, int s, float *out, int B, cudaStream_t st);
+int bwd_gz(const float *gout, const float *y_int, const float *rL, const float *mask, size_t mask_bstride,
+           int act, float *gz, int B, int N, cudaStream_t st);
+// gw9 (9 floats) <- sum_{b,i,j} g[b,i,j] * r[b, i*stride + a - pad, j*stride + c - pad]
+int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int pad, float *gw9, int B,
+                void *ws, size_t ws_bytes, cudaStream_t st);
+size_t weight_grad_ws_bytes(int B, int Hg);
+int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream_t st);
+
+// npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)
+constexpr int STREAM_THREADS = 128;  // 4 independent warp strips per CTA
+
+// A (B,N,N) field with an arbitrary row pitch / batch stride (floats): the
+// reference layout is {p, N, N*N}; internal ping-pong buffers use a padded pitch.
+struct FieldView {
+  const float *p;
+  int pitch;
+  long bstride;
+};
+struct FieldViewMut {
+  float *p;
+  int pitch;
+  long bstride;
+};
+inline FieldView ref_view(const float *p, int N) { return FieldView{p, N, (long)N * N}; }
+inline FieldViewMut ref_view_mut(float *p, int N) { return FieldViewMut{p, N, (long)N * N}; }
+int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st);  // npde_grid_ops.cu
+inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch, v.bstride}; }
+
+// square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
+bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
+int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, const float *w_host,
+                int n_layers, int act, int B, int N, cudaStream_t st);
+// depth in {1,2,4,8} Jacobi steps per launch (1 when f != NULL); square domain only
+int jacobi_stream_max_depth(const float *f);
+int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, int depth, int B,
+                  int N, cudaStream_t st);
+
+}  // namespace npde

@@ -1,0 +1,324 @@
+"""Tensor-level wrappers over the C ABI (include/npde.h).
+
+Every function takes torch tensors that live on a CUDA device, hands raw device
+pointers plus the current CUDA stream to libnpde_b200.so, and returns fresh
+output tensors.  Nothing here computes: torch is used for memory, streams and
+autograd bookkeeping only.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ACT, AGG, BC_MASK, BC_SQUARE, IterateDesc, check, lib
+
+_workspaces = {}
+
+
+def _require(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda and not _lib.is_emulated():
+        raise RuntimeError("%s must be a CUDA tensor: npde-b200 has no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+    return t.detach().contiguous()
+
+
+def _opt(t, name):
+    return None if t is None else _require(t, name)
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    if t.is_cuda:
+        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
+def _workspace(nbytes, like):
+    """Scratch for one call: cached per (device, stream), grown on demand, 256-byte aligned."""
+    if nbytes == 0:
+        return None, 0
+    if like.is_cuda:
+        key = (like.device, torch.cuda.current_stream(like.device).cuda_stream)
+    else:
+        key = (like.device, 0)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes + 256:
+        buf = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=like.device)
+        _workspaces[key] = buf
+    base = buf.data_ptr()
+    off = (-base) % 256
+    return ctypes.c_void_p(base + off), buf.numel() - off
+
+
+def bc_kind(x, bc):
+    """utils/heat_utils.py:29-42 is_bc_mask, as the C enum.  Raises like the reference on a bad shape."""
+    B, N = x.shape[0], x.shape[-1]
+    if tuple(bc.shape) == (B, 2, N, N):
+        return BC_MASK
+    if tuple(bc.shape) == (B, 4):
+        return BC_SQUARE
+    print(x.shape, bc.shape)
+    raise Exception("bc must be (B,4) or (B,2,N,N)")
+
+
+def _field(x, name="x"):
+    x = _require(x, name)
+    if x.dim() != 3 or x.shape[1] != x.shape[2]:
+        raise ValueError("%s must be (B, N, N), got %s" % (name, tuple(x.shape)))
+    return x
+
+
+def _act(act):
+    if act not in ACT:
+        raise NotImplementedError("activation %r" % (act,))  # models/iterators/iterator.py:25-26
+    return ACT[act]
+
+
+# ----------------------------------------------------------------- grid ops --
+def set_boundary_(x, bc):
+    """G in place (utils/heat_utils.py:44-59)."""
+    xc = _field(x)
+    if xc.data_ptr() != x.data_ptr():
+        raise ValueError("set_boundary_ needs a contiguous tensor")
+    bc = _require(bc, "bc")
+    B, N, _ = xc.shape
+    check(lib().npde_set_boundary(_ptr(xc), _ptr(bc), bc_kind(xc, bc), B, N, _stream(xc)), "npde_set_boundary")
+    return x
+
+
+def pad_boundary(xin, bc):
+    xin = _field(xin, "xin")
+    bc = _require(bc, "bc")
+    B, S, _ = xin.shape
+    N = S + 2
+    y = torch.empty((B, N, N), dtype=torch.float32, device=xin.device)
+    check(lib().npde_pad_boundary(_ptr(xin), _ptr(bc), bc_kind(y, bc), _ptr(y), B, N, _stream(xin)),
+          "npde_pad_boundary")
+    return y
+
+
+def fd_step(x, bc, f=None):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    B, N, _ = x.shape
+    y = torch.empty_like(x)
+    check(lib().npde_fd_step(_ptr(x), _ptr(bc), bc_kind(x, bc), _ptr(f), _ptr(y), B, N, _stream(x)), "npde_fd_step")
+    return y
+
+
+def fd_error(x, bc, f=None, aggregate="max"):
+    if aggregate not in AGG:
+        raise NotImplementedError(aggregate)  # heat_utils.py:130-131
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    B, N, _ = x.shape
+    err = torch.empty((B,), dtype=torch.float32, device=x.device)
+    kind = bc_kind(x, bc)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_REDUCE, B, N, kind, 0, 0, 0, 0), x)
+    check(lib().npde_fd_error(_ptr(x), _ptr(bc), kind, _ptr(f), AGG[aggregate], _ptr(err), B, N, ws, wsb,
+                              _stream(x)), "npde_fd_error")
+    return err
+
+
+def l2_error(x, gt):
+    if x.dim() != 3:
+        raise NotImplementedError  # heat_utils.py:140-141
+    x = _field(x)
+    gt = _field(gt, "gt")
+    B, N, _ = x.shape
+    err = torch.empty((B,), dtype=torch.float32, device=x.device)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_REDUCE, B, N, 0, 0, 0, 0, 0), x)
+    check(lib().npde_l2_error(_ptr(x), _ptr(gt), _ptr(err), B, N, ws, wsb, _stream(x)), "npde_l2_error")
+    return err
+
+
+def subsample(x):
+    x = _field(x)
+    B, N, _ = x.shape
+    M = (N - 1) // 2 + 1
+    y = torch.empty((B, M, M), dtype=torch.float32, device=x.device)
+    check(lib().npde_subsample(_ptr(x), _ptr(y), B, N, _stream(x)), "npde_subsample")
+    return y
+
+
+def restriction(x, bc_sub):
+    x = _field(x)
+    bc_sub = _require(bc_sub, "bc")
+    B, N, _ = x.shape
+    M = (N - 1) // 2 + 1
+    y = torch.empty((B, M, M), dtype=torch.float32, device=x.device)
+    check(lib().npde_restrict(_ptr(x), _ptr(bc_sub), bc_kind(y, bc_sub), _ptr(y), B, N, _stream(x)), "npde_restrict")
+    return y
+
+
+def interpolation(x, bc):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    B, M, _ = x.shape
+    N = 2 * M - 1
+    y = torch.empty((B, N, N), dtype=torch.float32, device=x.device)
+    check(lib().npde_prolong(_ptr(x), _ptr(bc), bc_kind(y, bc), _ptr(y), B, M, _stream(x)), "npde_prolong")
+    return y
+
+
+# ------------------------------------------------------------------- Conv --
+def _weights(w, name="w"):
+    w = _require(w, name)
+    return w.reshape(-1, 3, 3)
+
+
+def conv_H(r, bc, w, is_bc_mask):
+    """ConvIterator.H on r (B,N-2,N-2) (conv_iterator.py:19-31)."""
+    r = _field(r, "r")
+    w = _weights(w)
+    B, S, _ = r.shape
+    N = S + 2
+    kind = BC_MASK if is_bc_mask else BC_SQUARE
+    bcp = _require(bc, "bc") if is_bc_mask else None
+    out = torch.empty_like(r)
+    L = int(w.shape[0])
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_FWD, B, N, kind, L, 0, 0, 0), r)
+    check(lib().npde_conv_H(_ptr(r), _ptr(bcp), kind, _ptr(w), L, _ptr(out), B, N, ws, wsb, _stream(r)),
+          "npde_conv_H")
+    return out
+
+
+def conv_step(x, bc, f, w, act, w_host=None):
+    """ConvIterator.forward without autograd.  w: (L,3,3) device; w_host: numpy copy (enables the fused kernel)."""
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    w = _weights(w)
+    B, N, _ = x.shape
+    L = int(w.shape[0])
+    kind = bc_kind(x, bc)
+    y = torch.empty_like(x)
+    wh = None
+    if w_host is not None:
+        w_host = np.ascontiguousarray(w_host, dtype=np.float32).reshape(-1)
+        assert w_host.size == 9 * L
+        wh = w_host.ctypes.data_as(ctypes.c_void_p)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_FWD, B, N, kind, L, 0, 0, 0), x)
+    check(lib().npde_conv_step_fwd(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(w), wh, L, _act(act), _ptr(y), B, N, ws,
+                                   wsb, _stream(x)), "npde_conv_step_fwd")
+    return y
+
+
+def conv_step_bwd(x, bc, f, w, act, gout, need_gx):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    w = _weights(w)
+    gout = _field(gout, "gout")
+    B, N, _ = x.shape
+    L = int(w.shape[0])
+    kind = bc_kind(x, bc)
+    gw = torch.empty((L, 3, 3), dtype=torch.float32, device=x.device)
+    gx = torch.empty_like(x) if need_gx else None
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_BWD, B, N, kind, L, 0, 0, 0), x)
+    check(lib().npde_conv_step_bwd(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(w), L, _act(act), _ptr(gout), _ptr(gw),
+                                   _ptr(gx), B, N, ws, wsb, _stream(x)), "npde_conv_step_bwd")
+    return gw, gx
+
+
+class ConvStepFn(torch.autograd.Function):
+    """Differentiable ConvIterator.forward: the reference gets this from autograd over
+    F.conv2d (models/heat_model.py:52-53,71-72); here both directions are C-ABI calls."""
+
+    @staticmethod
+    def forward(ctx, x, bc, f, w, act, w_host):
+        ctx.save_for_backward(x, bc, f if f is not None else x.new_empty(0), w)
+        ctx.has_f = f is not None
+        ctx.act = act
+        return conv_step(x, bc, f, w, act, w_host)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, bc, f, w = ctx.saved_tensors
+        gw, gx = conv_step_bwd(x, bc, f if ctx.has_f else None, w, ctx.act, gout, ctx.needs_input_grad[0])
+        return gx, None, None, gw.reshape(w.shape), None, None
+
+
+# -------------------------------------------------------- Multigrid / UNet --
+def mg_step(x, bc, f, n_layers, pre, post):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    B, N, _ = x.shape
+    kind = bc_kind(x, bc)
+    y = torch.empty_like(x)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_MG, B, N, kind, n_layers, pre, post, 0), x)
+    check(lib().npde_mg_step(_ptr(x), _ptr(bc), kind, _ptr(f), n_layers, pre, post, _ptr(y), B, N, ws, wsb,
+                             _stream(x)), "npde_mg_step")
+    return y
+
+
+def unet_H(r, bc, w_first, w_pool, w_second, n_layers, pre, post, is_bc_mask):
+    r = _field(r, "r")
+    B, S, _ = r.shape
+    N = S + 2
+    kind = BC_MASK if is_bc_mask else BC_SQUARE
+    bcp = _require(bc, "bc") if is_bc_mask else None
+    wf, wp, wsn = _opt(w_first, "w_first"), _opt(w_pool, "w_pool"), _opt(w_second, "w_second")
+    out = torch.empty_like(r)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_UNET_FWD, B, N, kind, n_layers, pre, post, 0), r)
+    check(lib().npde_unet_H(_ptr(r), _ptr(bcp), kind, _ptr(wf), _ptr(wp), _ptr(wsn), n_layers, pre, post, _ptr(out),
+                            B, N, ws, wsb, _stream(r)), "npde_unet_H")
+    return out
+
+
+def unet_step(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    wf, wp, wsn = _opt(w_first, "w_first"), _opt(w_pool, "w_pool"), _opt(w_second, "w_second")
+    B, N, _ = x.shape
+    kind = bc_kind(x, bc)
+    y = torch.empty_like(x)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_UNET_FWD, B, N, kind, n_layers, pre, post, 0), x)
+    check(lib().npde_unet_step_fwd(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wf), _ptr(wp), _ptr(wsn), n_layers, pre,
+                                   post, _act(act), _ptr(y), B, N, ws, wsb, _stream(x)), "npde_unet_step_fwd")
+    return y
+
+
+# -------------------------------------------------------------- k-step loop --
+def iterate(iterator, x, bc, f, k, *, w=None, w_host=None, n_layers=0, pre=0, post=0, act="none", gt=None,
+            want_l2=False, want_fd=False, temporal_depth=0, out=None):
+    """k applications of one iterator in a single C call (npde_iterate).
+
+    iterator: _lib.IT_*.  Returns (x_k, err_l2 or None, err_fd or None) with
+    err_l2 (k,B) = l2_error(x_{t+1}, gt) and err_fd (k+1,B) = fd_error(x_t,'max').
+    """
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    gt = _opt(gt, "gt")
+    w = None if w is None else _require(w, "w").reshape(-1)
+    B, N, _ = x.shape
+    kind = bc_kind(x, bc)
+    y = torch.empty_like(x) if out is None else out
+    e2 = torch.empty((k, B), dtype=torch.float32, device=x.device) if want_l2 else None
+    efd = torch.empty((k + 1, B), dtype=torch.float32, device=x.device) if want_fd else None
+    if want_l2 and gt is None:
+        raise ValueError("want_l2 needs gt")
+    wh = None
+    if w_host is not None:
+        w_host = np.ascontiguousarray(w_host, dtype=np.float32).reshape(-1)
+        wh = w_host.ctypes.data_as(ctypes.c_void_p)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_ITERATE + iterator, B, N, kind, n_layers, pre, post, k), x)
+    d = IterateDesc(iterator=iterator, B=B, N=N, bc_kind=kind, n_layers=n_layers, pre=pre, post=post, act=_act(act),
+                    k=k, temporal_depth=temporal_depth, x_in=x.data_ptr(), x_out=y.data_ptr(), bc=bc.data_ptr(),
+                    f=None if f is None else f.data_ptr(), w=None if w is None else w.data_ptr(), w_host=wh,
+                    gt=None if gt is None else gt.data_ptr(), err_l2=None if e2 is None else e2.data_ptr(),
+                    err_fd=None if efd is None else efd.data_ptr(), workspace=ws, workspace_bytes=wsb)
+    check(lib().npde_iterate(ctypes.byref(d), _stream(x)), "npde_iterate")
+    return y, e2, efd

@@ -1,0 +1,225 @@
+"""Drop-in iterators: same classes, constructor arguments, attributes and
+state-dict keys as models/iterators/*.py of the reference, with ``forward``
+running as fused CUDA kernels through the C ABI instead of an F.conv2d chain.
+
+Extension over the reference contract: every iterator also has
+``iterate(x, bc, f, k, gt=None, want_l2=False, want_fd=False)`` -- k applications
+in one library call -- which the loop drivers (heat_utils.calculate_errors,
+HeatModel.train/evaluate, runtime) use instead of Python loops.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as F_
+from . import heat_utils as utils
+from ._lib import IT_CONV, IT_JACOBI, IT_MULTIGRID, IT_UNET
+
+
+class Iterator(nn.Module):
+    """models/iterators/iterator.py:6-44."""
+
+    def __init__(self, act=None):
+        super(Iterator, self).__init__()
+        self.act = act
+        self.n_operations = None
+        self.is_bc_mask = False
+
+    def activation(self, x):
+        if self.act == 'sigmoid':
+            x = torch.sigmoid(x)
+        elif self.act == 'clamp':
+            x = x.clamp(0, 1)
+        elif self.act == 'none':
+            pass
+        else:
+            raise NotImplementedError
+        return x
+
+    def _check_act(self):
+        if self.act not in ('sigmoid', 'clamp', 'none'):
+            raise NotImplementedError  # iterator.py:25-26
+
+    def iter_step(self, x, bc, f):
+        return self.forward(x, bc, f)
+
+    def forward(self, x, bc, f):
+        raise NotImplementedError
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        raise NotImplementedError
+
+    def name(self):
+        raise NotImplementedError
+
+
+class JacobiIterator(Iterator):
+    """models/iterators/jacobi_iterator.py:7-20."""
+
+    def __init__(self):
+        super(JacobiIterator, self).__init__()
+        self.n_operations = 1
+
+    def forward(self, x, bc, f):
+        return utils.fd_step(x, bc, f)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None, temporal_depth=0):
+        return F_.iterate(IT_JACOBI, x, bc, f, k, gt=gt, want_l2=want_l2, want_fd=want_fd,
+                          temporal_depth=temporal_depth, out=out)
+
+    def name(self):
+        return 'Jacobi'
+
+
+class MultigridIterator(Iterator):
+    """models/iterators/jacobi_iterator.py:23-78: one V-cycle per forward."""
+
+    def __init__(self, n_layers, pre_smoothing, post_smoothing):
+        super(MultigridIterator, self).__init__()
+        self.n_layers = n_layers
+        self.pre_smoothing = pre_smoothing
+        self.post_smoothing = post_smoothing
+        self.n_operations = (pre_smoothing + post_smoothing + 2) * 4 / 3
+
+    def forward(self, x, bc, f):
+        return F_.mg_step(x, bc, f, self.n_layers, self.pre_smoothing, self.post_smoothing)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        return F_.iterate(IT_MULTIGRID, x, bc, f, k, n_layers=self.n_layers, pre=self.pre_smoothing,
+                          post=self.post_smoothing, gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+
+    def name(self):
+        return 'Multigrid'
+
+
+class _WeightCache(object):
+    """Device (n,3,3) stack + host numpy copy of a list of (1,1,3,3) conv weights.  The host
+    copy lets the fused kernel take the weights as launch parameters; it is refreshed only
+    when a parameter's version counter moves (one tiny D2H per optimizer step)."""
+
+    def __init__(self):
+        self.key = None
+        self.dev = None
+        self.host = None
+
+    def get(self, params):
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key != self.key:
+            with torch.no_grad():
+                if len(params):
+                    self.dev = torch.stack([p.detach().reshape(3, 3) for p in params]).contiguous()
+                else:
+                    self.dev = torch.empty((0, 3, 3), device='cpu')
+                self.host = self.dev.cpu().numpy().copy()
+            self.key = key
+        return self.dev, self.host
+
+
+class ConvIterator(Iterator):
+    """models/iterators/conv_iterator.py:8-54.  State-dict keys: layers.{i}.weight (1,1,3,3)."""
+
+    def __init__(self, act, n_layers=1):
+        super(ConvIterator, self).__init__(act)
+        layers = []
+        for i in range(n_layers):
+            layers += [nn.Conv2d(1, 1, 3, stride=1, padding=1, bias=False)]
+        self.layers = nn.ModuleList(layers)
+        self.n_layers = n_layers
+        self.n_operations = 1 + n_layers
+        self._cache = _WeightCache()
+
+    def _params(self):
+        return [l.weight for l in self.layers]
+
+    def _consistent(self, x, bc):
+        if utils.is_bc_mask(x, bc) != bool(self.is_bc_mask):
+            raise NotImplementedError(
+                "is_bc_mask=%r does not match the bc tensor shape %s" % (self.is_bc_mask, tuple(bc.shape)))
+
+    def H(self, r, bc):
+        """r: (B,1,N-2,N-2) -> H(r), same shape (conv_iterator.py:19-31)."""
+        w, _ = self._cache.get(self._params())
+        return F_.conv_H(r.squeeze(1), bc, w, self.is_bc_mask).unsqueeze(1)
+
+    def forward(self, x, bc, f):
+        self._check_act()
+        self._consistent(x, bc)
+        params = self._params()
+        w_dev, w_host = self._cache.get(params)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            w = torch.stack([p.reshape(3, 3) for p in params]) if params else w_dev
+            return F_.ConvStepFn.apply(x, bc, f, w, self.act, w_host)
+        return F_.conv_step(x, bc, f, w_dev, self.act, w_host)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        self._check_act()
+        self._consistent(x, bc)
+        w_dev, w_host = self._cache.get(self._params())
+        return F_.iterate(IT_CONV, x, bc, f, k, w=w_dev, w_host=w_host, n_layers=self.n_layers, act=self.act,
+                          gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+
+    def name(self):
+        return 'Conv{}'.format(self.n_layers)
+
+
+class UNetIterator(Iterator):
+    """models/iterators/unet_iterator.py:8-108.  State-dict keys:
+    first_layers.{i}.weight, pooling_layers.{i}.weight, second_layers.{i}.weight."""
+
+    def __init__(self, act, n_layers, pre_smoothing, post_smoothing):
+        super(UNetIterator, self).__init__(act)
+        self.n_layers = n_layers
+        self.pre_smoothing = pre_smoothing
+        self.post_smoothing = post_smoothing
+        self.n_operations = (pre_smoothing + post_smoothing + 2) * 4 / 3
+        first_layers = []
+        for i in range(n_layers):
+            for j in range(pre_smoothing):
+                first_layers.append(nn.Conv2d(1, 1, 3, stride=1, padding=1, bias=False))
+        self.first_layers = nn.ModuleList(first_layers)
+        pooling_layers = []
+        for i in range(n_layers - 1):
+            pooling_layers.append(nn.Conv2d(1, 1, 3, stride=2, padding=0, bias=False))
+        self.pooling_layers = nn.ModuleList(pooling_layers)
+        second_layers = []
+        for i in range(n_layers):
+            for j in range(post_smoothing):
+                second_layers.append(nn.Conv2d(1, 1, 3, stride=1, padding=1, bias=False))
+        self.second_layers = nn.ModuleList(second_layers)
+        self._cache = _WeightCache()
+
+    def _params(self):
+        return ([l.weight for l in self.first_layers] + [l.weight for l in self.pooling_layers] +
+                [l.weight for l in self.second_layers])
+
+    def _split(self, w):
+        nf = self.n_layers * self.pre_smoothing
+        npool = self.n_layers - 1
+        return w[:nf], w[nf:nf + npool], w[nf + npool:]
+
+    def H(self, r, bc):
+        w, _ = self._cache.get(self._params())
+        wf, wp, ws = self._split(w)
+        return F_.unet_H(r.squeeze(1), bc, wf, wp, ws, self.n_layers, self.pre_smoothing, self.post_smoothing,
+                         self.is_bc_mask).unsqueeze(1)
+
+    def forward(self, x, bc, f):
+        self._check_act()
+        if utils.is_bc_mask(x, bc) != bool(self.is_bc_mask):
+            raise NotImplementedError("is_bc_mask does not match the bc tensor shape")
+        params = self._params()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
+            raise NotImplementedError("UNetIterator backward is not built yet (npde_unet_step_bwd); "
+                                      "call under torch.no_grad()")
+        w, _ = self._cache.get(params)
+        wf, wp, ws = self._split(w)
+        return F_.unet_step(x, bc, f, wf, wp, ws, self.n_layers, self.pre_smoothing, self.post_smoothing, self.act)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        self._check_act()
+        w, _ = self._cache.get(self._params())
+        return F_.iterate(IT_UNET, x, bc, f, k, w=w, n_layers=self.n_layers, pre=self.pre_smoothing,
+                          post=self.post_smoothing, act=self.act, gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+
+    def name(self):
+        return 'UNet{}'.format(self.n_layers)

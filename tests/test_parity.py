@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the Python drop-in API and the C ABI) with
+the reference's golden vectors and with the CPU oracle.
+
+Every test runs on two backends:
+  * ``cuda`` (marked gpu): the product -- libnpde_b200.so on a B200;
+  * ``emu``  (CPU): the SAME .cu sources compiled for the host against the SIMT
+    emulator of tests/emu (test infrastructure), so kernel index logic and the
+    host-side schedules are exercised in the CPU suite as well.
+
+Bar: bit-exact against the golden vectors wherever the oracle is (see
+tests/test_oracle_golden.py); otherwise <= 1e-5 relative (BASELINE.json
+north_star), stated next to each assert.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_bitwise, golden_names, load_golden, rel_err
+
+ACTS = {0: "none", 1: "clamp", 2: "sigmoid"}
+BACKENDS = [pytest.param("emu", id="emu"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)]
+
+
+class Backend(object):
+    def __init__(self, kind):
+        self.kind = kind
+        self.npde = importlib.import_module("neural-pde-solver_b200")
+        if kind == "emu":
+            build = importlib.import_module("neural-pde-solver_b200.build")
+            self.npde._lib._use_emulator(build.build_emulator())
+            self.device = torch.device("cpu")
+        else:
+            assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+            self.npde._lib._use_cuda_library()
+            self.npde._lib.lib()  # raises if libnpde_b200.so is missing: no fallback
+            self.device = torch.device("cuda:0")
+        self.F = self.npde.functional
+        self.utils = self.npde.utils
+
+    def t(self, a):
+        return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+
+    @staticmethod
+    def n(t):
+        return t.detach().cpu().numpy()
+
+
+@pytest.fixture(params=BACKENDS)
+def be(request):
+    b = Backend(request.param)
+    yield b
+    b.npde._lib._use_cuda_library()
+
+
+# ------------------------------------------------------------ grid operators --
+@pytest.mark.parametrize("name", golden_names("ops_"))
+def test_grid_operators(be, name):
+    g = load_golden(name)
+    u = be.utils
+    x, bc, gt = be.t(g["x"]), be.t(g["bc"]), be.t(g["gt"])
+    assert_bitwise(be.n(u.fd_step(x, bc, None)), g["fd_step"], "fd_step")
+    assert_bitwise(be.n(u.fd_error(x, bc, None, "max")), g["fd_error_max"], "fd_error max")
+    assert rel_err(be.n(u.fd_error(x, bc, None, "mean")), g["fd_error_mean"]) < 1e-6
+    f = be.t(g.get("f"))
+    if f is not None:
+        assert_bitwise(be.n(u.fd_step(x, bc, f)), g["fd_step_f"], "fd_step f")
+        assert_bitwise(be.n(u.fd_error(x, bc, f, "max")), g["fd_error_max_f"], "fd_error f")
+        assert rel_err(be.n(u.fd_error(x, bc, f, "mean")), g["fd_error_mean_f"]) < 1e-6
+    assert rel_err(be.n(u.l2_error(x, gt)), g["l2_error"]) < 1e-6
+    assert_bitwise(be.n(u.set_boundary(gt.clone(), bc)), g["set_boundary"], "set_boundary")
+    assert_bitwise(be.n(u.pad_boundary(gt[:, 1:-1, 1:-1], bc)), g["pad_boundary"], "pad_boundary")
+    assert_bitwise(be.n(u.subsample(x)), g["subsample"], "subsample")
+    assert_bitwise(be.n(u.restriction(x, be.t(g["bc_sub"]))), g["restriction"], "restriction")
+    assert_bitwise(be.n(u.interpolation(be.t(g["xs"]), bc)), g["interpolation"], "interpolation")
+    # x is not modified by any of the calls above
+    assert_bitwise(be.n(x), g["x"], "inputs untouched")
+
+
+@pytest.mark.parametrize("name", golden_names("ops_"))
+@pytest.mark.parametrize("depth", [0, 1, 2, 4])
+def test_jacobi_chain(be, name, depth):
+    """25 chained Jacobi steps (temporally blocked on the square path) + fd_error rows."""
+    g = load_golden(name)
+    x, bc, f = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f"))
+    it = be.npde.JacobiIterator()
+    y, _, _ = it.iterate(x, bc, f, 25, temporal_depth=depth)
+    assert_bitwise(be.n(y), g["jacobi25"], "25 fused Jacobi steps, depth %d" % depth)
+    if depth == 0:
+        y2, _, efd = it.iterate(x, bc, f, 25, want_fd=True)
+        assert_bitwise(be.n(y2), g["jacobi25"], "25 Jacobi steps with norms")
+        assert_bitwise(be.n(efd[-1]), g["jacobi25_fd_error"], "fd_error row 25")
+        assert_bitwise(be.n(efd[0]), g["fd_error_max_f" if f is not None else "fd_error_max"], "fd_error row 0")
+        z = x
+        for _ in range(25):
+            z = it(z, bc, f)
+        assert_bitwise(be.n(z), g["jacobi25"], "25 single Jacobi steps")
+
+
+# ---------------------------------------------------------------- ConvIterator --
+def make_conv(be, g):
+    L, act, is_mask = (int(v) for v in g["meta"])
+    it = be.npde.ConvIterator(ACTS[act], L)
+    it.is_bc_mask = bool(is_mask)
+    with torch.no_grad():
+        for l, w in zip(it.layers, g["w"]):
+            l.weight.copy_(torch.from_numpy(w).view(1, 1, 3, 3))
+    return it.to(be.device)
+
+
+@pytest.mark.parametrize("name", golden_names("conv_"))
+def test_conv_iterator(be, name):
+    g = load_golden(name)
+    it = make_conv(be, g)
+    x, bc, f = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f"))
+    with torch.no_grad():
+        y1 = it(x, bc, f)
+        h = it.H(be.t(g["r"]).unsqueeze(1), bc)[:, 0]
+        y10, _, _ = it.iterate(x, bc, f, 10)
+        z = x
+        for _ in range(10):
+            z = it.iter_step(z, bc, f)
+    assert_bitwise(be.n(z), be.n(y10), "iterate(10) == 10 x forward")
+    if g["x"].shape[0] >= 2 and it.act != "sigmoid":
+        assert_bitwise(be.n(h), g["H"], "H")
+        assert_bitwise(be.n(y1), g["step1"], "conv step")
+        assert_bitwise(be.n(y10), g["step10"], "10 conv steps")
+    else:  # B == 1 changes ATen's conv order; sigmoid uses a different exp: north-star tolerance
+        assert rel_err(be.n(h), g["H"]) <= 1e-5
+        assert rel_err(be.n(y1), g["step1"]) <= 1e-5
+        assert rel_err(be.n(y10), g["step10"]) <= 1e-5
+
+
+def test_conv_zero_weights_is_jacobi(be):
+    """ConvIterator with H = 0 (act none) equals JacobiIterator bitwise."""
+    g = load_golden("ops_square33")
+    x, bc, f = be.t(g["x"]), be.t(g["bc"]), be.t(g["f"])
+    it = be.npde.ConvIterator("none", 3).to(be.device)
+    with torch.no_grad():
+        for l in it.layers:
+            l.weight.zero_()
+        y = it(x, bc, f)
+    assert_bitwise(be.n(y), g["fd_step_f"], "zero-H conv == Jacobi")
+
+
+def test_constant_field_is_fixed_point(be):
+    """a constant field with equal bc is an exact fixed point of every iterator."""
+    B, N = 2, 33
+    x = torch.full((B, N, N), 0.375, device=be.device)
+    bc = torch.full((B, 4), 0.375, device=be.device)
+    its = [be.npde.JacobiIterator(), be.npde.ConvIterator("clamp", 3).to(be.device),
+           be.npde.MultigridIterator(3, 2, 2), be.npde.UNetIterator("clamp", 3, 1, 1).to(be.device)]
+    with torch.no_grad():
+        for it in its:
+            assert_bitwise(be.n(it(x, bc, None)), be.n(x), it.name())
+
+
+# ------------------------------------------------------------ Multigrid / UNet --
+@pytest.mark.parametrize("name", golden_names("mg_"))
+def test_multigrid_iterator(be, name):
+    g = load_golden(name)
+    nl, pre, post, is_mask = (int(v) for v in g["meta"])
+    it = be.npde.MultigridIterator(nl, pre, post)
+    it.is_bc_mask = bool(is_mask)
+    x, bc, f = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f"))
+    y1 = it(x, bc, f)
+    assert_bitwise(be.n(y1), g["step1"], "V-cycle")
+    y3, _, _ = it.iterate(x, bc, f, 3)
+    assert_bitwise(be.n(y3), g["step3"], "3 V-cycles")
+
+
+def make_unet(be, g):
+    nl, pre, post, act, is_mask = (int(v) for v in g["meta"])
+    it = be.npde.UNetIterator(ACTS[act], nl, pre, post)
+    it.is_bc_mask = bool(is_mask)
+    with torch.no_grad():
+        for ml, ws in ((it.first_layers, g["w_first"]), (it.pooling_layers, g["w_pool"]),
+                       (it.second_layers, g["w_second"])):
+            for l, w in zip(ml, ws):
+                l.weight.copy_(torch.from_numpy(w).view(1, 1, 3, 3))
+    return it.to(be.device)
+
+
+@pytest.mark.parametrize("name", golden_names("unet_"))
+def test_unet_iterator(be, name):
+    g = load_golden(name)
+    it = make_unet(be, g)
+    x, bc, f = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f"))
+    with torch.no_grad():
+        h = it.H(be.t(g["r"]).unsqueeze(1), bc)[:, 0]
+        y1 = it(x, bc, f)
+        y5, _, _ = it.iterate(x, bc, f, 5)
+    assert_bitwise(be.n(h), g["H"], "unet H")
+    assert_bitwise(be.n(y1), g["step1"], "unet step")
+    assert_bitwise(be.n(y5), g["step5"], "5 unet steps")
+
+
+# ------------------------------------------------------------------- backward --
+@pytest.mark.parametrize("name", golden_names("bwd_conv_"))
+def test_conv_backward(be, name):
+    """One differentiable step + MSE, gradients vs the reference's autograd
+    (models/heat_model.py:52-53,71-72).  Reduction order differs: tolerance 2e-5 of the largest entry."""
+    g = load_golden(name)
+    it = make_conv(be, g)
+    x, bc, f, gt = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f")), be.t(g["gt"])
+    xg = x.clone().requires_grad_(True)
+    y = it(xg, bc, f)
+    loss = torch.nn.MSELoss()(y, gt)
+    loss.backward()
+    assert rel_err(be.n(y), g["y"]) <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    gw = np.stack([be.n(l.weight.grad)[0, 0] for l in it.layers])
+    assert rel_err(gw, g["gw"]) <= 2e-5, (gw, g["gw"])
+    assert rel_err(be.n(xg.grad), g["gx"]) <= 2e-5
+
+
+# ------------------------------------------------------------------- drivers --
+def make_opt(**kw):
+    import argparse
+    d = dict(iterator="conv", activation="clamp", conv_n_layers=3, mg_n_layers=3, mg_pre_smoothing=2,
+             mg_post_smoothing=2, cg_n_iters=4, geometry="square", is_train=True, optimizer="adam", lr_init=1e-3,
+             max_iter_steps=6, max_iter_steps_from_gt=4, lambda_gt=0.0)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_get_iterator_contract(be):
+    rows = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "get_iterator_contract.npy"),
+                   allow_pickle=True)
+    for itname, geom, name, cmp_name, ratio, is_train, is_mask, n_ops in rows:
+        it, cmp_, r, tr = be.npde.get_iterator(make_opt(iterator=itname, geometry=geom))
+        assert it.name() == name
+        assert ("" if cmp_ is None else cmp_.name()) == cmp_name
+        assert float(r) == float(ratio) and bool(tr) == bool(is_train)
+        assert bool(it.is_bc_mask) == bool(is_mask) and float(it.n_operations) == float(n_ops)
+    with pytest.raises(NotImplementedError):
+        be.npde.get_iterator(make_opt(iterator="nope"))
+
+
+def test_state_dict_keys(be):
+    """Checkpoint compatibility (models/base_model.py:52-60): same keys and shapes as the reference modules."""
+    c = be.npde.ConvIterator("clamp", 3)
+    assert list(c.state_dict().keys()) == ["layers.0.weight", "layers.1.weight", "layers.2.weight"]
+    assert all(tuple(v.shape) == (1, 1, 3, 3) for v in c.state_dict().values())
+    u = be.npde.UNetIterator("clamp", 3, 2, 1)
+    keys = list(u.state_dict().keys())
+    assert keys == (["first_layers.%d.weight" % i for i in range(6)] + ["pooling_layers.%d.weight" % i for i in range(2)]
+                    + ["second_layers.%d.weight" % i for i in range(3)])
+
+
+def test_driver_evaluate(be):
+    """HeatModel.evaluate / calculate_errors vs the reference run (golden): same error curves, same
+    early-exit column, same final iterate."""
+    g = load_golden("driver_evaluate_conv17")
+    model = be.npde.HeatModel(make_opt(is_train=False))
+    model.iterator.to(be.device)
+    with torch.no_grad():
+        for l, w in zip(model.iterator.layers, g["w"]):
+            l.weight.copy_(torch.from_numpy(w).view(1, 1, 3, 3))
+    results, xf = model.evaluate(be.t(g["x"]), be.t(g["gt"]), be.t(g["bc"]), None, 60)
+    je, me = results["Jacobi errors"].numpy(), results["model errors"].numpy()
+    assert je.shape == g["jacobi_errors"].shape and me.shape == g["model_errors"].shape
+    # l2 reduction order differs from torch's mean: 1e-5 relative on the curves, exact zero-padding pattern
+    assert np.array_equal(je == 0, g["jacobi_errors"] == 0) and np.array_equal(me == 0, g["model_errors"] == 0)
+    assert rel_err(je, g["jacobi_errors"]) <= 1e-5 and rel_err(me, g["model_errors"]) <= 1e-5
+    assert_bitwise(be.n(xf), g["x_final"], "final iterate of evaluate")
+
+
+@pytest.mark.parametrize("tag", ["conv_adam", "conv_sgd"])
+def test_driver_train(be, tag):
+    """HeatModel.train: three optimiser steps reproduce the reference's losses and updated weights."""
+    g = load_golden("driver_train_" + tag)
+    opt = make_opt(lambda_gt=0.3) if tag == "conv_adam" else make_opt(optimizer="sgd", lr_init=1e-2)
+    model = be.npde.HeatModel(opt)
+    model.iterator.to(be.device)
+    with torch.no_grad():
+        model.iterator.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w0/")})
+    np.random.seed(1234)
+    x, gt, bc, f = be.t(g["x"]), be.t(g["gt"]), be.t(g["bc"]), be.t(g["f"])
+    losses = []
+    for _ in range(3):
+        out = model.train(x.clone(), gt, bc, f)
+        losses.append([out["loss"].get("loss_x", np.nan), out["loss"].get("loss_gt", np.nan)])
+    losses = np.array(losses)
+    ref = g["losses"]
+    assert np.array_equal(np.isnan(losses), np.isnan(ref))
+    assert np.allclose(losses[~np.isnan(ref)], ref[~np.isnan(ref)], rtol=2e-4)
+    for k, v in g.items():
+        if k.startswith("w1/"):
+            got = model.iterator.state_dict()[k[3:]].cpu().numpy()
+            assert np.allclose(got, v, rtol=0, atol=2e-5), (k, got, v)
+
+
+# --------------------------------------------------------------- error paths --
+def test_error_behaviour(be):
+    x = torch.zeros(2, 17, 17, device=be.device)
+    with pytest.raises(Exception):  # heat_utils.py:40-42
+        be.utils.fd_step(x, torch.zeros(2, 5, device=be.device), None)
+    it = be.npde.ConvIterator("relu", 2).to(be.device)
+    with pytest.raises(NotImplementedError):  # iterator.py:25-26
+        it(x, torch.zeros(2, 4, device=be.device), None)
+    with pytest.raises(NotImplementedError):  # heat_utils.py:130-131
+        be.utils.fd_error(x, torch.zeros(2, 4, device=be.device), None, "sum")
+    with pytest.raises(be.npde._lib.NpdeError):  # even multigrid level size
+        be.npde.MultigridIterator(3, 1, 1)(torch.zeros(2, 19, 19, device=be.device),
+                                           torch.zeros(2, 4, device=be.device), None)
