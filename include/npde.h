@@ -70,6 +70,9 @@ extern "C" {
 #define NPDE_WS_ITERATE 16   /* npde_iterate: pass NPDE_WS_ITERATE + NPDE_IT_* of the iterator */
 
 int npde_version(void);
+
+/* Statistics: kernels enqueued by this library since it was loaded (bench.py's gpu_launches). */
+unsigned long long npde_debug_launch_count(void);
 const char *npde_strerror(int code);
 
 /* Scratch bytes needed by operation `op` (NPDE_WS_*).  bc_kind, n_layers, pre,

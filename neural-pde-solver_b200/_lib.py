@@ -39,6 +39,7 @@ class IterateDesc(ctypes.Structure):
 # name -> (restype, argtypes); must list every symbol of include/npde.h
 PROTOTYPES = {
     "npde_version": (_int, []),
+    "npde_debug_launch_count": (ctypes.c_ulonglong, []),
     "npde_strerror": (ctypes.c_char_p, [_int]),
     "npde_workspace_bytes": (_size, [_int] * 8),
     "npde_set_boundary": (_int, [_vp, _vp, _int, _int, _int, _vp]),

@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
+        run([nvcc, "-shared", "-o", LIB] + objs)  # default: static cudart, no runtime-library lookup at load time
     return LIB
 
 

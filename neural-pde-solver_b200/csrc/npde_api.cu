@@ -2,10 +2,14 @@
 // argument validation, workspace carving and the host-side schedules that
 // string kernels together (V-cycle, UNet, backward, the k-step loop).  Nothing
 // here synchronises or allocates.
+#include <atomic>
 #include <new>
 
 #include "npde_common.cuh"
 #include "npde_internal.h"
+
+static std::atomic<unsigned long long> g_launches{0};
+void npde_note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {
 
@@ -352,6 +356,8 @@ struct IterWs {
 extern "C" {
 
 int npde_version(void) { return 100; }
+
+unsigned long long npde_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char *npde_strerror(int code) {
   switch (code) {

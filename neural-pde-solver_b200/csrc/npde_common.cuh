@@ -13,7 +13,7 @@
 #else
 #include <cuda_runtime.h>
 #define NPDE_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+  (npde_note_launch(), kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define NPDE_DYN_SMEM(type, name) \
   extern __shared__ __align__(16) unsigned char name##_raw[]; \
   type *name = reinterpret_cast<type *>(name##_raw)
@@ -22,6 +22,9 @@
 #include <stdint.h>
 
 #include "../../include/npde.h"
+
+// statistics only (npde_debug_launch_count): number of kernels this library has enqueued
+void npde_note_launch();
 
 #define NPDE_FULL_MASK 0xffffffffu
 
