@@ -104,50 +104,34 @@ __device__ __forceinline__ LaneCols make_cols(int cs, int lane, int N, int vs, i
 }
 
 // One grid row (this lane's four columns) -> o0 = {A col0, B col0}, o1 = {A col1, B col1}.
-// VEC: rows are 8-byte aligned and the strip starts on an even column, so each
-// half is one 64-bit load.
-template <bool VEC>
+// Four 32-bit loads straight into the halves of the packed registers: a 64-bit load per half
+// would need four register moves to re-pair {A,B}, and rows of a 2^n+1 grid are not 8-byte
+// aligned anyway.  The two loads of a half hit the same 128-byte lines (L1).
 __device__ __forceinline__ void load_row(const float *__restrict__ row, const LaneCols &c, f2 &o0, f2 &o1) {
-  float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f;
-  if (VEC && (c.in_img & 3u) == 3u) {
-    float2 t = __ldg(reinterpret_cast<const float2 *>(row + c.colA));
-    a0 = t.x;
-    a1 = t.y;
-  } else {
-    if (c.in_img & 1u) a0 = __ldg(row + c.colA);
-    if (c.in_img & 2u) a1 = __ldg(row + c.colA + 1);
-  }
-  if (VEC && (c.in_img & 12u) == 12u) {
-    float2 t = __ldg(reinterpret_cast<const float2 *>(row + c.colB));
-    b0 = t.x;
-    b1 = t.y;
-  } else {
-    if (c.in_img & 4u) b0 = __ldg(row + c.colB);
-    if (c.in_img & 8u) b1 = __ldg(row + c.colB + 1);
-  }
-  o0 = make_float2(a0, b0);
-  o1 = make_float2(a1, b1);
+  o0.x = (c.in_img & 1u) ? __ldg(row + c.colA) : 0.0f;
+  o1.x = (c.in_img & 2u) ? __ldg(row + c.colA + 1) : 0.0f;
+  o0.y = (c.in_img & 4u) ? __ldg(row + c.colB) : 0.0f;
+  o1.y = (c.in_img & 8u) ? __ldg(row + c.colB + 1) : 0.0f;
+}
+// same for a strip whose 128 columns all exist; p points at this lane's first column
+__device__ __forceinline__ void load_row_full(const float *__restrict__ p, f2 &o0, f2 &o1) {
+  o0.x = __ldg(p);
+  o1.x = __ldg(p + 1);
+  o0.y = __ldg(p + HALF);
+  o1.y = __ldg(p + HALF + 1);
 }
 
-template <bool VEC>
-__device__ __forceinline__ void store_row(float *__restrict__ row, const LaneCols &c, f2 o0, f2 o1) {
-  if (VEC && (c.store & 3u) == 3u) {
-    *reinterpret_cast<float2 *>(row + c.colA) = make_float2(o0.x, o1.x);
-  } else {
-    if (c.store & 1u) row[c.colA] = o0.x;
-    if (c.store & 2u) row[c.colA + 1] = o1.x;
-  }
-  if (VEC && (c.store & 12u) == 12u) {
-    *reinterpret_cast<float2 *>(row + c.colB) = make_float2(o0.y, o1.y);
-  } else {
-    if (c.store & 4u) row[c.colB] = o0.y;
-    if (c.store & 8u) row[c.colB + 1] = o1.y;
-  }
+// mask bits as LaneCols: which of the four columns this lane writes
+__device__ __forceinline__ void store_row(float *__restrict__ p, unsigned mask, f2 o0, f2 o1) {
+  if (mask & 1u) p[0] = o0.x;
+  if (mask & 2u) p[1] = o1.x;
+  if (mask & 4u) p[HALF] = o0.y;
+  if (mask & 8u) p[HALF + 1] = o1.y;
 }
 
-__device__ __forceinline__ void prefetch_row(const float *row, const LaneCols &c) {
-  if (c.in_img & 1u) prefetch_l2(row + c.colA);
-  if (c.in_img & 4u) prefetch_l2(row + c.colB);
+__device__ __forceinline__ void prefetch_row(const float *p, unsigned mask) {
+  if (mask & 1u) prefetch_l2(p);
+  if (mask & 4u) prefetch_l2(p + HALF);
 }
 
 // Horizontal halos of a freshly produced row.  w[1], w[2] are this lane's own
@@ -250,133 +234,313 @@ struct ConvStreamParams {
   float w[4][9];
 };
 
-template <int L, bool VIN, bool VOUT>
-__global__ void __launch_bounds__(npde::STREAM_THREADS)
+__device__ __forceinline__ float and_bits(float v, unsigned m) { return __uint_as_float(__float_as_uint(v) & m); }
+__device__ __forceinline__ float sel_bits(float v, unsigned keep, unsigned val) {
+  return __uint_as_float((__float_as_uint(v) & keep) | val);  // one LOP3
+}
+
+// iterator.py:17-27.  Sigmoid is kept out of line: it is rare and its expf/division
+// expansion would otherwise sit in the middle of the streaming loop.
+__device__ __noinline__ float sigmoid_slow(float z) { return 1.0f / (1.0f + expf(-z)); }
+__device__ __forceinline__ f2 act_pair(f2 z, int act) {
+  if (act == NPDE_ACT_CLAMP) return make_float2(fminf(fmaxf(z.x, 0.0f), 1.0f), fminf(fmaxf(z.y, 0.0f), 1.0f));
+  if (act == NPDE_ACT_SIGMOID) return make_float2(sigmoid_slow(z.x), sigmoid_slow(z.y));
+  return z;
+}
+
+// Streaming form of the row-major 3x3 chain.  A row of the stage input (with its
+// halos) arrives once and serves three output rows: it FINISHES the chain of the
+// row above it (taps w6..w8), CONTINUES the chain of its own row (w3..w5) and
+// STARTS the chain of the row below (w0..w2, first tap a plain product).  Per
+// output the operation order is exactly w0..w8, so results equal the windowed
+// form bit for bit, but only two partial sums per column stay live instead of a
+// 3-row window.
+struct ConvAcc {
+  f2 mid[2];  // after w0..w5: finished by the next row
+  f2 top[2];  // after w0..w2
+};
+__device__ __forceinline__ void conv_feed(const f2 (&row)[4], const float *w, ConvAcc &a, f2 &out0, f2 &out1) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    f2 fin = fma2(bc2(w[6]), row[c], a.mid[c]);
+    fin = fma2(bc2(w[7]), row[c + 1], fin);
+    fin = fma2(bc2(w[8]), row[c + 2], fin);
+    f2 mid = fma2(bc2(w[3]), row[c], a.top[c]);
+    mid = fma2(bc2(w[4]), row[c + 1], mid);
+    mid = fma2(bc2(w[5]), row[c + 2], mid);
+    f2 top = mul2(bc2(w[0]), row[c]);
+    top = fma2(bc2(w[1]), row[c + 1], top);
+    top = fma2(bc2(w[2]), row[c + 2], top);
+    a.mid[c] = mid;
+    a.top[c] = top;
+    if (c == 0) out0 = fin; else out1 = fin;
+  }
+}
+
+template <int L>
+struct ConvState {
+  f2 xb[4];      // x row it-1 with halos
+  f2 yu[2];      // 0.25 * x[it-2]: first tap of Psi for output row it-1
+  f2 rb[L][4];   // rb[k]: the row of r_k produced in the previous step, with halos
+  ConvAcc acc[L];
+  f2 pf[2], pff[2];  // x row `it` / f row it-1, fetched during the previous step
+};
+
+struct ConvLaneCtx {
+  unsigned keep[4];  // per column (A0, A1, B0, B1): all ones if interior, else 0
+  unsigned gval[4];  // Dirichlet value bits of a ring column, else 0
+  unsigned in_img, store;  // LaneCols bit masks, pinned in registers
+  const float *pin;  // this lane's first column in the NEXT input row to fetch
+  const float *pfin; // same for f (row `it`)
+  float *pout;       // this lane's first column in the output row of the current step
+  char *delay;       // this lane's slot 0 of the y delay line (shared memory)
+  float top, bottom;
+  int N, i0, i1, x_last, in_pitch, out_pitch, lane_l, lane_r;
+  bool first, last;  // lane 0 / lane 31
+};
+
+#ifndef NPDE_EMU
+// Keeps a loop-invariant per-lane constant in a register: without this ptxas
+// rematerialises the column masks from the column index in every step (2-3
+// instructions each) to save registers.
+__device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)); }
+#else
+__device__ __forceinline__ void pin_reg(unsigned &) {}
+#endif
+
+__device__ __forceinline__ void exchange_halo_ctx(f2 (&w)[4], const ConvLaneCtx &x) {
+  f2 l = shfl2(w[2], x.lane_l);
+  f2 r = shfl2(w[1], x.lane_r);
+  if (x.first) l.y = l.x;
+  if (x.last) r.x = r.y;
+  w[0] = l;
+  w[3] = r;
+}
+
+template <int ACT>
+__device__ __forceinline__ f2 act_t(f2 z) {
+  if (ACT == NPDE_ACT_CLAMP) return make_float2(fminf(fmaxf(z.x, 0.0f), 1.0f), fminf(fmaxf(z.y, 0.0f), 1.0f));
+  if (ACT == NPDE_ACT_SIGMOID) return make_float2(sigmoid_slow(z.x), sigmoid_slow(z.y));
+  return z;
+}
+
+// One step: input row `it` has arrived in s.pf.  Stage k (0..L) works on row it-1-2k.
+// STEADY: every stage row is an interior row, the output row lies inside the band and the
+//         next input row exists -- no row tests at all.
+// EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per column,
+//         stage outputs are masked to the interior columns and G fixes the ring columns.
+// DS = delay-line slots (power of two >= 2L+1), 512 bytes per slot and warp.
+template <int L, int ACT, bool HASF, bool STEADY, bool EDGE>
+__device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
+                                          unsigned &woff) {
+  constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
+  constexpr unsigned RING = DS * 512u - 1u;
+  const int N = x.N;
+  const unsigned roff = (woff + (DS - 2 * L) * 512u) & RING;  // y written 2L steps ago
+
+  // ---- stages L .. 1 (reverse order: each reads the row its producer made LAST step) ----
+#pragma unroll
+  for (int k = L; k >= 1; --k) {
+    const int rk = it - 1 - 2 * k;
+    f2 h0, h1;
+    conv_feed(s.rb[k - 1], p.w[k - 1], s.acc[k - 1], h0, h1);
+    if (k == L) {
+      if (STEADY || (rk >= x.i0 && rk < x.i1)) {
+        f2 o0, o1;
+        if (STEADY || (rk >= 1 && rk <= N - 2)) {
+          float4 yv = *reinterpret_cast<const float4 *>(x.delay + roff);
+          o0 = act_t<ACT>(add2(make_float2(yv.x, yv.y), h0));
+          o1 = act_t<ACT>(add2(make_float2(yv.z, yv.w), h1));
+        } else {
+          o0 = o1 = bc2(rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+        }
+        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value
+          o0.x = sel_bits(o0.x, x.keep[0], x.gval[0]);
+          o1.x = sel_bits(o1.x, x.keep[1], x.gval[1]);
+          o0.y = sel_bits(o0.y, x.keep[2], x.gval[2]);
+          o1.y = sel_bits(o1.y, x.keep[3], x.gval[3]);
+        }
+        store_row(x.pout, x.store, o0, o1);
+      }
+      if (STEADY || rk >= 0) x.pout += x.out_pitch;  // invariant: pout points at row max(rk, 0)
+    } else {
+      if (!STEADY && !(rk >= 1 && rk <= N - 2)) h0 = h1 = zero2();
+      if (EDGE) {
+        h0.x = and_bits(h0.x, x.keep[0]);
+        h1.x = and_bits(h1.x, x.keep[1]);
+        h0.y = and_bits(h0.y, x.keep[2]);
+        h1.y = and_bits(h1.y, x.keep[3]);
+      }
+      s.rb[k][1] = h0;
+      s.rb[k][2] = h1;
+      exchange_halo_ctx(s.rb[k], x);
+    }
+  }
+
+  // ---- stage 0: y = Psi(x) - f and r_0 = y - x for row it-1 ------------------------------
+  {
+    const int r0 = it - 1;
+    const f2 q = bc2(0.25f);
+    f2 y0 = fma2(q, s.xb[0], s.yu[0]);  // taps: up (in yu), left, right, down
+    y0 = fma2(q, s.xb[2], y0);
+    y0 = fma2(q, s.pf[0], y0);
+    f2 y1 = fma2(q, s.xb[1], s.yu[1]);
+    y1 = fma2(q, s.xb[3], y1);
+    y1 = fma2(q, s.pf[1], y1);
+    if (HASF) {
+      y0 = sub2(y0, s.pff[0]);
+      y1 = sub2(y1, s.pff[1]);
+    }
+    f2 q0 = sub2(y0, s.xb[1]);
+    f2 q1 = sub2(y1, s.xb[2]);
+    if (!STEADY && !(r0 >= 1 && r0 <= N - 2)) q0 = q1 = zero2();
+    if (EDGE) {
+      q0.x = and_bits(q0.x, x.keep[0]);
+      q1.x = and_bits(q1.x, x.keep[1]);
+      q0.y = and_bits(q0.y, x.keep[2]);
+      q1.y = and_bits(q1.y, x.keep[3]);
+    }
+    *reinterpret_cast<float4 *>(x.delay + woff) = make_float4(y0.x, y0.y, y1.x, y1.y);
+    s.yu[0] = mul2(q, s.xb[1]);  // first tap of the next output row (row it): up = x[it-1]
+    s.yu[1] = mul2(q, s.xb[2]);
+    s.rb[0][1] = q0;
+    s.rb[0][2] = q1;
+    exchange_halo_ctx(s.rb[0], x);
+    s.xb[1] = s.pf[0];
+    s.xb[2] = s.pf[1];
+    exchange_halo_ctx(s.xb, x);
+  }
+
+  // ---- fetch the rows of the next step (x row it+1, f row it) ---------------------------------
+  {
+    const int nx = it + 1;
+    if (STEADY || nx <= x.x_last) {
+      if (EDGE) {
+        s.pf[0].x = (x.in_img & 1u) ? __ldg(x.pin) : 0.0f;
+        s.pf[1].x = (x.in_img & 2u) ? __ldg(x.pin + 1) : 0.0f;
+        s.pf[0].y = (x.in_img & 4u) ? __ldg(x.pin + HALF) : 0.0f;
+        s.pf[1].y = (x.in_img & 8u) ? __ldg(x.pin + HALF + 1) : 0.0f;
+      } else {
+        load_row_full(x.pin, s.pf[0], s.pf[1]);
+      }
+      if (nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
+        prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, EDGE ? x.in_img : 15u);
+      x.pin += x.in_pitch;
+    } else {
+      s.pf[0] = s.pf[1] = zero2();
+    }
+    if (HASF) {
+      if (STEADY || (it >= 1 && it <= N - 2)) {
+        if (EDGE) {
+          s.pff[0].x = (x.in_img & 1u) ? __ldg(x.pfin) : 0.0f;
+          s.pff[1].x = (x.in_img & 2u) ? __ldg(x.pfin + 1) : 0.0f;
+          s.pff[0].y = (x.in_img & 4u) ? __ldg(x.pfin + HALF) : 0.0f;
+          s.pff[1].y = (x.in_img & 8u) ? __ldg(x.pfin + HALF + 1) : 0.0f;
+        } else {
+          load_row_full(x.pfin, s.pff[0], s.pff[1]);
+        }
+      } else {
+        s.pff[0] = s.pff[1] = zero2();
+      }
+      if (it + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
+      x.pfin += N;
+    }
+  }
+  woff = (woff + 512u) & RING;
+}
+
+template <int L, int ACT, bool HASF>
+__global__ void __launch_bounds__(npde::STREAM_THREADS, 4)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
-  constexpr int RC = (R + 1) & ~1;   // column halo, even: pair loads stay aligned
-  constexpr int D = 2 * L + 1;       // delay-line depth: y(row) is consumed 2L steps later
-  NPDE_DYN_SMEM(float4, ydl);        // [warp][D][32]: per-lane private slots
+  constexpr int RC = (R + 1) & ~1;   // column halo (even)
+  constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
+  NPDE_DYN_SMEM(float4, ydl);        // [warp][DS][32]: per-lane private slots
 
   StripItem item;
   if (!decode_item(p.B, p.strips, p.bands, item)) return;
+  ConvLaneCtx x;
   const int lane = threadIdx.x & 31;
-  float4 *delay = ydl + (size_t)(threadIdx.x >> 5) * D * 32 + lane;
-
+  x.lane_l = (lane + 31) & 31;
+  x.lane_r = (lane + 1) & 31;
+  x.first = lane == 0;
+  x.last = lane == 31;
+  x.delay = reinterpret_cast<char *>(ydl + (size_t)(threadIdx.x >> 5) * DS * 32 + lane);
+  x.N = p.N;
   const int N = p.N;
   const int vs = item.strip * p.wv, ve = min(vs + p.wv, N);
-  const LaneCols c = make_cols(vs - RC, lane, N, vs, ve);
-  const int i0 = item.band * p.band_rows, i1 = min(i0 + p.band_rows, N);
-  const float *xin = p.in + (size_t)item.b * p.in_bstride;
-  float *xout = p.out + (size_t)item.b * p.out_bstride;
-  const float *fin = p.f ? p.f + (size_t)item.b * N * N : nullptr;
+  const int cs = vs - RC;
+  const LaneCols c = make_cols(cs, lane, N, vs, ve);
+  x.in_img = c.in_img;
+  x.store = c.store;
+  pin_reg(x.in_img);
+  pin_reg(x.store);
+  x.i0 = item.band * p.band_rows;
+  x.i1 = min(x.i0 + p.band_rows, N);
+  x.in_pitch = p.in_pitch;
+  x.out_pitch = p.out_pitch;
   const float *bcb = p.bc4 + (size_t)item.b * 4;
-  const float top = __ldg(bcb + 0), bottom = __ldg(bcb + 1), left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+  x.top = __ldg(bcb + 0);
+  x.bottom = __ldg(bcb + 1);
+  const float left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = ((q & 2) ? c.colB : c.colA) + (q & 1);
+    x.keep[q] = (c.interior >> q & 1u) ? 0xffffffffu : 0u;
+    x.gval[q] = col == 0 ? __float_as_uint(left) : (col == N - 1 ? __float_as_uint(right) : 0u);
+    pin_reg(x.keep[q]);
+    pin_reg(x.gval[q]);
+  }
+  // the strip needs the EDGE code iff one of its 128 columns is not an interior column
+  const bool edge_strip = cs < 1 || cs + STRIP - 1 > N - 2;
 
-  f2 xw[3][4];     // x rows it-2, it-1, it (ring over the step phase)
-  f2 rw[L][3][4];  // r_0 .. r_{L-1}: the three newest rows of each stage
+  ConvState<L> s;
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
+  for (int q = 0; q < 4; ++q) {
+    s.xb[q] = zero2();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      xw[s][q] = zero2();
+    for (int k = 0; k < L; ++k) s.rb[k][q] = zero2();
+  }
 #pragma unroll
-      for (int k = 0; k < L; ++k) rw[k][s][q] = zero2();
-    }
+  for (int k = 0; k < L; ++k) s.acc[k].mid[0] = s.acc[k].mid[1] = s.acc[k].top[0] = s.acc[k].top[1] = zero2();
+  s.yu[0] = s.yu[1] = s.pf[0] = s.pf[1] = s.pff[0] = s.pff[1] = zero2();
 #pragma unroll
-  for (int s = 0; s < D; ++s) delay[s * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < DS; ++d) *reinterpret_cast<float4 *>(x.delay + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // input rows it = it_first .. it_last; the output row of a step is it - 1 - 2L
-  const int it_first = max(i0 - R, 0);  // rows above the grid are zeros == the initial state
-  const int it_last = i1 + 2 * L;
-  const int x_last = min(i1 - 1 + R, N - 1);  // last input row that exists and matters
-  f2 pf[2], pff[2];                            // x row / f row prefetched for the next step
-  pf[0] = pf[1] = pff[0] = pff[1] = zero2();
-  load_row<VIN>(xin + (size_t)it_first * p.in_pitch, c, pf[0], pf[1]);
-  int wslot = 0;  // delay-line write slot of this step (step index mod D)
+  const int it_first = max(x.i0 - R, 0);  // rows above the grid are zeros == the initial state
+  const int it_last = x.i1 + 2 * L;
+  x.x_last = min(x.i1 - 1 + R, N - 1);    // last input row that exists and matters
+  const float *xin = p.in + (size_t)item.b * p.in_bstride;
+  load_row(xin + (size_t)it_first * p.in_pitch, c, s.pf[0], s.pf[1]);
+  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-2L (clamped at 0)
+  x.pin = xin + (size_t)(it_first + 1) * p.in_pitch + c.colA;
+  x.pfin = HASF ? p.f + (size_t)item.b * N * N + (size_t)it_first * N + c.colA : nullptr;
+  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.colA;
+  unsigned woff = 0;
 
-  for (int it_base = it_first; it_base <= it_last; it_base += 3) {
-#pragma unroll
-    for (int ph = 0; ph < 3; ++ph) {
-      const int it = it_base + ph;
-      const int s_new = ph, s_m1 = (ph + 2) % 3, s_m2 = (ph + 1) % 3;  // rows of step t, t-1, t-2
-
-      // ---- stage L: r_L row ro, out = G(act(y + r_L)) ------------------------------
-      const int ro = it - 1 - 2 * L;
-      const int rslot = (wslot + 1 == D) ? 0 : wslot + 1;  // written 2L steps ago
-      if (ro >= i0 && ro < i1) {
-        f2 o0, o1;
-        if (ro >= 1 && ro <= N - 2) {
-          f2 h0 = conv9(rw[L - 1][s_new], rw[L - 1][s_m2], rw[L - 1][s_m1], p.w[L - 1], 0);
-          f2 h1 = conv9(rw[L - 1][s_new], rw[L - 1][s_m2], rw[L - 1][s_m1], p.w[L - 1], 1);
-          float4 yv = delay[rslot * 32];
-          o0 = act2(add2(make_float2(yv.x, yv.y), h0), p.act);
-          o1 = act2(add2(make_float2(yv.z, yv.w), h1), p.act);
-        } else {
-          o0 = o1 = zero2();
-        }
-        apply_G_square(o0, o1, ro, N, c, top, bottom, left, right);
-        store_row<VOUT>(xout + (size_t)ro * p.out_pitch, c, o0, o1);
+  // steady range of `it`: all stage rows interior, output row inside the band, next row loadable
+  const int steady_lo = max(x.i0, 1) + 1 + 2 * L;
+  const int steady_hi = min(min(N - 2, x.i1 + 2 * L), x.x_last - 1);
+  int it = it_first;
+  while (it <= it_last) {
+    if (it >= steady_lo && it + 1 <= steady_hi) {
+      if (edge_strip) {
+        do {
+          conv_step<L, ACT, HASF, true, true>(s, x, p, it, woff);
+          conv_step<L, ACT, HASF, true, true>(s, x, p, it + 1, woff);
+          it += 2;
+        } while (it + 1 <= steady_hi);
+      } else {
+        do {
+          conv_step<L, ACT, HASF, true, false>(s, x, p, it, woff);
+          conv_step<L, ACT, HASF, true, false>(s, x, p, it + 1, woff);
+          it += 2;
+        } while (it + 1 <= steady_hi);
       }
-
-      // ---- stages L-1 .. 1: r_k row (it - 1 - 2k) from r_{k-1} ------------------------
-#pragma unroll
-      for (int k = L - 1; k >= 1; --k) {
-        const int rk = it - 1 - 2 * k;
-        f2 o0, o1;
-        if (rk >= 1 && rk <= N - 2) {
-          o0 = conv9(rw[k - 1][s_new], rw[k - 1][s_m2], rw[k - 1][s_m1], p.w[k - 1], 0);
-          o1 = conv9(rw[k - 1][s_new], rw[k - 1][s_m2], rw[k - 1][s_m1], p.w[k - 1], 1);
-          if (c.interior != 15u) keep_interior(o0, o1, c.interior);
-        } else {
-          o0 = o1 = zero2();
-        }
-        rw[k][s_new][1] = o0;
-        rw[k][s_new][2] = o1;
-        exchange_halo(rw[k][s_new], lane);
-      }
-
-      // ---- stage 0: x row it arrives; y and r_0 for row it-1 ---------------------------
-      xw[s_new][1] = pf[0];
-      xw[s_new][2] = pf[1];
-      {
-        const int r0 = it - 1;
-        f2 y0 = psi2(xw[s_m2][1], xw[s_m1][0], xw[s_m1][2], xw[s_new][1]);
-        f2 y1 = psi2(xw[s_m2][2], xw[s_m1][1], xw[s_m1][3], xw[s_new][2]);
-        if (fin) {
-          y0 = sub2(y0, pff[0]);
-          y1 = sub2(y1, pff[1]);
-        }
-        f2 q0 = sub2(y0, xw[s_m1][1]);
-        f2 q1 = sub2(y1, xw[s_m1][2]);
-        if (r0 >= 1 && r0 <= N - 2) {
-          if (c.interior != 15u) keep_interior(q0, q1, c.interior);
-        } else {
-          q0 = q1 = zero2();
-        }
-        delay[wslot * 32] = make_float4(y0.x, y0.y, y1.x, y1.y);
-        rw[0][s_new][1] = q0;
-        rw[0][s_new][2] = q1;
-        exchange_halo(rw[0][s_new], lane);
-      }
-      exchange_halo(xw[s_new], lane);
-
-      // ---- fetch the next rows -----------------------------------------------------------
-      {
-        const int nx = it + 1;
-        if (nx <= x_last) {
-          load_row<VIN>(xin + (size_t)nx * p.in_pitch, c, pf[0], pf[1]);
-        } else {
-          pf[0] = pf[1] = zero2();
-        }
-        if (fin) {  // f row for the next step's stage 0 is row `it`
-          if (it >= 1 && it <= N - 2) load_row<false>(fin + (size_t)it * N, c, pff[0], pff[1]);
-          else pff[0] = pff[1] = zero2();
-          if (it + L2_AHEAD <= x_last) prefetch_row(fin + (size_t)(it + L2_AHEAD) * N, c);
-        }
-        if (nx + L2_AHEAD <= x_last) prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch, c);
-      }
-      wslot = (wslot + 1 == D) ? 0 : wslot + 1;
+    } else {
+      conv_step<L, ACT, HASF, false, true>(s, x, p, it, woff);
+      ++it;
     }
   }
 }
@@ -393,7 +557,7 @@ struct JacobiStreamParams {
   int strips, bands, band_rows, wv;
 };
 
-template <int T, bool VIN, bool VOUT>
+template <int T>
 __global__ void __launch_bounds__(npde::STREAM_THREADS)
 k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   constexpr int RC = (T + 1) & ~1;
@@ -426,8 +590,8 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const int x_last = min(it_last, N - 1);
   f2 pf[2], pff[2];
   pf[0] = pf[1] = pff[0] = pff[1] = zero2();
-  load_row<VIN>(xin + (size_t)it_first * p.in_pitch, c, pf[0], pf[1]);
-  if (fin && it_first >= 1) load_row<false>(fin + (size_t)(it_first - 1) * N, c, pff[0], pff[1]);
+  load_row(xin + (size_t)it_first * p.in_pitch, c, pf[0], pf[1]);
+  if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * N, c, pff[0], pff[1]);
 
   for (int it_base = it_first; it_base <= it_last; it_base += 3) {
 #pragma unroll
@@ -452,7 +616,7 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
           win[s < T ? s : 0][s_new][1] = o0;
           win[s < T ? s : 0][s_new][2] = o1;
         } else if (row >= i0 && row < i1) {
-          store_row<VOUT>(xout + (size_t)row * p.out_pitch, c, o0, o1);
+          store_row(xout + (size_t)row * p.out_pitch + c.colA, c.store, o0, o1);
         }
       }
 #pragma unroll
@@ -460,15 +624,15 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
 
       const int nx = it + 1;
       if (nx <= x_last) {
-        load_row<VIN>(xin + (size_t)nx * p.in_pitch, c, pf[0], pf[1]);
+        load_row(xin + (size_t)nx * p.in_pitch, c, pf[0], pf[1]);
       } else {
         pf[0] = pf[1] = zero2();
       }
       if (T == 1 && fin) {  // next step's output row is `it`
-        if (it <= N - 1) load_row<false>(fin + (size_t)it * N, c, pff[0], pff[1]);
-        if (it + L2_AHEAD <= x_last) prefetch_row(fin + (size_t)(it + L2_AHEAD) * N, c);
+        if (it <= N - 1) load_row(fin + (size_t)it * N, c, pff[0], pff[1]);
+        if (it + L2_AHEAD <= x_last) prefetch_row(fin + (size_t)(it + L2_AHEAD) * N + c.colA, c.in_img);
       }
-      if (nx + L2_AHEAD <= x_last) prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch, c);
+      if (nx + L2_AHEAD <= x_last) prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch + c.colA, c.in_img);
     }
   }
 }
@@ -511,45 +675,44 @@ int resident_warps_cached(const void *kernel, size_t smem, int *cache) {
 #endif
 }
 
-inline bool vec_ok(const void *base, long bstride, int pitch) {
-  return ((uintptr_t)base % 8 == 0) && (bstride % 2 == 0) && (pitch % 2 == 0);
+template <int L, int ACT>
+int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  if (p.f) NPDE_LAUNCH((k_conv_stream<L, ACT, true>), grid, block, smem, st, p);
+  else NPDE_LAUNCH((k_conv_stream<L, ACT, false>), grid, block, smem, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
 }
 
 template <int L>
 int launch_conv(ConvStreamParams &p, cudaStream_t st) {
-  constexpr int R = L + 1, RC = (R + 1) & ~1, D = 2 * L + 1;
-  const size_t smem = sizeof(float4) * D * 32 * (npde::STREAM_THREADS / 32);
-  const bool vin = vec_ok(p.in, p.in_bstride, p.in_pitch), vout = vec_ok(p.out, p.out_bstride, p.out_pitch);
+  constexpr int R = L + 1, RC = (R + 1) & ~1, DS = (2 * L + 1 <= 8) ? 8 : 16;
+  const size_t smem = sizeof(float4) * DS * 32 * (npde::STREAM_THREADS / 32);
   static int cache = 0;
-  int resident = resident_warps_cached((const void *)k_conv_stream<L, true, true>, smem, &cache);
+  int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache);
   Split s = make_split(p.B, p.N, RC, R, resident);
   p.strips = s.strips; p.bands = s.bands; p.band_rows = s.band_rows; p.wv = s.wv;
   long items = (long)p.B * s.strips * s.bands;
   const int wpb = npde::STREAM_THREADS / 32;
   dim3 grid((unsigned)((items + wpb - 1) / wpb)), block(npde::STREAM_THREADS);
-  if (vin && vout) NPDE_LAUNCH((k_conv_stream<L, true, true>), grid, block, smem, st, p);
-  else if (vin) NPDE_LAUNCH((k_conv_stream<L, true, false>), grid, block, smem, st, p);
-  else if (vout) NPDE_LAUNCH((k_conv_stream<L, false, true>), grid, block, smem, st, p);
-  else NPDE_LAUNCH((k_conv_stream<L, false, false>), grid, block, smem, st, p);
-  NPDE_CHECK_LAUNCH();
-  return NPDE_OK;
+  switch (p.act) {
+    case NPDE_ACT_NONE: return launch_conv_f<L, NPDE_ACT_NONE>(p, grid, block, smem, st);
+    case NPDE_ACT_CLAMP: return launch_conv_f<L, NPDE_ACT_CLAMP>(p, grid, block, smem, st);
+    case NPDE_ACT_SIGMOID: return launch_conv_f<L, NPDE_ACT_SIGMOID>(p, grid, block, smem, st);
+    default: return NPDE_ERR_ACT;
+  }
 }
 
 template <int T>
 int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 1) & ~1;
-  const bool vin = vec_ok(p.in, p.in_bstride, p.in_pitch), vout = vec_ok(p.out, p.out_bstride, p.out_pitch);
   static int cache = 0;
-  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, true, true>, 0, &cache);
+  int resident = resident_warps_cached((const void *)k_jacobi_stream<T>, 0, &cache);
   Split s = make_split(p.B, p.N, RC, T, resident);
   p.strips = s.strips; p.bands = s.bands; p.band_rows = s.band_rows; p.wv = s.wv;
   long items = (long)p.B * s.strips * s.bands;
   const int wpb = npde::STREAM_THREADS / 32;
   dim3 grid((unsigned)((items + wpb - 1) / wpb)), block(npde::STREAM_THREADS);
-  if (vin && vout) NPDE_LAUNCH((k_jacobi_stream<T, true, true>), grid, block, 0, st, p);
-  else if (vin) NPDE_LAUNCH((k_jacobi_stream<T, true, false>), grid, block, 0, st, p);
-  else if (vout) NPDE_LAUNCH((k_jacobi_stream<T, false, true>), grid, block, 0, st, p);
-  else NPDE_LAUNCH((k_jacobi_stream<T, false, false>), grid, block, 0, st, p);
+  NPDE_LAUNCH((k_jacobi_stream<T>), grid, block, 0, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
