@@ -49,7 +49,7 @@ size_t weight_grad_ws_bytes(int B, int Hg);
 int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream_t st);
 
 // npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)
-constexpr int STREAM_THREADS = 128;  // 4 independent warp strips per CTA
+constexpr int STREAM_THREADS = 32;  // one warp strip per CTA (see decode_item in npde_stream.cu)
 
 // A (B,N,N) field with an arbitrary row pitch / batch stride (floats): the
 // reference layout is {p, N, N*N}; internal ping-pong buffers use a padded pitch.

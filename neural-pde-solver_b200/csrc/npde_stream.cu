@@ -212,8 +212,11 @@ __device__ __forceinline__ f2 act2(f2 z, int act) {
 struct StripItem {
   int b, strip, band;
 };
+// One warp per CTA: the work item depends on blockIdx only, so ptxas can prove that the band /
+// strip bookkeeping and the loop-versioning branches are warp-uniform and keep the conv weights
+// in uniform registers (FFMA2 R, R, UR.F32, R) instead of re-loading them from the constant bank.
 __device__ __forceinline__ bool decode_item(int B, int strips, int bands, StripItem &it) {
-  long item = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long item = (long)blockIdx.x;
   if (item >= (long)B * strips * bands) return false;
   it.strip = (int)(item % strips);
   it.band = (int)((item / strips) % bands);
@@ -283,7 +286,7 @@ struct ConvState {
   f2 yu[2];      // 0.25 * x[it-2]: first tap of Psi for output row it-1
   f2 rb[L][4];   // rb[k]: the row of r_k produced in the previous step, with halos
   ConvAcc acc[L];
-  f2 pf[2], pff[2];  // x row `it` / f row it-1, fetched during the previous step
+  f2 pf[2][2], pff[2][2];  // [parity of it]: x row `it` / f row it-1, fetched two steps earlier
 };
 
 struct ConvLaneCtx {
@@ -330,9 +333,12 @@ __device__ __forceinline__ f2 act_t(f2 z) {
 // EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per column,
 //         stage outputs are masked to the interior columns and G fixes the ring columns.
 // DS = delay-line slots (power of two >= 2L+1), 512 bytes per slot and warp.
-template <int L, int ACT, bool HASF, bool STEADY, bool EDGE>
+// PH = parity slot of the row buffers used by this step (the loop alternates 0,1).
+template <int L, int ACT, bool HASF, bool STEADY, bool EDGE, int PH>
 __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
                                           unsigned &woff) {
+  f2 (&pf)[2] = s.pf[PH];
+  f2 (&pff)[2] = s.pff[PH];
   constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
   constexpr unsigned RING = DS * 512u - 1u;
   const int N = x.N;
@@ -383,13 +389,13 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     const f2 q = bc2(0.25f);
     f2 y0 = fma2(q, s.xb[0], s.yu[0]);  // taps: up (in yu), left, right, down
     y0 = fma2(q, s.xb[2], y0);
-    y0 = fma2(q, s.pf[0], y0);
+    y0 = fma2(q, pf[0], y0);
     f2 y1 = fma2(q, s.xb[1], s.yu[1]);
     y1 = fma2(q, s.xb[3], y1);
-    y1 = fma2(q, s.pf[1], y1);
+    y1 = fma2(q, pf[1], y1);
     if (HASF) {
-      y0 = sub2(y0, s.pff[0]);
-      y1 = sub2(y1, s.pff[1]);
+      y0 = sub2(y0, pff[0]);
+      y1 = sub2(y1, pff[1]);
     }
     f2 q0 = sub2(y0, s.xb[1]);
     f2 q1 = sub2(y1, s.xb[2]);
@@ -406,43 +412,44 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     s.rb[0][1] = q0;
     s.rb[0][2] = q1;
     exchange_halo_ctx(s.rb[0], x);
-    s.xb[1] = s.pf[0];
-    s.xb[2] = s.pf[1];
+    s.xb[1] = pf[0];
+    s.xb[2] = pf[1];
     exchange_halo_ctx(s.xb, x);
   }
 
-  // ---- fetch the rows of the next step (x row it+1, f row it) ---------------------------------
+  // ---- refill this parity's buffers: x row it+2 and f row it+1 (consumed two steps from now) ----
   {
-    const int nx = it + 1;
+    const int nx = it + 2;
     if (STEADY || nx <= x.x_last) {
       if (EDGE) {
-        s.pf[0].x = (x.in_img & 1u) ? __ldg(x.pin) : 0.0f;
-        s.pf[1].x = (x.in_img & 2u) ? __ldg(x.pin + 1) : 0.0f;
-        s.pf[0].y = (x.in_img & 4u) ? __ldg(x.pin + HALF) : 0.0f;
-        s.pf[1].y = (x.in_img & 8u) ? __ldg(x.pin + HALF + 1) : 0.0f;
+        pf[0].x = (x.in_img & 1u) ? __ldg(x.pin) : 0.0f;
+        pf[1].x = (x.in_img & 2u) ? __ldg(x.pin + 1) : 0.0f;
+        pf[0].y = (x.in_img & 4u) ? __ldg(x.pin + HALF) : 0.0f;
+        pf[1].y = (x.in_img & 8u) ? __ldg(x.pin + HALF + 1) : 0.0f;
       } else {
-        load_row_full(x.pin, s.pf[0], s.pf[1]);
+        load_row_full(x.pin, pf[0], pf[1]);
       }
       if (nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
         prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, EDGE ? x.in_img : 15u);
       x.pin += x.in_pitch;
     } else {
-      s.pf[0] = s.pf[1] = zero2();
+      pf[0] = pf[1] = zero2();
     }
     if (HASF) {
-      if (STEADY || (it >= 1 && it <= N - 2)) {
+      const int nf = it + 1;  // f row used by the stage 0 of step it+2
+      if (STEADY || (nf >= 1 && nf <= N - 2)) {
         if (EDGE) {
-          s.pff[0].x = (x.in_img & 1u) ? __ldg(x.pfin) : 0.0f;
-          s.pff[1].x = (x.in_img & 2u) ? __ldg(x.pfin + 1) : 0.0f;
-          s.pff[0].y = (x.in_img & 4u) ? __ldg(x.pfin + HALF) : 0.0f;
-          s.pff[1].y = (x.in_img & 8u) ? __ldg(x.pfin + HALF + 1) : 0.0f;
+          pff[0].x = (x.in_img & 1u) ? __ldg(x.pfin) : 0.0f;
+          pff[1].x = (x.in_img & 2u) ? __ldg(x.pfin + 1) : 0.0f;
+          pff[0].y = (x.in_img & 4u) ? __ldg(x.pfin + HALF) : 0.0f;
+          pff[1].y = (x.in_img & 8u) ? __ldg(x.pfin + HALF + 1) : 0.0f;
         } else {
-          load_row_full(x.pfin, s.pff[0], s.pff[1]);
+          load_row_full(x.pfin, pff[0], pff[1]);
         }
       } else {
-        s.pff[0] = s.pff[1] = zero2();
+        pff[0] = pff[1] = zero2();
       }
-      if (it + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
+      if (nf + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
       x.pfin += N;
     }
   }
@@ -450,7 +457,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
 }
 
 template <int L, int ACT, bool HASF>
-__global__ void __launch_bounds__(npde::STREAM_THREADS, 4)
+__global__ void __launch_bounds__(npde::STREAM_THREADS, 16)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
   constexpr int RC = (R + 1) & ~1;   // column halo (even)
@@ -465,7 +472,7 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.lane_r = (lane + 1) & 31;
   x.first = lane == 0;
   x.last = lane == 31;
-  x.delay = reinterpret_cast<char *>(ydl + (size_t)(threadIdx.x >> 5) * DS * 32 + lane);
+  x.delay = reinterpret_cast<char *>(ydl + lane);
   x.N = p.N;
   const int N = p.N;
   const int vs = item.strip * p.wv, ve = min(vs + p.wv, N);
@@ -503,7 +510,9 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   }
 #pragma unroll
   for (int k = 0; k < L; ++k) s.acc[k].mid[0] = s.acc[k].mid[1] = s.acc[k].top[0] = s.acc[k].top[1] = zero2();
-  s.yu[0] = s.yu[1] = s.pf[0] = s.pf[1] = s.pff[0] = s.pff[1] = zero2();
+  s.yu[0] = s.yu[1] = zero2();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) s.pf[h][0] = s.pf[h][1] = s.pff[h][0] = s.pff[h][1] = zero2();
 #pragma unroll
   for (int d = 0; d < DS; ++d) *reinterpret_cast<float4 *>(x.delay + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -512,34 +521,46 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   const int it_last = x.i1 + 2 * L;
   x.x_last = min(x.i1 - 1 + R, N - 1);    // last input row that exists and matters
   const float *xin = p.in + (size_t)item.b * p.in_bstride;
-  load_row(xin + (size_t)it_first * p.in_pitch, c, s.pf[0], s.pf[1]);
-  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-2L (clamped at 0)
-  x.pin = xin + (size_t)(it_first + 1) * p.in_pitch + c.colA;
-  x.pfin = HASF ? p.f + (size_t)item.b * N * N + (size_t)it_first * N + c.colA : nullptr;
+  const float *fimg = HASF ? p.f + (size_t)item.b * N * N : nullptr;
+  // buffers of parity 0 / 1 hold rows it_first / it_first+1 (f: one row behind)
+  load_row(xin + (size_t)it_first * p.in_pitch, c, s.pf[0][0], s.pf[0][1]);
+  if (it_first + 1 <= x.x_last) load_row(xin + (size_t)(it_first + 1) * p.in_pitch, c, s.pf[1][0], s.pf[1][1]);
+  if (HASF) {
+    if (it_first - 1 >= 1) load_row(fimg + (size_t)(it_first - 1) * N, c, s.pff[0][0], s.pff[0][1]);
+    if (it_first >= 1 && it_first <= N - 2) load_row(fimg + (size_t)it_first * N, c, s.pff[1][0], s.pff[1][1]);
+  }
+  // running pointers: pin -> row it+2 of x, pfin -> row it+1 of f, pout -> output row it-1-2L (clamped at 0)
+  x.pin = xin + (size_t)(it_first + 2) * p.in_pitch + c.colA;
+  x.pfin = HASF ? fimg + (size_t)(it_first + 1) * N + c.colA : nullptr;
   x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.colA;
   unsigned woff = 0;
 
-  // steady range of `it`: all stage rows interior, output row inside the band, next row loadable
+  // steady range of `it`: all stage rows interior, output row inside the band, rows it+2 (x) and
+  // it+1 (f) loadable
   const int steady_lo = max(x.i0, 1) + 1 + 2 * L;
-  const int steady_hi = min(min(N - 2, x.i1 + 2 * L), x.x_last - 1);
+  const int steady_hi = min(min(N - 3, x.i1 + 2 * L), x.x_last - 2);
   int it = it_first;
   while (it <= it_last) {
-    if (it >= steady_lo && it + 1 <= steady_hi) {
+    // parity bookkeeping: steps alternate buffer 0,1 starting with 0 at it_first
+    if (((it - it_first) & 1) == 0 && it >= steady_lo && it + 1 <= steady_hi) {
       if (edge_strip) {
         do {
-          conv_step<L, ACT, HASF, true, true>(s, x, p, it, woff);
-          conv_step<L, ACT, HASF, true, true>(s, x, p, it + 1, woff);
+          conv_step<L, ACT, HASF, true, true, 0>(s, x, p, it, woff);
+          conv_step<L, ACT, HASF, true, true, 1>(s, x, p, it + 1, woff);
           it += 2;
         } while (it + 1 <= steady_hi);
       } else {
         do {
-          conv_step<L, ACT, HASF, true, false>(s, x, p, it, woff);
-          conv_step<L, ACT, HASF, true, false>(s, x, p, it + 1, woff);
+          conv_step<L, ACT, HASF, true, false, 0>(s, x, p, it, woff);
+          conv_step<L, ACT, HASF, true, false, 1>(s, x, p, it + 1, woff);
           it += 2;
         } while (it + 1 <= steady_hi);
       }
+    } else if (((it - it_first) & 1) == 0) {
+      conv_step<L, ACT, HASF, false, true, 0>(s, x, p, it, woff);
+      ++it;
     } else {
-      conv_step<L, ACT, HASF, false, true>(s, x, p, it, woff);
+      conv_step<L, ACT, HASF, false, true, 1>(s, x, p, it, woff);
       ++it;
     }
   }
