@@ -10,7 +10,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnpde_b200.so")
+# NPDE_B200_LIB: development hook to A/B-test differently compiled builds of the SAME CUDA library
+LIB_PATH = os.environ.get("NPDE_B200_LIB") or os.path.join(HERE, "libnpde_b200.so")
 
 OK = 0
 BC_SQUARE, BC_MASK = 0, 1

@@ -77,7 +77,10 @@ __device__ __forceinline__ f2 shfl2(f2 v, int src) {
 
 constexpr int STRIP = 128;        // columns per warp strip
 constexpr int HALF = STRIP / 2;   // columns per half (the two lanes of a packed value)
-constexpr int L2_AHEAD = 6;       // rows of L2 prefetch distance
+#ifndef NPDE_L2_AHEAD
+#define NPDE_L2_AHEAD 6
+#endif
+constexpr int L2_AHEAD = NPDE_L2_AHEAD;  // rows of L2 prefetch distance (0: no prefetch instructions)
 
 // Column bookkeeping of one lane: bit0 = left-half col 0, bit1 = left-half col 1,
 // bit2 = right-half col 0, bit3 = right-half col 1.
@@ -328,8 +331,10 @@ __device__ __forceinline__ f2 act_t(f2 z) {
 }
 
 // One step: input row `it` has arrived in s.pf.  Stage k (0..L) works on row it-1-2k.
-// STEADY: every stage row is an interior row, the output row lies inside the band and the
-//         next input row exists -- no row tests at all.
+// STEADY: every stage row (it-1-2k, k=0..L) is an interior row of the grid: no ring-row handling.
+//         Whether the output row belongs to this band and whether the rows to fetch exist are
+//         uniform predicates evaluated in every step (a few instructions), so the warm-up and
+//         drain steps of a band in the middle of the grid run the same fast code.
 // EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per column,
 //         stage outputs are masked to the interior columns and G fixes the ring columns.
 // DS = delay-line slots (power of two >= 2L+1), 512 bytes per slot and warp.
@@ -351,7 +356,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     f2 h0, h1;
     conv_feed(s.rb[k - 1], p.w[k - 1], s.acc[k - 1], h0, h1);
     if (k == L) {
-      if (STEADY || (rk >= x.i0 && rk < x.i1)) {
+      if (rk >= x.i0 && rk < x.i1) {
         f2 o0, o1;
         if (STEADY || (rk >= 1 && rk <= N - 2)) {
           float4 yv = *reinterpret_cast<const float4 *>(x.delay + roff);
@@ -420,7 +425,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
   // ---- refill this parity's buffers: x row it+2 and f row it+1 (consumed two steps from now) ----
   {
     const int nx = it + 2;
-    if (STEADY || nx <= x.x_last) {
+    if (nx <= x.x_last) {
       if (EDGE) {
         pf[0].x = (x.in_img & 1u) ? __ldg(x.pin) : 0.0f;
         pf[1].x = (x.in_img & 2u) ? __ldg(x.pin + 1) : 0.0f;
@@ -429,7 +434,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
       } else {
         load_row_full(x.pin, pf[0], pf[1]);
       }
-      if (nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
+      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
         prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, EDGE ? x.in_img : 15u);
       x.pin += x.in_pitch;
     } else {
@@ -437,7 +442,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     }
     if (HASF) {
       const int nf = it + 1;  // f row used by the stage 0 of step it+2
-      if (STEADY || (nf >= 1 && nf <= N - 2)) {
+      if (nf <= x.x_last && (STEADY || (nf >= 1 && nf <= N - 2))) {
         if (EDGE) {
           pff[0].x = (x.in_img & 1u) ? __ldg(x.pfin) : 0.0f;
           pff[1].x = (x.in_img & 2u) ? __ldg(x.pfin + 1) : 0.0f;
@@ -449,7 +454,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
       } else {
         pff[0] = pff[1] = zero2();
       }
-      if (nf + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
+      if (L2_AHEAD > 0 && nf + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
       x.pfin += N;
     }
   }
@@ -457,7 +462,10 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
 }
 
 template <int L, int ACT, bool HASF>
-__global__ void __launch_bounds__(npde::STREAM_THREADS, 16)
+#ifndef NPDE_CONV_MIN_CTAS
+#define NPDE_CONV_MIN_CTAS 16
+#endif
+__global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_CONV_MIN_CTAS)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
   constexpr int RC = (R + 1) & ~1;   // column halo (even)
@@ -535,10 +543,9 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.colA;
   unsigned woff = 0;
 
-  // steady range of `it`: all stage rows interior, output row inside the band, rows it+2 (x) and
-  // it+1 (f) loadable
-  const int steady_lo = max(x.i0, 1) + 1 + 2 * L;
-  const int steady_hi = min(min(N - 3, x.i1 + 2 * L), x.x_last - 2);
+  // steady range of `it`: all stage rows it-1-2L .. it-1 are interior rows (and so is f row it+1)
+  const int steady_lo = 2 + 2 * L;
+  const int steady_hi = min(N - 3, it_last);
   int it = it_first;
   while (it <= it_last) {
     // parity bookkeeping: steps alternate buffer 0,1 starting with 0 at it_first
