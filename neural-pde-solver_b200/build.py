@@ -63,6 +63,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """DEVELOPMENT: a tuning build of the same library with extra -D flags (only the Conv3 / clamp
+    stream kernel is instantiated, see NPDE_DEV_ONLY_CONV3) -> tools/_build/libnpde_<name>.so.
+    Loaded through the NPDE_B200_LIB hook of _lib.py by tools/ab_bench.py; never shipped."""
+    out_dir = os.path.join(ROOT, "tools", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    build()
+    obj = os.path.join(out_dir, "npde_stream_%s.o" % name)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DNPDE_DEV_ONLY_CONV3"] + ["-D" + d for d in defines] + \
+          ["-c", "-o", obj, os.path.join(CSRC, "npde_stream.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), r.stderr))
+    objs = [obj if s == "npde_stream.cu" else os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    out = os.path.join(out_dir, "libnpde_%s.so" % name)
+    r = subprocess.run([_nvcc(), "-shared", "-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed: " + r.stderr)
+    return out
+
+
 def build_emulator(force=False):
     """TEST INFRASTRUCTURE: the same .cu sources compiled for the host against
     tests/emu/cuda_emu.h (a SIMT emulator) -> tests/emu/_build/libnpde_emu.so.

@@ -207,7 +207,7 @@ int jacobi_steps(const float *src, float *buf0, float *buf1, const float *bc, in
     if (bc_kind == NPDE_BC_SQUARE) {
       int depth = 1;
       if (!f) depth = left >= 8 ? 8 : (left >= 4 ? 4 : (left >= 2 ? 2 : 1));
-      TRY(jacobi_stream(ref_view(cur, N), ref_view_mut(dst, N), bc, f, depth, B, N, st));
+      TRY(jacobi_stream(ref_view(cur, N), ref_view_mut(dst, N), bc, ref_view(f, N), depth, B, N, st));
       left -= depth;
     } else {
       TRY(fd_step_simple(cur, bc, bc_kind, f, dst, B, N, st));
@@ -328,6 +328,7 @@ int level_sizes_ok(int N, int L) {
 // reduction scratch and the largest per-step workspace any iterator may need.
 struct IterWs {
   float *buf[2];
+  float *fpad;  // the source in the padded layout (Jacobi / Conv fast path)
   int pitch;
   long bstride;
   void *red;
@@ -340,6 +341,7 @@ struct IterWs {
     size_t cells = (size_t)B * bstride;  // >= B*N*N, so the generic loop can use them unpadded
     buf[0] = b.take<float>(cells);
     buf[1] = b.take<float>(cells);
+    fpad = (iterator == NPDE_IT_JACOBI || iterator == NPDE_IT_CONV) ? b.take<float>(cells) : nullptr;
     red_bytes = npde::reduce_ws_bytes(B, N);
     red = b.take_bytes(red_bytes);
     step_bytes = 0;
@@ -430,8 +432,8 @@ int npde_conv_step_fwd(const float *x, const float *bc, int bc_kind, const float
   if (n_layers > 0 && !w) return NPDE_ERR_NULL;
   if (x == y) return NPDE_ERR_ARG;
   if (npde::conv_stream_supported(bc_kind, n_layers, w_host))
-    return npde::conv_stream(npde::ref_view(x, N), npde::ref_view_mut(y, N), bc, f, w_host, n_layers, act, B, N,
-                             S(stream));
+    return npde::conv_stream(npde::ref_view(x, N), npde::ref_view_mut(y, N), bc, npde::ref_view(f, N), w_host,
+                             n_layers, act, B, N, S(stream));
   TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_CONV_FWD, B, N, bc_kind, n_layers, 0, 0, 0)));
   return conv_step_layered(x, bc, bc_kind, f, w, n_layers, act, y, B, N, ws, S(stream));
 }
@@ -645,8 +647,15 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   if ((conv_fast || jac_fast) && !want_err) {
     if (d->k == 0) return d2d(d->x_out, d->x_in, sizeof(float) * cells, st);
     npde::FieldView cur = npde::ref_view(d->x_in, N);
-    npde::FieldViewMut pad[2] = {{w.buf[0], w.pitch, w.bstride}, {w.buf[1], w.pitch, w.bstride}};
+    npde::FieldViewMut pad[2] = {{w.buf[0], w.pitch, w.bstride, 1}, {w.buf[1], w.pitch, w.bstride, 1}};
     npde::FieldViewMut last = npde::ref_view_mut(d->x_out, N);
+    // the source is read in every step: give it 16-byte aligned rows once (128-bit loads)
+    npde::FieldView fv = npde::ref_view(d->f, N);
+    if (d->f && d->k >= 3) {
+      npde::FieldViewMut fp = {w.fpad, w.pitch, w.bstride, 1};
+      TRY(npde::copy_field(fv, fp, B, N, st));
+      fv = npde::as_const(fp);
+    }
     int left = d->k, flip = 0;
     while (left > 0) {
       int adv = 1;
@@ -659,9 +668,9 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       bool alias = final_launch && (const void *)d->x_out == (const void *)cur.p;  // k == 1 in place
       npde::FieldViewMut dst = (final_launch && !alias) ? last : pad[flip];
       if (conv_fast)
-        TRY(npde::conv_stream(cur, dst, d->bc, d->f, d->w_host, d->n_layers, d->act, B, N, st));
+        TRY(npde::conv_stream(cur, dst, d->bc, fv, d->w_host, d->n_layers, d->act, B, N, st));
       else
-        TRY(npde::jacobi_stream(cur, dst, d->bc, d->f, adv, B, N, st));
+        TRY(npde::jacobi_stream(cur, dst, d->bc, fv, adv, B, N, st));
       left -= adv;
       if (final_launch && alias) TRY(npde::copy_field(npde::as_const(dst), last, B, N, st));
       cur = npde::as_const(dst);

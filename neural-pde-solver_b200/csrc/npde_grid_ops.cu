@@ -152,11 +152,17 @@ k_l2_error(const float *__restrict__ x, const float *__restrict__ gt, float *err
   block_reduce_finish<false>(acc, ws, chunks, err, b, (double)n, true);
 }
 
-__global__ void k_copy_field(const float *__restrict__ src, int sp, long sb, float *__restrict__ dst, int dp, long db,
-                             int N) {
+// column j inside a row of a field view: the pair-permuted layout stores every aligned group of
+// four columns (c0,c1,c2,c3) as (c0,c2,c1,c3) (npde_internal.h FieldView)
+__device__ __forceinline__ int view_col(int j, int perm) {
+  return perm ? ((j & ~3) | ((j & 1) << 1) | ((j >> 1) & 1)) : j;
+}
+__global__ void k_copy_field(const float *__restrict__ src, int sp, long sb, int sperm, float *__restrict__ dst,
+                             int dp, long db, int dperm, int N) {
   int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (i >= N || j >= N) return;
-  dst[(size_t)b * db + (size_t)i * dp + j] = __ldg(src + (size_t)b * sb + (size_t)i * sp + j);
+  dst[(size_t)b * db + (size_t)i * dp + view_col(j, dperm)] =
+      __ldg(src + (size_t)b * sb + (size_t)i * sp + view_col(j, sperm));
 }
 
 // ------------------------------------------------------ transfer ops ------
@@ -316,8 +322,8 @@ int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t 
 }
 
 int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st) {
-  NPDE_LAUNCH(k_copy_field, grid2d(N, N, B), dim3(TX, TY), 0, st, src.p, src.pitch, src.bstride, dst.p, dst.pitch,
-              dst.bstride, N);
+  NPDE_LAUNCH(k_copy_field, grid2d(N, N, B), dim3(TX, TY), 0, st, src.p, src.pitch, src.bstride, src.perm, dst.p,
+              dst.pitch, dst.bstride, dst.perm, N);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -51,30 +51,38 @@ int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream
 // npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)
 constexpr int STREAM_THREADS = 32;  // one warp strip per CTA (see decode_item in npde_stream.cu)
 
-// A (B,N,N) field with an arbitrary row pitch / batch stride (floats): the
-// reference layout is {p, N, N*N}; internal ping-pong buffers use a padded pitch.
+// A (B,N,N) field with an arbitrary row pitch / batch stride (floats).  The reference layout
+// is {p, N, N*N, perm = 0}.  The internal ping-pong buffers of the k-step loop use the
+// "pair-permuted padded layout" (perm = 1): 16-byte aligned rows of pitch >= round_up(N, 4)
+// in which every aligned group of four columns (c0,c1,c2,c3) is stored as (c0,c2,c1,c3), the
+// register-pair order of the stream kernels (npde_stream.cu), so a lane moves its four
+// columns with one 128-bit access.
 struct FieldView {
   const float *p;
   int pitch;
   long bstride;
+  int perm;
 };
 struct FieldViewMut {
   float *p;
   int pitch;
   long bstride;
+  int perm;
 };
-inline FieldView ref_view(const float *p, int N) { return FieldView{p, N, (long)N * N}; }
-inline FieldViewMut ref_view_mut(float *p, int N) { return FieldViewMut{p, N, (long)N * N}; }
+inline FieldView ref_view(const float *p, int N) { return FieldView{p, N, (long)N * N, 0}; }  // p may be nullptr
+inline FieldViewMut ref_view_mut(float *p, int N) { return FieldViewMut{p, N, (long)N * N, 0}; }
+// layout conversion / copy between any two views
 int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st);  // npde_grid_ops.cu
-inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch, v.bstride}; }
+inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch, v.bstride, v.perm}; }
 
 // square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
 bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
-int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, const float *w_host,
-                int n_layers, int act, int B, int N, cudaStream_t st);
+// f.p == nullptr: Laplace.  perm views are accessed with 128-bit loads / stores, natural ones with 32-bit.
+int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f,
+                const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st);
 // depth in {1,2,4,8} Jacobi steps per launch (1 when f != NULL); square domain only
 int jacobi_stream_max_depth(const float *f);
-int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, int depth, int B,
-                  int N, cudaStream_t st);
+int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f, int depth,
+                  int B, int N, cudaStream_t st);
 
 }  // namespace npde

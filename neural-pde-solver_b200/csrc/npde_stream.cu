@@ -5,87 +5,135 @@
 //     per HBM round trip.
 //
 // Design ("warp strips"):
-//   - A warp owns a strip of 128 grid columns and marches down the rows of a
-//     band.  Lane l holds columns {2l, 2l+1} of the left half AND {64+2l, 65+2l}
-//     of the right half, packed as float2 {left, right}: every arithmetic
-//     instruction is a packed FFMA2/FADD2/FMUL2 (fma.rn.f32x2, new on sm_100),
-//     which does two IEEE-rn FMAs per issue slot with naturally aligned operands.
-//   - Each pipeline stage keeps a 3-row sliding window in registers (rows rotate
-//     by a 3x unrolled loop, no register moves).  Horizontal neighbours come from
-//     warp shuffles; nothing is exchanged between warps, so there is no
-//     __syncthreads anywhere: a strip recomputes a halo of (L+1) columns instead.
-//   - Conv stages are software-pipelined two rows apart so that all stages of a
-//     step are independent instruction streams (ILP instead of occupancy).
-//   - The Jacobi value y of a row is needed 2L steps later; it waits in a
-//     per-lane shared-memory delay line (private slots, no synchronisation).
-//   - Input rows are prefetched one step ahead into registers and several rows
-//     ahead into L2 (prefetch.global.L2).
-//   - Arithmetic order is the oracle's: row-major fmaf chain, first tap a plain
-//     product (oracle/npde_oracle.c conv3x3_img / orc_fd_step), so iterates are
-//     bit-identical to the CPU restatement.
+//   - A warp owns a strip of 128 grid columns and marches down the rows of a band.  Lane l
+//     holds the four adjacent columns c0..c3 = cs+4l .. cs+4l+3 as two packed pairs
+//     Q0 = {c0, c2}, Q1 = {c1, c3}.  With this pairing the centre and the inner horizontal
+//     taps of a 3-wide stencil are naturally aligned pairs (out Q0: centre Q0, right Q1;
+//     out Q1: left Q0, centre Q1) and run as packed FFMA2 (fma.rn.f32x2, new on sm_100: two
+//     IEEE-rn FMAs per issue slot); only the two outer taps (left of Q0 = {c-1, c1}, right of
+//     Q1 = {c2, c4}) mix registers of different pairs and run as two scalar FFMAs on the
+//     halves of the accumulator pair.  c-1 and c4 come from the neighbour lanes by ONE warp
+//     shuffle each per row; nothing is exchanged between warps, so there is no
+//     __syncthreads anywhere: a strip recomputes a halo of whole lanes instead.
+//   - The internal ping-pong fields of the k-step loop use a padded pitch and store every
+//     aligned group of four columns as (c0, c2, c1, c3) ("pair-permuted layout"): one 128-bit
+//     load delivers Q0 and Q1 as register pairs, one 128-bit store writes a lane's outputs.
+//     Reference-layout tensors (pitch 2^n+1, rows only 4-byte aligned) use 32-bit accesses.
+//   - Each conv stage keeps three partial-sum rows that are updated in place and swap roles
+//     every step, and the three live x rows rotate the same way; the step index modulo 3 is a template
+//     parameters of a 3x unrolled loop, so the rotation costs no register moves.
+//   - Conv stages are software-pipelined two rows apart so that all stages of a step are
+//     independent instruction streams (ILP instead of occupancy).
+//   - The Jacobi value y of a row is needed 2L steps later; it waits in a per-lane
+//     shared-memory delay line (private slots, no synchronisation).
+//   - Input rows are loaded one step ahead straight into their register slot and several
+//     rows ahead into L2 (prefetch.global.L2).
+//   - Arithmetic order is the oracle's: row-major fmaf chain, first tap a plain product
+//     (oracle/npde_oracle.c conv3x3_img / orc_fd_step), so iterates are bit-identical to the
+//     CPU restatement.
 #include "npde_common.cuh"
 #include "npde_internal.h"
 
 namespace {
 
-typedef float2 f2;
-
+// f2 = two fp32 values in one 64-bit register pair.  On the device it is an opaque 64-bit
+// integer that is packed / unpacked explicitly (mov.b64), so ptxas sees exactly one register
+// pair per value and every packed instruction takes it as is; in the emulator it is a struct.
 #ifdef NPDE_EMU
 #define NPDE_GRID_CONSTANT
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+struct f2 { float x, y; };
+struct f2x2 { f2 a, b; };
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; r.x = lo; r.y = hi; return r; }
+__device__ __forceinline__ float lo(f2 a) { return a.x; }
+__device__ __forceinline__ float hi(f2 a) { return a.y; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return mk2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) { return mk2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+// bitwise AND with a pair of 32-bit masks
+__device__ __forceinline__ f2 and2(f2 a, unsigned mlo, unsigned mhi) {
+  return mk2(__uint_as_float(__float_as_uint(a.x) & mlo), __uint_as_float(__float_as_uint(a.y) & mhi));
+}
 __device__ __forceinline__ void prefetch_l2(const void *) {}
+// 16 bytes at p -> two pairs {p[0], p[1]}, {p[2], p[3]}
+__device__ __forceinline__ void ld_pairs(const float *p, f2 &a, f2 &b) {
+  a = mk2(p[0], p[1]);
+  b = mk2(p[2], p[3]);
+}
+__device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
+  p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
 #else
 #define NPDE_GRID_CONSTANT __grid_constant__
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk(f2 a) { return *reinterpret_cast<u64 *>(&a); }
-__device__ __forceinline__ f2 upk(u64 a) { return *reinterpret_cast<f2 *>(&a); }
-// Packed fp32: two independent round-to-nearest operations per instruction.
-// The only products that are later added (first conv tap, 0.25*u) feed an fma's
-// addend, which ptxas cannot contract, so the rounding sequence is exactly the
-// scalar fmaf chain's.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 mk2(float lo, float hi) {
+  f2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ float lo(f2 a) {
+  float l, h;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a));
+  return l;
+}
+__device__ __forceinline__ float hi(f2 a) {
+  float l, h;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(l), "=f"(h) : "l"(a));
+  return h;
+}
+// Packed fp32 (new on sm_100): two independent round-to-nearest operations per instruction.
+// The only products that are later added (first conv tap, 0.25*u) feed an fma's addend, which
+// ptxas cannot contract, so the rounding sequence is exactly the scalar fmaf chain's.
 __device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-  u64 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
-  return upk(d);
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
 }
 __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-  u64 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
-  return upk(d);
-}
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-  u64 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
-  return upk(d);
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 __device__ __forceinline__ f2 sub2(f2 a, f2 b) {
-  u64 d;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
-  return upk(d);
+  f2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 and2(f2 a, unsigned mlo, unsigned mhi) {
+  return a & (((f2)mhi << 32) | (f2)mlo);
 }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void ld_pairs(const float *p, f2 &a, f2 &b) {
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(p));
+  a = v.x;
+  b = v.y;
+}
+__device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
+  *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
+}
 #endif
 
-__device__ __forceinline__ f2 bc2(float s) { return make_float2(s, s); }
-__device__ __forceinline__ f2 zero2() { return make_float2(0.0f, 0.0f); }
-__device__ __forceinline__ f2 shfl2(f2 v, int src) {
-  return make_float2(__shfl_sync(NPDE_FULL_MASK, v.x, src), __shfl_sync(NPDE_FULL_MASK, v.y, src));
+__device__ __forceinline__ f2 bc2(float s) { return mk2(s, s); }
+__device__ __forceinline__ f2 zero2() { return mk2(0.0f, 0.0f); }
+// acc + w * {a_lo, a_hi} on the two halves separately (two scalar FFMAs: the operand pair is
+// not a register pair)
+__device__ __forceinline__ f2 fma_lohi(float w, float a_lo, float a_hi, f2 acc) {
+  return mk2(__fmaf_rn(w, a_lo, lo(acc)), __fmaf_rn(w, a_hi, hi(acc)));
+}
+__device__ __forceinline__ f2 mul_lohi(float w, float a_lo, float a_hi) {
+  return mk2(__fmul_rn(w, a_lo), __fmul_rn(w, a_hi));
 }
 
-constexpr int STRIP = 128;        // columns per warp strip
-constexpr int HALF = STRIP / 2;   // columns per half (the two lanes of a packed value)
+constexpr int STRIP = 128;        // columns per warp strip: lane l owns the 4 adjacent columns cs+4l .. cs+4l+3
+constexpr int LANE_COLS = 4;
 #ifndef NPDE_L2_AHEAD
-#define NPDE_L2_AHEAD 6
+#define NPDE_L2_AHEAD 4
 #endif
 constexpr int L2_AHEAD = NPDE_L2_AHEAD;  // rows of L2 prefetch distance (0: no prefetch instructions)
 
-// Column bookkeeping of one lane: bit0 = left-half col 0, bit1 = left-half col 1,
-// bit2 = right-half col 0, bit3 = right-half col 1.
+// Column bookkeeping of one lane: bit q <-> column c0 + q
+// (bit0 = lo(Q0), bit1 = lo(Q1), bit2 = hi(Q0), bit3 = hi(Q1)).
 struct LaneCols {
-  int colA, colB;
+  int c0;
   unsigned in_img;    // column exists (0 <= c < N)
   unsigned interior;  // 1 <= c <= N-2
   unsigned store;     // column belongs to this strip's valid output range
@@ -93,12 +141,11 @@ struct LaneCols {
 
 __device__ __forceinline__ LaneCols make_cols(int cs, int lane, int N, int vs, int ve) {
   LaneCols c;
-  c.colA = cs + 2 * lane;
-  c.colB = c.colA + HALF;
+  c.c0 = cs + LANE_COLS * lane;
   c.in_img = c.interior = c.store = 0u;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    int col = ((q & 2) ? c.colB : c.colA) + (q & 1);
+    int col = c.c0 + q;
     if (col >= 0 && col < N) c.in_img |= 1u << q;
     if (col >= 1 && col <= N - 2) c.interior |= 1u << q;
     if (col >= vs && col < ve) c.store |= 1u << q;
@@ -106,58 +153,66 @@ __device__ __forceinline__ LaneCols make_cols(int cs, int lane, int N, int vs, i
   return c;
 }
 
-// One grid row (this lane's four columns) -> o0 = {A col0, B col0}, o1 = {A col1, B col1}.
-// Four 32-bit loads straight into the halves of the packed registers: a 64-bit load per half
-// would need four register moves to re-pair {A,B}, and rows of a 2^n+1 grid are not 8-byte
-// aligned anyway.  The two loads of a half hit the same 128-byte lines (L1).
-__device__ __forceinline__ void load_row(const float *__restrict__ row, const LaneCols &c, f2 &o0, f2 &o1) {
-  o0.x = (c.in_img & 1u) ? __ldg(row + c.colA) : 0.0f;
-  o1.x = (c.in_img & 2u) ? __ldg(row + c.colA + 1) : 0.0f;
-  o0.y = (c.in_img & 4u) ? __ldg(row + c.colB) : 0.0f;
-  o1.y = (c.in_img & 8u) ? __ldg(row + c.colB + 1) : 0.0f;
-}
-// same for a strip whose 128 columns all exist; p points at this lane's first column
-__device__ __forceinline__ void load_row_full(const float *__restrict__ p, f2 &o0, f2 &o1) {
-  o0.x = __ldg(p);
-  o1.x = __ldg(p + 1);
-  o0.y = __ldg(p + HALF);
-  o1.y = __ldg(p + HALF + 1);
-}
-
-// mask bits as LaneCols: which of the four columns this lane writes
-__device__ __forceinline__ void store_row(float *__restrict__ p, unsigned mask, f2 o0, f2 o1) {
-  if (mask & 1u) p[0] = o0.x;
-  if (mask & 2u) p[1] = o1.x;
-  if (mask & 4u) p[HALF] = o0.y;
-  if (mask & 8u) p[HALF + 1] = o1.y;
+// One grid row, this lane's four columns -> q0 = Q0 = {c0,c2}, q1 = Q1 = {c1,c3}.  p points at
+// the lane's group of four.
+// perm (pair-permuted padded layout, memory order c0,c2,c1,c3): one 128-bit load, enabled per lane.
+// natural layout: four 32-bit loads with per-column predicates (any alignment).
+__device__ __forceinline__ void load_row(const float *__restrict__ p, bool perm, bool lane_ok, unsigned in_img,
+                                         f2 &q0, f2 &q1) {
+  if (perm) {
+    if (lane_ok) ld_pairs(p, q0, q1);
+    else q0 = q1 = zero2();
+  } else {
+    const float v0 = (in_img & 1u) ? __ldg(p) : 0.0f;
+    const float v1 = (in_img & 2u) ? __ldg(p + 1) : 0.0f;
+    const float v2 = (in_img & 4u) ? __ldg(p + 2) : 0.0f;
+    const float v3 = (in_img & 8u) ? __ldg(p + 3) : 0.0f;
+    q0 = mk2(v0, v2);
+    q1 = mk2(v1, v3);
+  }
 }
 
-__device__ __forceinline__ void prefetch_row(const float *p, unsigned mask) {
-  if (mask & 1u) prefetch_l2(p);
-  if (mask & 4u) prefetch_l2(p + HALF);
+// o0 = {c0,c2}, o1 = {c1,c3}.  perm: one 128-bit store per enabled lane (a lane stores all of
+// its columns or none: strip ranges are multiples of 4); natural: per-column predicates.
+__device__ __forceinline__ void store_row(float *__restrict__ p, bool perm, bool lane_ok, unsigned mask, f2 o0,
+                                          f2 o1) {
+  if (perm) {
+    if (lane_ok) st_pairs(p, o0, o1);
+  } else {
+    if (mask & 1u) p[0] = lo(o0);
+    if (mask & 2u) p[1] = lo(o1);
+    if (mask & 4u) p[2] = hi(o0);
+    if (mask & 8u) p[3] = hi(o1);
+  }
 }
 
-// Horizontal halos of a freshly produced row.  w[1], w[2] are this lane's own
-// columns; w[0] / w[3] become the columns to their left / right.  The seam
-// between the halves: lane 31's right neighbour (left half) is lane 0's
-// right-half col 0, lane 0's left neighbour (right half) is lane 31's left-half
-// col 1.  The strip's outer edges receive don't-care values (they only reach
-// cells outside the strip's valid range).
-__device__ __forceinline__ void exchange_halo(f2 (&w)[4], int lane) {
-  f2 l = shfl2(w[2], (lane + 31) & 31);
-  f2 r = shfl2(w[1], (lane + 1) & 31);
-  if (lane == 0) l.y = l.x;
-  if (lane == 31) r.x = r.y;
-  w[0] = l;
-  w[3] = r;
+// same from the four column values c0..c3 (fresh scalars: ptxas allocates them as one quad)
+__device__ __forceinline__ void store_cols(float *__restrict__ p, bool perm, bool lane_ok, unsigned mask, float v0,
+                                           float v1, float v2, float v3) {
+  if (perm) {
+    if (lane_ok) *reinterpret_cast<float4 *>(p) = make_float4(v0, v2, v1, v3);
+  } else {
+    if (mask & 1u) p[0] = v0;
+    if (mask & 2u) p[1] = v1;
+    if (mask & 4u) p[2] = v2;
+    if (mask & 8u) p[3] = v3;
+  }
 }
 
-// Zero the components whose column is not an interior column (bits as LaneCols).
-__device__ __forceinline__ void keep_interior(f2 &o0, f2 &o1, unsigned interior) {
-  if (!(interior & 1u)) o0.x = 0.0f;
-  if (!(interior & 2u)) o1.x = 0.0f;
-  if (!(interior & 4u)) o0.y = 0.0f;
-  if (!(interior & 8u)) o1.y = 0.0f;
+// L2 prefetch of the 512-byte row segment of a strip
+#ifndef NPDE_PF_LANES
+#define NPDE_PF_LANES 1  // every lane: the segment is not line-aligned (a sparser prefetch misses its tail line)
+#endif
+__device__ __forceinline__ void prefetch_row(const float *p, int lane, unsigned in_img) {
+  if ((lane & (NPDE_PF_LANES - 1)) == 0 && (in_img & 1u)) prefetch_l2(p);
+}
+
+// The two outer horizontal neighbours of a row: c-1 = c3 of the left lane, c4 = c0 of the right
+// lane.  The strip's outer edges (lane 0 left, lane 31 right) receive wrapped-around
+// don't-care values; they only reach cells outside the strip's valid range.
+__device__ __forceinline__ void halo_scalars(f2 q0, f2 q1, int lane_l, int lane_r, float &hl, float &hr) {
+  hl = __shfl_sync(NPDE_FULL_MASK, hi(q1), lane_l);
+  hr = __shfl_sync(NPDE_FULL_MASK, lo(q0), lane_r);
 }
 
 // G on the square domain for one output row: ring rows take top/bottom, then the
@@ -172,58 +227,59 @@ __device__ __forceinline__ void apply_G_square(f2 &o0, f2 &o1, int row, int N, c
     o1 = o0;
   }
   if (c.interior != 15u) {
-    if (c.colA == 0) o0.x = left;
-    if (c.colA == N - 1) o0.x = right;
-    if (c.colA + 1 == N - 1) o1.x = right;  // colA is even or <0, so colA+1 is never 0
-    if (c.colA + 1 == 0) o1.x = left;
-    if (c.colB == 0) o0.y = left;
-    if (c.colB == N - 1) o0.y = right;
-    if (c.colB + 1 == N - 1) o1.y = right;
-    if (c.colB + 1 == 0) o1.y = left;
+    float v0 = lo(o0), v1 = lo(o1), v2 = hi(o0), v3 = hi(o1);
+    if (c.c0 == 0) v0 = left;
+    if (c.c0 == N - 1) v0 = right;
+    if (c.c0 + 1 == 0) v1 = left;
+    if (c.c0 + 1 == N - 1) v1 = right;
+    if (c.c0 + 2 == 0) v2 = left;
+    if (c.c0 + 2 == N - 1) v2 = right;
+    if (c.c0 + 3 == 0) v3 = left;
+    if (c.c0 + 3 == N - 1) v3 = right;
+    o0 = mk2(v0, v2);
+    o1 = mk2(v1, v3);
   }
 }
 
-// 3x3 cross-correlation of a 3-row window for this lane's column c (0 or 1):
-// row-major fmaf chain, first tap a plain product (oracle conv3x3_img).
-__device__ __forceinline__ f2 conv9(const f2 (&t)[4], const f2 (&m)[4], const f2 (&b)[4], const float *w, int c) {
-  f2 acc = mul2(bc2(w[0]), t[c]);
-  acc = fma2(bc2(w[1]), t[c + 1], acc);
-  acc = fma2(bc2(w[2]), t[c + 2], acc);
-  acc = fma2(bc2(w[3]), m[c], acc);
-  acc = fma2(bc2(w[4]), m[c + 1], acc);
-  acc = fma2(bc2(w[5]), m[c + 2], acc);
-  acc = fma2(bc2(w[6]), b[c], acc);
-  acc = fma2(bc2(w[7]), b[c + 1], acc);
-  acc = fma2(bc2(w[8]), b[c + 2], acc);
-  return acc;
-}
-
-// Jacobi average, taps in the oracle's order up, left, right, down (orc_fd_step).
-__device__ __forceinline__ f2 psi2(f2 u, f2 l, f2 r, f2 d) {
+// Jacobi average of one row (centre pairs m0, m1 with outer neighbours hl, hr; rows above u*
+// and below d*), taps in the oracle's order up, left, right, down (orc_fd_step).
+__device__ __forceinline__ void psi_row(f2 u0, f2 u1, f2 m0, f2 m1, float hl, float hr, f2 d0, f2 d1, f2 &o0,
+                                        f2 &o1) {
   const f2 q = bc2(0.25f);
-  f2 acc = mul2(q, u);
-  acc = fma2(q, l, acc);
-  acc = fma2(q, r, acc);
-  acc = fma2(q, d, acc);
-  return acc;
+  o0 = mul2(q, u0);
+  o0 = fma_lohi(0.25f, hl, lo(m1), o0);  // left of {c0,c2} = {c-1, c1}
+  o0 = fma2(q, m1, o0);                  // right of {c0,c2} = {c1, c3}
+  o0 = fma2(q, d0, o0);
+  o1 = mul2(q, u1);
+  o1 = fma2(q, m0, o1);                  // left of {c1,c3} = {c0, c2}
+  o1 = fma_lohi(0.25f, hi(m0), hr, o1);  // right of {c1,c3} = {c2, c4}
+  o1 = fma2(q, d1, o1);
 }
 
-__device__ __forceinline__ f2 act2(f2 z, int act) {
-  return make_float2(npde_act(z.x, act), npde_act(z.y, act));
-}
-
-struct StripItem {
-  int b, strip, band;
-};
+// Work partition: B * strips * bands warp items, the strip index fastest.  The warps that share a
+// band of an image walk down the same rows at the same time, so their 512-byte row segments hit
+// the same open DRAM pages (a partition into equal-cost pieces at unrelated rows measured 7% slower).
 // One warp per CTA: the work item depends on blockIdx only, so ptxas can prove that the band /
-// strip bookkeeping and the loop-versioning branches are warp-uniform and keep the conv weights
+// strip bookkeeping and the loop-versioning branches are warp-uniform and keeps the conv weights
 // in uniform registers (FFMA2 R, R, UR.F32, R) instead of re-loading them from the constant bank.
-__device__ __forceinline__ bool decode_item(int B, int strips, int bands, StripItem &it) {
+struct StripItem {
+  int b, strip, i0, i1;  // image, strip, rows [i0, i1)
+};
+struct Split {
+  int strips, bands, band_rows, wv;
+};
+__host__ __device__ __forceinline__ bool strip_is_edge(int strip, int wv, int rc, int N) {
+  const int cs = strip * wv - rc;
+  return cs < 1 || cs + STRIP - 1 > N - 2;
+}
+__device__ __forceinline__ bool decode_item(int B, int N, const Split &sp, StripItem &it) {
   long item = (long)blockIdx.x;
-  if (item >= (long)B * strips * bands) return false;
-  it.strip = (int)(item % strips);
-  it.band = (int)((item / strips) % bands);
-  it.b = (int)(item / ((long)strips * bands));
+  if (item >= (long)B * sp.strips * sp.bands) return false;
+  it.strip = (int)(item % sp.strips);
+  const int band = (int)((item / sp.strips) % sp.bands);
+  it.b = (int)(item / ((long)sp.strips * sp.bands));
+  it.i0 = band * sp.band_rows;
+  it.i1 = min(it.i0 + sp.band_rows, N);
   return true;
 }
 
@@ -231,78 +287,94 @@ __device__ __forceinline__ bool decode_item(int B, int strips, int bands, StripI
 struct ConvStreamParams {
   const float *in;
   float *out;
-  const float *f;    // reference layout (pitch N) or NULL
+  const float *f;    // NULL: Laplace
   const float *bc4;  // (B,4)
-  long in_bstride, out_bstride;
-  int in_pitch, out_pitch;
+  long in_bstride, out_bstride, f_bstride;
+  int in_pitch, out_pitch, f_pitch;
+  int in_perm, out_perm, f_perm;  // field is in the pair-permuted padded layout (128-bit accesses)
   int B, N, act;
-  int strips, bands, band_rows, wv;
+  Split split;
   float w[4][9];
 };
 
-__device__ __forceinline__ float and_bits(float v, unsigned m) { return __uint_as_float(__float_as_uint(v) & m); }
 __device__ __forceinline__ float sel_bits(float v, unsigned keep, unsigned val) {
   return __uint_as_float((__float_as_uint(v) & keep) | val);  // one LOP3
 }
 
-// iterator.py:17-27.  Sigmoid is kept out of line: it is rare and its expf/division
-// expansion would otherwise sit in the middle of the streaming loop.
+// iterator.py:17-27 applied to z = y + h.  Sigmoid is kept out of line: it is rare and its
+// expf/division expansion would otherwise sit in the middle of the streaming loop.
 __device__ __noinline__ float sigmoid_slow(float z) { return 1.0f / (1.0f + expf(-z)); }
-__device__ __forceinline__ f2 act_pair(f2 z, int act) {
-  if (act == NPDE_ACT_CLAMP) return make_float2(fminf(fmaxf(z.x, 0.0f), 1.0f), fminf(fmaxf(z.y, 0.0f), 1.0f));
-  if (act == NPDE_ACT_SIGMOID) return make_float2(sigmoid_slow(z.x), sigmoid_slow(z.y));
+template <int ACT>
+__device__ __forceinline__ float add_act(float y, float h) {
+  if (ACT == NPDE_ACT_CLAMP) {
+#ifdef NPDE_EMU
+    return fminf(fmaxf(__fadd_rn(y, h), 0.0f), 1.0f);
+#else
+    float z;  // one FADD.SAT: round(y + h) clamped to [0, 1]
+    asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(z) : "f"(y), "f"(h));
+    return z;
+#endif
+  }
+  const float z = __fadd_rn(y, h);
+  if (ACT == NPDE_ACT_SIGMOID) return sigmoid_slow(z);
   return z;
 }
 
-// Streaming form of the row-major 3x3 chain.  A row of the stage input (with its
-// halos) arrives once and serves three output rows: it FINISHES the chain of the
-// row above it (taps w6..w8), CONTINUES the chain of its own row (w3..w5) and
-// STARTS the chain of the row below (w0..w2, first tap a plain product).  Per
-// output the operation order is exactly w0..w8, so results equal the windowed
-// form bit for bit, but only two partial sums per column stay live instead of a
-// 3-row window.
-struct ConvAcc {
-  f2 mid[2];  // after w0..w5: finished by the next row
-  f2 top[2];  // after w0..w2
-};
-__device__ __forceinline__ void conv_feed(const f2 (&row)[4], const float *w, ConvAcc &a, f2 &out0, f2 &out1) {
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    f2 fin = fma2(bc2(w[6]), row[c], a.mid[c]);
-    fin = fma2(bc2(w[7]), row[c + 1], fin);
-    fin = fma2(bc2(w[8]), row[c + 2], fin);
-    f2 mid = fma2(bc2(w[3]), row[c], a.top[c]);
-    mid = fma2(bc2(w[4]), row[c + 1], mid);
-    mid = fma2(bc2(w[5]), row[c + 2], mid);
-    f2 top = mul2(bc2(w[0]), row[c]);
-    top = fma2(bc2(w[1]), row[c + 1], top);
-    top = fma2(bc2(w[2]), row[c + 2], top);
-    a.mid[c] = mid;
-    a.top[c] = top;
-    if (c == 0) out0 = fin; else out1 = fin;
-  }
+// Streaming form of the row-major 3x3 chain.  A row of the stage input (centre pairs c0p, c1p
+// and its outer neighbours hl, hr) arrives once and serves three output rows: it FINISHES the
+// chain of the row above it (taps w6..w8), CONTINUES the chain of its own row (w3..w5) and
+// STARTS the chain of the row below (w0..w2, first tap a plain product).  Per output the
+// operation order is exactly w0..w8 (oracle conv3x3_img), so results equal the windowed form
+// bit for bit, but only partial sums stay live instead of a 3-row window.  The three
+// partial-sum rows of a stage are updated IN PLACE and swap roles every step
+// (fin -> top -> mid -> fin).
+__device__ __forceinline__ void conv_taps(f2 c0p, f2 c1p, float hl, float hr, float wl, float wc, float wr,
+                                          f2 &a0, f2 &a1) {
+  a0 = fma_lohi(wl, hl, lo(c1p), a0);  // out {c0,c2}: left {c-1,c1}, centre {c0,c2}, right {c1,c3}
+  a0 = fma2(bc2(wc), c0p, a0);
+  a0 = fma2(bc2(wr), c1p, a0);
+  a1 = fma2(bc2(wl), c0p, a1);         // out {c1,c3}: left {c0,c2}, centre {c1,c3}, right {c2,c4}
+  a1 = fma2(bc2(wc), c1p, a1);
+  a1 = fma_lohi(wr, hi(c0p), hr, a1);
+}
+__device__ __forceinline__ void conv_feed(f2 c0p, f2 c1p, float hl, float hr, const float *w, f2 (&fin)[2],
+                                          f2 (&mid)[2], f2 (&top)[2]) {
+  conv_taps(c0p, c1p, hl, hr, w[6], w[7], w[8], fin[0], fin[1]);
+  conv_taps(c0p, c1p, hl, hr, w[3], w[4], w[5], mid[0], mid[1]);
+  top[0] = mul_lohi(w[0], hl, lo(c1p));
+  top[0] = fma2(bc2(w[1]), c0p, top[0]);
+  top[0] = fma2(bc2(w[2]), c1p, top[0]);
+  top[1] = mul2(bc2(w[0]), c0p);
+  top[1] = fma2(bc2(w[1]), c1p, top[1]);
+  top[1] = fma_lohi(w[2], hi(c0p), hr, top[1]);
 }
 
 template <int L>
 struct ConvState {
-  f2 xb[4];      // x row it-1 with halos
-  f2 yu[2];      // 0.25 * x[it-2]: first tap of Psi for output row it-1
-  f2 rb[L][4];   // rb[k]: the row of r_k produced in the previous step, with halos
-  ConvAcc acc[L];
-  f2 pf[2][2], pff[2][2];  // [parity of it]: x row `it` / f row it-1, fetched two steps earlier
+  f2 X[3][2];      // x rows, slot = row index modulo 3 (relative to the band): row `it` (loaded during the
+                   // previous step), row it-1 (centre row of Psi) and the slot the load of row it+1 fills
+  float xhl, xhr;  // outer neighbours of x row it-1
+  f2 yu[2];        // 0.25 * x[it-2]: first tap of Psi for output row it-1
+  f2 r0c[2];       // the r_0 row stage 0 produced in the previous step
+  float r0l, r0r;  // ... and its outer neighbours
+  f2 A[L][3][2];   // A[k-1]: the three partial-sum rows of conv stage k; the row finished in the
+                   // previous step stays in its slot as the next stage's input
+  float rl[L], rr[L];  // rl/rr[k-1]: outer neighbours of the row stage k finished in the previous step
+  f2 pff[2];       // f row it-1, fetched one step earlier
 };
 
 struct ConvLaneCtx {
-  unsigned keep[4];  // per column (A0, A1, B0, B1): all ones if interior, else 0
+  unsigned keep[4];  // per column c0..c3: all ones if interior, else 0
   unsigned gval[4];  // Dirichlet value bits of a ring column, else 0
-  unsigned in_img, store;  // LaneCols bit masks, pinned in registers
-  const float *pin;  // this lane's first column in the NEXT input row to fetch
-  const float *pfin; // same for f (row `it`)
-  float *pout;       // this lane's first column in the output row of the current step
+  unsigned in_img, store;  // LaneCols bit masks
+  bool in_perm, out_perm, f_perm;  // layouts (uniform)
+  bool ld_ok, st_ok; // permuted layout: this lane's 128-bit load / store is enabled
+  const float *pin;  // this lane's group of four in the NEXT input row to fetch
+  const float *pfin; // same for f
+  float *pout;       // this lane's group of four in the output row of the current step
   char *delay;       // this lane's slot 0 of the y delay line (shared memory)
   float top, bottom;
-  int N, i0, i1, x_last, in_pitch, out_pitch, lane_l, lane_r;
-  bool first, last;  // lane 0 / lane 31
+  int N, i0, i1, x_last, in_pitch, out_pitch, f_pitch, lane, lane_l, lane_r;
 };
 
 #ifndef NPDE_EMU
@@ -314,77 +386,81 @@ __device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)
 __device__ __forceinline__ void pin_reg(unsigned &) {}
 #endif
 
-__device__ __forceinline__ void exchange_halo_ctx(f2 (&w)[4], const ConvLaneCtx &x) {
-  f2 l = shfl2(w[2], x.lane_l);
-  f2 r = shfl2(w[1], x.lane_r);
-  if (x.first) l.y = l.x;
-  if (x.last) r.x = r.y;
-  w[0] = l;
-  w[3] = r;
-}
-
-template <int ACT>
-__device__ __forceinline__ f2 act_t(f2 z) {
-  if (ACT == NPDE_ACT_CLAMP) return make_float2(fminf(fmaxf(z.x, 0.0f), 1.0f), fminf(fmaxf(z.y, 0.0f), 1.0f));
-  if (ACT == NPDE_ACT_SIGMOID) return make_float2(sigmoid_slow(z.x), sigmoid_slow(z.y));
-  return z;
-}
-
-// One step: input row `it` has arrived in s.pf.  Stage k (0..L) works on row it-1-2k.
-// STEADY: every stage row (it-1-2k, k=0..L) is an interior row of the grid: no ring-row handling.
-//         Whether the output row belongs to this band and whether the rows to fetch exist are
-//         uniform predicates evaluated in every step (a few instructions), so the warm-up and
-//         drain steps of a band in the middle of the grid run the same fast code.
-// EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per column,
-//         stage outputs are masked to the interior columns and G fixes the ring columns.
+// One step: input row `it` has arrived in s.X[J].  Stage k (0..L) works on row it-1-2k.
+// MAIN:   every stage row (it-1-2k, k=0..L) is an interior row of the grid, the output row
+//         belongs to this band and the rows to fetch exist: no row tests at all.
+// !MAIN:  generic step (band warm-up / drain, ring rows): uniform row tests everywhere.
+// EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per lane or
+//         column, stage outputs are masked to the interior columns and G fixes the ring columns.
+// PERM:   all fields are in the pair-permuted padded layout (128-bit accesses); otherwise the
+//         layout of each field is a run-time flag.
+// J:      step index modulo 3: roles of the partial-sum rows and of the x row slots.  Everything
+//         that rotates has period 3, so a 3x unrolled loop needs no register moves and its body
+//         (~370 instructions) stays inside the 6 KB L0 instruction cache.
 // DS = delay-line slots (power of two >= 2L+1), 512 bytes per slot and warp.
-// PH = parity slot of the row buffers used by this step (the loop alternates 0,1).
-template <int L, int ACT, bool HASF, bool STEADY, bool EDGE, int PH>
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM, int J>
 __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
                                           unsigned &woff) {
-  f2 (&pf)[2] = s.pf[PH];
-  f2 (&pff)[2] = s.pff[PH];
   constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
   constexpr unsigned RING = DS * 512u - 1u;
+  constexpr int JF = J % 3, JM = (J + 1) % 3, JT = (J + 2) % 3;  // slots: finishing, continuing, starting
   const int N = x.N;
   const unsigned roff = (woff + (DS - 2 * L) * 512u) & RING;  // y written 2L steps ago
+  const bool in_perm = PERM || x.in_perm, out_perm = PERM || x.out_perm, f_perm = PERM || x.f_perm;
+  const bool ld_ok = !EDGE || x.ld_ok;
+  const f2 (&D)[2] = s.X[JF];  // row it: the Psi "down" tap now, the centre row of the next step
+  const f2 (&C)[2] = s.X[JT];  // centre row it-1
 
-  // ---- stages L .. 1 (reverse order: each reads the row its producer made LAST step) ----
+  // ---- fetch x row it+1 into the slot that held row it-2 (consumed by the next step) ----
+  {
+    const int nx = it + 1;
+    if (MAIN || nx <= x.x_last) {
+      load_row(x.pin, in_perm, ld_ok, EDGE ? x.in_img : 15u, s.X[JM][0], s.X[JM][1]);
+      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
+        prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, x.lane, EDGE ? x.in_img : 15u);
+      x.pin += x.in_pitch;
+    } else {
+      s.X[JM][0] = s.X[JM][1] = zero2();
+    }
+  }
+
+  // ---- stages L .. 1 (reverse order: each reads the row its producer finished LAST step) ----
 #pragma unroll
   for (int k = L; k >= 1; --k) {
     const int rk = it - 1 - 2 * k;
-    f2 h0, h1;
-    conv_feed(s.rb[k - 1], p.w[k - 1], s.acc[k - 1], h0, h1);
+    f2 (&fin)[2] = s.A[k - 1][JF];
+    if (k == 1) conv_feed(s.r0c[0], s.r0c[1], s.r0l, s.r0r, p.w[0], fin, s.A[0][JM], s.A[0][JT]);
+    else conv_feed(s.A[k - 2][JT][0], s.A[k - 2][JT][1], s.rl[k - 2], s.rr[k - 2], p.w[k - 1], fin, s.A[k - 1][JM],
+                   s.A[k - 1][JT]);
     if (k == L) {
-      if (rk >= x.i0 && rk < x.i1) {
-        f2 o0, o1;
-        if (STEADY || (rk >= 1 && rk <= N - 2)) {
-          float4 yv = *reinterpret_cast<const float4 *>(x.delay + roff);
-          o0 = act_t<ACT>(add2(make_float2(yv.x, yv.y), h0));
-          o1 = act_t<ACT>(add2(make_float2(yv.z, yv.w), h1));
+      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+        float o0, o1, o2, o3;  // columns c0..c3
+        if (MAIN || (rk >= 1 && rk <= N - 2)) {
+          // delay slot = (y.c0, y.c2, y.c1, y.c3): the register pairs of stage 0, stored as they are
+          const float4 yv = *reinterpret_cast<const float4 *>(x.delay + roff);
+          o0 = add_act<ACT>(yv.x, lo(fin[0]));
+          o2 = add_act<ACT>(yv.y, hi(fin[0]));
+          o1 = add_act<ACT>(yv.z, lo(fin[1]));
+          o3 = add_act<ACT>(yv.w, hi(fin[1]));
         } else {
-          o0 = o1 = bc2(rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+          o0 = o1 = o2 = o3 = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
         }
         if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value
-          o0.x = sel_bits(o0.x, x.keep[0], x.gval[0]);
-          o1.x = sel_bits(o1.x, x.keep[1], x.gval[1]);
-          o0.y = sel_bits(o0.y, x.keep[2], x.gval[2]);
-          o1.y = sel_bits(o1.y, x.keep[3], x.gval[3]);
+          o0 = sel_bits(o0, x.keep[0], x.gval[0]);
+          o1 = sel_bits(o1, x.keep[1], x.gval[1]);
+          o2 = sel_bits(o2, x.keep[2], x.gval[2]);
+          o3 = sel_bits(o3, x.keep[3], x.gval[3]);
         }
-        store_row(x.pout, x.store, o0, o1);
+        store_cols(x.pout, out_perm, x.st_ok, EDGE ? x.store : 15u, o0, o1, o2, o3);
       }
-      if (STEADY || rk >= 0) x.pout += x.out_pitch;  // invariant: pout points at row max(rk, 0)
+      if (MAIN || rk >= 0) x.pout += x.out_pitch;  // invariant: pout points at row max(rk, 0)
     } else {
-      if (!STEADY && !(rk >= 1 && rk <= N - 2)) h0 = h1 = zero2();
+      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = zero2();
       if (EDGE) {
-        h0.x = and_bits(h0.x, x.keep[0]);
-        h1.x = and_bits(h1.x, x.keep[1]);
-        h0.y = and_bits(h0.y, x.keep[2]);
-        h1.y = and_bits(h1.y, x.keep[3]);
+        fin[0] = and2(fin[0], x.keep[0], x.keep[2]);
+        fin[1] = and2(fin[1], x.keep[1], x.keep[3]);
       }
-      s.rb[k][1] = h0;
-      s.rb[k][2] = h1;
-      exchange_halo_ctx(s.rb[k], x);
+      halo_scalars(fin[0], fin[1], x.lane_l, x.lane_r, s.rl[k - 1], s.rr[k - 1]);
     }
   }
 
@@ -392,135 +468,121 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
   {
     const int r0 = it - 1;
     const f2 q = bc2(0.25f);
-    f2 y0 = fma2(q, s.xb[0], s.yu[0]);  // taps: up (in yu), left, right, down
-    y0 = fma2(q, s.xb[2], y0);
-    y0 = fma2(q, pf[0], y0);
-    f2 y1 = fma2(q, s.xb[1], s.yu[1]);
-    y1 = fma2(q, s.xb[3], y1);
-    y1 = fma2(q, pf[1], y1);
+    f2 y0 = fma_lohi(0.25f, s.xhl, lo(C[1]), s.yu[0]);  // taps: up (in yu), left, right, down
+    y0 = fma2(q, C[1], y0);
+    y0 = fma2(q, D[0], y0);
+    f2 y1 = fma2(q, C[0], s.yu[1]);
+    y1 = fma_lohi(0.25f, hi(C[0]), s.xhr, y1);
+    y1 = fma2(q, D[1], y1);
     if (HASF) {
-      y0 = sub2(y0, pff[0]);
-      y1 = sub2(y1, pff[1]);
+      y0 = sub2(y0, s.pff[0]);
+      y1 = sub2(y1, s.pff[1]);
+      const int nf = it;  // f row used by the stage 0 of the next step
+      if (MAIN || (nf <= x.x_last && nf >= 1 && nf <= N - 2)) {
+        load_row(x.pfin, f_perm, ld_ok, EDGE ? x.in_img : 15u, s.pff[0], s.pff[1]);
+      } else {
+        s.pff[0] = s.pff[1] = zero2();
+      }
+      if (L2_AHEAD > 0 && nf + L2_AHEAD <= x.x_last)
+        prefetch_row(x.pfin + (size_t)L2_AHEAD * x.f_pitch, x.lane, EDGE ? x.in_img : 15u);
+      x.pfin += x.f_pitch;
     }
-    f2 q0 = sub2(y0, s.xb[1]);
-    f2 q1 = sub2(y1, s.xb[2]);
-    if (!STEADY && !(r0 >= 1 && r0 <= N - 2)) q0 = q1 = zero2();
+    f2 q0 = sub2(y0, C[0]);
+    f2 q1 = sub2(y1, C[1]);
+    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) q0 = q1 = zero2();
     if (EDGE) {
-      q0.x = and_bits(q0.x, x.keep[0]);
-      q1.x = and_bits(q1.x, x.keep[1]);
-      q0.y = and_bits(q0.y, x.keep[2]);
-      q1.y = and_bits(q1.y, x.keep[3]);
+      q0 = and2(q0, x.keep[0], x.keep[2]);
+      q1 = and2(q1, x.keep[1], x.keep[3]);
     }
-    *reinterpret_cast<float4 *>(x.delay + woff) = make_float4(y0.x, y0.y, y1.x, y1.y);
-    s.yu[0] = mul2(q, s.xb[1]);  // first tap of the next output row (row it): up = x[it-1]
-    s.yu[1] = mul2(q, s.xb[2]);
-    s.rb[0][1] = q0;
-    s.rb[0][2] = q1;
-    exchange_halo_ctx(s.rb[0], x);
-    s.xb[1] = pf[0];
-    s.xb[2] = pf[1];
-    exchange_halo_ctx(s.xb, x);
-  }
-
-  // ---- refill this parity's buffers: x row it+2 and f row it+1 (consumed two steps from now) ----
-  {
-    const int nx = it + 2;
-    if (nx <= x.x_last) {
-      if (EDGE) {
-        pf[0].x = (x.in_img & 1u) ? __ldg(x.pin) : 0.0f;
-        pf[1].x = (x.in_img & 2u) ? __ldg(x.pin + 1) : 0.0f;
-        pf[0].y = (x.in_img & 4u) ? __ldg(x.pin + HALF) : 0.0f;
-        pf[1].y = (x.in_img & 8u) ? __ldg(x.pin + HALF + 1) : 0.0f;
-      } else {
-        load_row_full(x.pin, pf[0], pf[1]);
-      }
-      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
-        prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, EDGE ? x.in_img : 15u);
-      x.pin += x.in_pitch;
-    } else {
-      pf[0] = pf[1] = zero2();
-    }
-    if (HASF) {
-      const int nf = it + 1;  // f row used by the stage 0 of step it+2
-      if (nf <= x.x_last && (STEADY || (nf >= 1 && nf <= N - 2))) {
-        if (EDGE) {
-          pff[0].x = (x.in_img & 1u) ? __ldg(x.pfin) : 0.0f;
-          pff[1].x = (x.in_img & 2u) ? __ldg(x.pfin + 1) : 0.0f;
-          pff[0].y = (x.in_img & 4u) ? __ldg(x.pfin + HALF) : 0.0f;
-          pff[1].y = (x.in_img & 8u) ? __ldg(x.pfin + HALF + 1) : 0.0f;
-        } else {
-          load_row_full(x.pfin, pff[0], pff[1]);
-        }
-      } else {
-        pff[0] = pff[1] = zero2();
-      }
-      if (L2_AHEAD > 0 && nf + L2_AHEAD <= x.x_last) prefetch_row(x.pfin + (size_t)L2_AHEAD * N, EDGE ? x.in_img : 15u);
-      x.pfin += N;
-    }
+    // two 64-bit stores: y0 and y1 stay independent register pairs (a 128-bit store would need
+    // them in one aligned quad and costs four register moves)
+    *reinterpret_cast<f2 *>(x.delay + woff) = y0;
+    *reinterpret_cast<f2 *>(x.delay + woff + 8) = y1;
+    s.yu[0] = mul2(q, C[0]);  // first tap of the next output row (row it): up = x[it-1]
+    s.yu[1] = mul2(q, C[1]);
+    s.r0c[0] = q0;
+    s.r0c[1] = q1;
+    halo_scalars(q0, q1, x.lane_l, x.lane_r, s.r0l, s.r0r);
+    halo_scalars(D[0], D[1], x.lane_l, x.lane_r, s.xhl, s.xhr);  // row `it` is the next centre row
   }
   woff = (woff + 512u) & RING;
 }
 
-template <int L, int ACT, bool HASF>
+// three consecutive steps = one period of the slot rotation
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM>
+__device__ __forceinline__ void conv_three(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
+                                           int it_last, unsigned &woff) {
+  conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 0>(s, x, p, it, woff);
+  if (MAIN || it + 1 <= it_last) conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 1>(s, x, p, it + 1, woff);
+  if (MAIN || it + 2 <= it_last) conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 2>(s, x, p, it + 2, woff);
+}
+
 #ifndef NPDE_CONV_MIN_CTAS
 #define NPDE_CONV_MIN_CTAS 16
 #endif
+template <int L, int ACT, bool HASF>
 __global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_CONV_MIN_CTAS)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
-  constexpr int RC = (R + 1) & ~1;   // column halo (even)
+  constexpr int RC = (R + 3) & ~3;   // column halo: whole lanes
   constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
-  NPDE_DYN_SMEM(float4, ydl);        // [warp][DS][32]: per-lane private slots
+  NPDE_DYN_SMEM(float4, ydl);        // [DS][32]: per-lane private slots
 
   StripItem item;
-  if (!decode_item(p.B, p.strips, p.bands, item)) return;
+  if (!decode_item(p.B, p.N, p.split, item)) return;
   ConvLaneCtx x;
   const int lane = threadIdx.x & 31;
+  x.lane = lane;
   x.lane_l = (lane + 31) & 31;
   x.lane_r = (lane + 1) & 31;
-  x.first = lane == 0;
-  x.last = lane == 31;
   x.delay = reinterpret_cast<char *>(ydl + lane);
   x.N = p.N;
   const int N = p.N;
-  const int vs = item.strip * p.wv, ve = min(vs + p.wv, N);
+  const int vs = item.strip * p.split.wv, ve = min(vs + p.split.wv, N);
   const int cs = vs - RC;
   const LaneCols c = make_cols(cs, lane, N, vs, ve);
   x.in_img = c.in_img;
   x.store = c.store;
   pin_reg(x.in_img);
   pin_reg(x.store);
-  x.i0 = item.band * p.band_rows;
-  x.i1 = min(x.i0 + p.band_rows, N);
+  x.in_perm = p.in_perm != 0;
+  x.out_perm = p.out_perm != 0;
+  x.f_perm = p.f_perm != 0;
+  x.ld_ok = c.c0 >= 0 && c.c0 < N;  // c0 is a multiple of 4 and a permuted pitch is >= round_up(N, 4)
+  x.st_ok = c.store != 0u;          // strip ranges are multiples of 4: a lane stores all of its columns or none
+  x.i0 = item.i0;
+  x.i1 = item.i1;
   x.in_pitch = p.in_pitch;
   x.out_pitch = p.out_pitch;
+  x.f_pitch = p.f_pitch;
   const float *bcb = p.bc4 + (size_t)item.b * 4;
   x.top = __ldg(bcb + 0);
   x.bottom = __ldg(bcb + 1);
   const float left = __ldg(bcb + 2), right = __ldg(bcb + 3);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const int col = ((q & 2) ? c.colB : c.colA) + (q & 1);
+    const int col = c.c0 + q;
     x.keep[q] = (c.interior >> q & 1u) ? 0xffffffffu : 0u;
     x.gval[q] = col == 0 ? __float_as_uint(left) : (col == N - 1 ? __float_as_uint(right) : 0u);
     pin_reg(x.keep[q]);
     pin_reg(x.gval[q]);
   }
   // the strip needs the EDGE code iff one of its 128 columns is not an interior column
-  const bool edge_strip = cs < 1 || cs + STRIP - 1 > N - 2;
+  const bool edge_strip = strip_is_edge(item.strip, p.split.wv, RC, N);
+  const bool all_perm = x.in_perm && x.out_perm && (!HASF || x.f_perm);
 
   ConvState<L> s;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    s.xb[q] = zero2();
+  for (int h = 0; h < 3; ++h) s.X[h][0] = s.X[h][1] = zero2();
 #pragma unroll
-    for (int k = 0; k < L; ++k) s.rb[k][q] = zero2();
+  for (int h = 0; h < 2; ++h) s.yu[h] = s.r0c[h] = s.pff[h] = zero2();
+  s.xhl = s.xhr = s.r0l = s.r0r = 0.0f;
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    s.rl[k] = s.rr[k] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s.A[k][j][0] = s.A[k][j][1] = zero2();
   }
-#pragma unroll
-  for (int k = 0; k < L; ++k) s.acc[k].mid[0] = s.acc[k].mid[1] = s.acc[k].top[0] = s.acc[k].top[1] = zero2();
-  s.yu[0] = s.yu[1] = zero2();
-#pragma unroll
-  for (int h = 0; h < 2; ++h) s.pf[h][0] = s.pf[h][1] = s.pff[h][0] = s.pff[h][1] = zero2();
 #pragma unroll
   for (int d = 0; d < DS; ++d) *reinterpret_cast<float4 *>(x.delay + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -528,47 +590,38 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   const int it_first = max(x.i0 - R, 0);  // rows above the grid are zeros == the initial state
   const int it_last = x.i1 + 2 * L;
   x.x_last = min(x.i1 - 1 + R, N - 1);    // last input row that exists and matters
-  const float *xin = p.in + (size_t)item.b * p.in_bstride;
-  const float *fimg = HASF ? p.f + (size_t)item.b * N * N : nullptr;
-  // buffers of parity 0 / 1 hold rows it_first / it_first+1 (f: one row behind)
-  load_row(xin + (size_t)it_first * p.in_pitch, c, s.pf[0][0], s.pf[0][1]);
-  if (it_first + 1 <= x.x_last) load_row(xin + (size_t)(it_first + 1) * p.in_pitch, c, s.pf[1][0], s.pf[1][1]);
-  if (HASF) {
-    if (it_first - 1 >= 1) load_row(fimg + (size_t)(it_first - 1) * N, c, s.pff[0][0], s.pff[0][1]);
-    if (it_first >= 1 && it_first <= N - 2) load_row(fimg + (size_t)it_first * N, c, s.pff[1][0], s.pff[1][1]);
-  }
-  // running pointers: pin -> row it+2 of x, pfin -> row it+1 of f, pout -> output row it-1-2L (clamped at 0)
-  x.pin = xin + (size_t)(it_first + 2) * p.in_pitch + c.colA;
-  x.pfin = HASF ? fimg + (size_t)(it_first + 1) * N + c.colA : nullptr;
-  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.colA;
+  const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
+  const float *fimg = HASF ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
+  // slot 0 receives row it_first (the first step runs with J = 0); f: one row behind
+  load_row(xin + (size_t)it_first * p.in_pitch, x.in_perm, x.ld_ok, c.in_img, s.X[0][0], s.X[0][1]);
+  if (HASF && it_first - 1 >= 1)
+    load_row(fimg + (size_t)(it_first - 1) * p.f_pitch, x.f_perm, x.ld_ok, c.in_img, s.pff[0], s.pff[1]);
+  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-2L (clamped at 0)
+  x.pin = xin + (size_t)(it_first + 1) * p.in_pitch;
+  x.pfin = HASF ? fimg + (size_t)it_first * p.f_pitch : nullptr;
+  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.c0;
   unsigned woff = 0;
 
-  // steady range of `it`: all stage rows it-1-2L .. it-1 are interior rows (and so is f row it+1)
-  const int steady_lo = 2 + 2 * L;
-  const int steady_hi = min(N - 3, it_last);
+  // MAIN range of `it`: stage rows it-1-2L .. it-1 interior, output row it-1-2L inside the band,
+  // x row it+1 exists and f row `it` is an interior row
+  const int main_lo = max(2 + 2 * L, x.i0 + 1 + 2 * L);
+  const int main_hi = min(N - 2, x.x_last - 1);
   int it = it_first;
   while (it <= it_last) {
-    // parity bookkeeping: steps alternate buffer 0,1 starting with 0 at it_first
-    if (((it - it_first) & 1) == 0 && it >= steady_lo && it + 1 <= steady_hi) {
-      if (edge_strip) {
-        do {
-          conv_step<L, ACT, HASF, true, true, 0>(s, x, p, it, woff);
-          conv_step<L, ACT, HASF, true, true, 1>(s, x, p, it + 1, woff);
-          it += 2;
-        } while (it + 1 <= steady_hi);
-      } else {
-        do {
-          conv_step<L, ACT, HASF, true, false, 0>(s, x, p, it, woff);
-          conv_step<L, ACT, HASF, true, false, 1>(s, x, p, it + 1, woff);
-          it += 2;
-        } while (it + 1 <= steady_hi);
-      }
-    } else if (((it - it_first) & 1) == 0) {
-      conv_step<L, ACT, HASF, false, true, 0>(s, x, p, it, woff);
-      ++it;
+    if (it >= main_lo && it + 2 <= main_hi) {
+      // the fast loops iterate in place: the register assignment of a variant is set up once per band
+#define NPDE_MAIN_LOOP(EDGE_, PERM_)                                              \
+  do {                                                                            \
+    conv_three<L, ACT, HASF, true, EDGE_, PERM_>(s, x, p, it, it_last, woff);     \
+    it += 3;                                                                      \
+  } while (it + 2 <= main_hi)
+      if (!all_perm) NPDE_MAIN_LOOP(true, false);
+      else if (edge_strip) NPDE_MAIN_LOOP(true, true);
+      else NPDE_MAIN_LOOP(false, true);
+#undef NPDE_MAIN_LOOP
     } else {
-      conv_step<L, ACT, HASF, false, true, 1>(s, x, p, it, woff);
-      ++it;
+      conv_three<L, ACT, HASF, false, true, false>(s, x, p, it, it_last, woff);
+      it += 3;
     }
   }
 }
@@ -577,39 +630,49 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
 struct JacobiStreamParams {
   const float *in;
   float *out;
-  const float *f;    // reference layout (pitch N) or NULL; only with T == 1
+  const float *f;    // NULL, or the source (only with T == 1)
   const float *bc4;  // (B,4)
-  long in_bstride, out_bstride;
-  int in_pitch, out_pitch;
+  long in_bstride, out_bstride, f_bstride;
+  int in_pitch, out_pitch, f_pitch;
+  int in_perm, out_perm, f_perm;  // field is in the pair-permuted padded layout (128-bit accesses)
   int B, N;
-  int strips, bands, band_rows, wv;
+  Split split;
 };
 
 template <int T>
 __global__ void __launch_bounds__(npde::STREAM_THREADS)
 k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
-  constexpr int RC = (T + 1) & ~1;
+  constexpr int RC = (T + 3) & ~3;  // column halo: whole lanes
   StripItem item;
-  if (!decode_item(p.B, p.strips, p.bands, item)) return;
+  if (!decode_item(p.B, p.N, p.split, item)) return;
   const int lane = threadIdx.x & 31;
+  const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
   const int N = p.N;
-  const int vs = item.strip * p.wv, ve = min(vs + p.wv, N);
+  const int vs = item.strip * p.split.wv, ve = min(vs + p.split.wv, N);
   const LaneCols c = make_cols(vs - RC, lane, N, vs, ve);
-  const int i0 = item.band * p.band_rows, i1 = min(i0 + p.band_rows, N);
-  const float *xin = p.in + (size_t)item.b * p.in_bstride;
-  float *xout = p.out + (size_t)item.b * p.out_bstride;
-  const float *fin = (T == 1 && p.f) ? p.f + (size_t)item.b * N * N : nullptr;
+  const int i0 = item.i0, i1 = item.i1;
+  const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
+  float *xout = p.out + (size_t)item.b * p.out_bstride + c.c0;
+  const float *fin = (T == 1 && p.f) ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
   const float *bcb = p.bc4 + (size_t)item.b * 4;
   const float top = __ldg(bcb + 0), bottom = __ldg(bcb + 1), left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+  // permuted layout: a lane whose first column exists moves its whole group of four; the pad
+  // columns it then touches only feed ring / out-of-grid cells and are rewritten by G or ignored
+  const bool in_perm = p.in_perm != 0, out_perm = p.out_perm != 0, f_perm = p.f_perm != 0;
+  const bool ld_ok = c.c0 >= 0 && c.c0 < N;
+  const bool st_ok = c.store != 0u;
 
-  // win[0] = x, win[s] = iterate after s steps (s < T); rows of step t, t-1, t-2
-  f2 win[T][3][4];
+  // win[0] = x, win[s] = iterate after s steps (s < T); rows of step t, t-1, t-2 (centre pairs
+  // and outer neighbours)
+  f2 win[T][3][2];
+  float wl[T][3], wr[T][3];
 #pragma unroll
   for (int s = 0; s < T; ++s)
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) win[s][r][q] = zero2();
+    for (int r = 0; r < 3; ++r) {
+      win[s][r][0] = win[s][r][1] = zero2();
+      wl[s][r] = wr[s][r] = 0.0f;
+    }
 
   // input rows it; stage s (1..T) produces row it - s in the same step (forward
   // order: the 5-point stencil needs no halo on its newest row)
@@ -618,21 +681,22 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const int x_last = min(it_last, N - 1);
   f2 pf[2], pff[2];
   pf[0] = pf[1] = pff[0] = pff[1] = zero2();
-  load_row(xin + (size_t)it_first * p.in_pitch, c, pf[0], pf[1]);
-  if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * N, c, pff[0], pff[1]);
+  load_row(xin + (size_t)it_first * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
+  if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
 
   for (int it_base = it_first; it_base <= it_last; it_base += 3) {
 #pragma unroll
     for (int ph = 0; ph < 3; ++ph) {
       const int it = it_base + ph;
       const int s_new = ph, s_m1 = (ph + 2) % 3, s_m2 = (ph + 1) % 3;
-      win[0][s_new][1] = pf[0];
-      win[0][s_new][2] = pf[1];
+      win[0][s_new][0] = pf[0];
+      win[0][s_new][1] = pf[1];
 #pragma unroll
       for (int s = 1; s <= T; ++s) {
         const int row = it - s;
-        f2 o0 = psi2(win[s - 1][s_m2][1], win[s - 1][s_m1][0], win[s - 1][s_m1][2], win[s - 1][s_new][1]);
-        f2 o1 = psi2(win[s - 1][s_m2][2], win[s - 1][s_m1][1], win[s - 1][s_m1][3], win[s - 1][s_new][2]);
+        f2 o0, o1;
+        psi_row(win[s - 1][s_m2][0], win[s - 1][s_m2][1], win[s - 1][s_m1][0], win[s - 1][s_m1][1],
+                wl[s - 1][s_m1], wr[s - 1][s_m1], win[s - 1][s_new][0], win[s - 1][s_new][1], o0, o1);
         if (T == 1 && fin) {
           o0 = sub2(o0, pff[0]);
           o1 = sub2(o1, pff[1]);
@@ -641,44 +705,43 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
         if (s < T) {
           // rows above/below the grid must read as zero padding for the next stage's ring
           // cells only, and those are overwritten by G: no masking needed.
-          win[s < T ? s : 0][s_new][1] = o0;
-          win[s < T ? s : 0][s_new][2] = o1;
+          win[s < T ? s : 0][s_new][0] = o0;
+          win[s < T ? s : 0][s_new][1] = o1;
         } else if (row >= i0 && row < i1) {
-          store_row(xout + (size_t)row * p.out_pitch + c.colA, c.store, o0, o1);
+          store_row(xout + (size_t)row * p.out_pitch, out_perm, st_ok, c.store, o0, o1);
         }
       }
 #pragma unroll
-      for (int s = 0; s < T; ++s) exchange_halo(win[s][s_new], lane);
+      for (int s = 0; s < T; ++s)
+        halo_scalars(win[s][s_new][0], win[s][s_new][1], lane_l, lane_r, wl[s][s_new], wr[s][s_new]);
 
       const int nx = it + 1;
       if (nx <= x_last) {
-        load_row(xin + (size_t)nx * p.in_pitch, c, pf[0], pf[1]);
+        load_row(xin + (size_t)nx * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
       } else {
         pf[0] = pf[1] = zero2();
       }
       if (T == 1 && fin) {  // next step's output row is `it`
-        if (it <= N - 1) load_row(fin + (size_t)it * N, c, pff[0], pff[1]);
-        if (it + L2_AHEAD <= x_last) prefetch_row(fin + (size_t)(it + L2_AHEAD) * N + c.colA, c.in_img);
+        if (it <= N - 1) load_row(fin + (size_t)it * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
+        if (L2_AHEAD > 0 && it + L2_AHEAD <= x_last)
+          prefetch_row(fin + (size_t)(it + L2_AHEAD) * p.f_pitch, lane, c.in_img);
       }
-      if (nx + L2_AHEAD <= x_last) prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch + c.colA, c.in_img);
+      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x_last)
+        prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch, lane, c.in_img);
     }
   }
 }
 
 // ------------------------------------------------------------- host side ---
-// Work split: B * strips * bands warp items.  Bands exist only to fill the
-// machine when B * strips is small; every band re-streams 2R halo rows.
-struct Split {
-  int strips, bands, band_rows, wv;
-};
-
+// Bands exist only to fill the machine when B * strips is small; every band re-streams
+// 2 * halo_rows rows and pays the pipeline fill, so bands are kept >= 8 * halo_rows rows long.
 Split make_split(int B, int N, int halo_cols, int halo_rows, int resident_warps) {
   Split s;
   s.wv = STRIP - 2 * halo_cols;
   s.strips = (N + s.wv - 1) / s.wv;
   long per_band = (long)B * s.strips;
   int bands = (int)(resident_warps / (per_band > 0 ? per_band : 1));
-  int max_bands = N / (8 * (halo_rows > 0 ? halo_rows : 1));  // keep the halo re-streaming <= 25%
+  int max_bands = N / (8 * (halo_rows > 0 ? halo_rows : 1));
   if (bands > max_bands) bands = max_bands;
   if (bands < 1) bands = 1;
   s.band_rows = (N + bands - 1) / bands;
@@ -713,33 +776,34 @@ int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaS
 
 template <int L>
 int launch_conv(ConvStreamParams &p, cudaStream_t st) {
-  constexpr int R = L + 1, RC = (R + 1) & ~1, DS = (2 * L + 1 <= 8) ? 8 : 16;
+  constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (2 * L + 1 <= 8) ? 8 : 16;
   const size_t smem = sizeof(float4) * DS * 32 * (npde::STREAM_THREADS / 32);
   static int cache = 0;
   int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache);
-  Split s = make_split(p.B, p.N, RC, R, resident);
-  p.strips = s.strips; p.bands = s.bands; p.band_rows = s.band_rows; p.wv = s.wv;
-  long items = (long)p.B * s.strips * s.bands;
-  const int wpb = npde::STREAM_THREADS / 32;
-  dim3 grid((unsigned)((items + wpb - 1) / wpb)), block(npde::STREAM_THREADS);
+  p.split = make_split(p.B, p.N, RC, R, resident);
+  dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
+#ifdef NPDE_DEV_ONLY_CONV3  // tools/ab_bench.py: quick-to-compile tuning builds, clamp / no source only
+  if (p.act != NPDE_ACT_CLAMP || p.f) return NPDE_ERR_ARG;
+  NPDE_LAUNCH((k_conv_stream<L, NPDE_ACT_CLAMP, false>), grid, block, smem, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+#else
   switch (p.act) {
     case NPDE_ACT_NONE: return launch_conv_f<L, NPDE_ACT_NONE>(p, grid, block, smem, st);
     case NPDE_ACT_CLAMP: return launch_conv_f<L, NPDE_ACT_CLAMP>(p, grid, block, smem, st);
     case NPDE_ACT_SIGMOID: return launch_conv_f<L, NPDE_ACT_SIGMOID>(p, grid, block, smem, st);
     default: return NPDE_ERR_ACT;
   }
+#endif
 }
 
 template <int T>
 int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
-  constexpr int RC = (T + 1) & ~1;
+  constexpr int RC = (T + 3) & ~3;
   static int cache = 0;
   int resident = resident_warps_cached((const void *)k_jacobi_stream<T>, 0, &cache);
-  Split s = make_split(p.B, p.N, RC, T, resident);
-  p.strips = s.strips; p.bands = s.bands; p.band_rows = s.band_rows; p.wv = s.wv;
-  long items = (long)p.B * s.strips * s.bands;
-  const int wpb = npde::STREAM_THREADS / 32;
-  dim3 grid((unsigned)((items + wpb - 1) / wpb)), block(npde::STREAM_THREADS);
+  p.split = make_split(p.B, p.N, RC, T, resident);
+  dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
   NPDE_LAUNCH((k_jacobi_stream<T>), grid, block, 0, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
@@ -753,37 +817,57 @@ bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host) {
   return bc_kind == NPDE_BC_SQUARE && n_layers >= 1 && n_layers <= 4 && w_host != nullptr;
 }
 
-int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, const float *w_host,
-                int n_layers, int act, int B, int N, cudaStream_t st) {
+// the pair-permuted layout needs 16-byte aligned rows and room for a whole lane at the right edge
+static bool perm_ok(const void *p, int pitch, long bstride, int perm, int N) {
+  if (!p || !perm) return true;
+  return ((uintptr_t)p & 15) == 0 && (pitch & 3) == 0 && (bstride & 3) == 0 && pitch >= ((N + 3) & ~3);
+}
+
+int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f,
+                const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st) {
   ConvStreamParams p;
   p.in = in.p; p.in_pitch = in.pitch; p.in_bstride = in.bstride;
   p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride;
-  p.f = f; p.bc4 = bc4; p.B = B; p.N = N; p.act = act;
+  p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride;
+  p.bc4 = bc4; p.B = B; p.N = N; p.act = act;
+  p.in_perm = in.perm; p.out_perm = out.perm; p.f_perm = f.p ? f.perm : 0;
+  if (!perm_ok(in.p, in.pitch, in.bstride, in.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
+      !perm_ok(f.p, f.pitch, f.bstride, f.perm, N))
+    return NPDE_ERR_ARG;
   for (int l = 0; l < 4; ++l)
     for (int t = 0; t < 9; ++t) p.w[l][t] = (l < n_layers) ? w_host[l * 9 + t] : 0.0f;
   switch (n_layers) {
+#ifndef NPDE_DEV_ONLY_CONV3
     case 1: return launch_conv<1>(p, st);
     case 2: return launch_conv<2>(p, st);
-    case 3: return launch_conv<3>(p, st);
     case 4: return launch_conv<4>(p, st);
+#endif
+    case 3: return launch_conv<3>(p, st);
     default: return NPDE_ERR_LAYERS;
   }
 }
 
 int jacobi_stream_max_depth(const float *f) { return f ? 1 : 8; }
 
-int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const float *f, int depth, int B,
-                  int N, cudaStream_t st) {
+int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f, int depth,
+                  int B, int N, cudaStream_t st) {
   JacobiStreamParams p;
   p.in = in.p; p.in_pitch = in.pitch; p.in_bstride = in.bstride;
   p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride;
-  p.f = f; p.bc4 = bc4; p.B = B; p.N = N;
-  if (f && depth != 1) return NPDE_ERR_ARG;
+  p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride;
+  p.bc4 = bc4; p.B = B; p.N = N;
+  p.in_perm = in.perm; p.out_perm = out.perm; p.f_perm = f.p ? f.perm : 0;
+  if (!perm_ok(in.p, in.pitch, in.bstride, in.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
+      !perm_ok(f.p, f.pitch, f.bstride, f.perm, N))
+    return NPDE_ERR_ARG;
+  if (f.p && depth != 1) return NPDE_ERR_ARG;
   switch (depth) {
     case 1: return launch_jacobi<1>(p, st);
+#ifndef NPDE_DEV_ONLY_CONV3
     case 2: return launch_jacobi<2>(p, st);
     case 4: return launch_jacobi<4>(p, st);
     case 8: return launch_jacobi<8>(p, st);
+#endif
     default: return NPDE_ERR_ARG;
   }
 }

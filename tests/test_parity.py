@@ -156,6 +156,38 @@ def test_constant_field_is_fixed_point(be):
             assert_bitwise(be.n(it(x, bc, None)), be.n(x), it.name())
 
 
+# --------------------------------------------- work partition of the stream kernels --
+@pytest.mark.parametrize("B,N,L,has_f", [(3, 129, 3, False), (5, 65, 2, True), (2, 257, 3, True), (3, 65, 4, False),
+                                         (1, 257, 1, False), (7, 33, 3, True)])
+def test_stream_partition_vs_oracle(be, oracle, B, N, L, has_f):
+    """Odd batch sizes, several strips per image and several bands per strip (npde_stream.cu make_split).
+    k-step loops (pair-permuted internal buffers, 128-bit accesses) and single steps (reference layout)
+    against the CPU oracle, bit for bit."""
+    rng = np.random.RandomState(B * 1000 + N + L)
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", L)
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    with torch.no_grad():
+        y1 = it(xd, bcd, fd)
+        y5, _, _ = it.iterate(xd, bcd, fd, 5)
+        j1 = be.npde.JacobiIterator()(xd, bcd, fd)
+        j11, _, _ = be.npde.JacobiIterator().iterate(xd, bcd, fd, 11)
+    assert_bitwise(be.n(y1), oracle.conv_step(x, bc, f, w, "clamp"), "conv step")
+    assert_bitwise(be.n(y5), oracle.iterate("conv", x, bc, f, w, "clamp", 5)[0], "5 conv steps")
+    assert_bitwise(be.n(j1), oracle.fd_step(x, bc, f), "jacobi step")
+    assert_bitwise(be.n(j11), oracle.iterate("jacobi", x, bc, f, None, "none", 11)[0], "11 jacobi steps")
+
+
 # ------------------------------------------------------------ Multigrid / UNet --
 @pytest.mark.parametrize("name", golden_names("mg_"))
 def test_multigrid_iterator(be, name):
