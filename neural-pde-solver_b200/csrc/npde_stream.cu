@@ -62,6 +62,10 @@ __device__ __forceinline__ void ld_pairs(const float *p, f2 &a, f2 &b) {
 __device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
   p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
 }
+// asynchronous 16-byte global -> shared copy and its group bookkeeping: synchronous in the emulator
+__device__ __forceinline__ void cp_async16(void *smem, const float *g) { memcpy(smem, g, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() {}
 #else
 #define NPDE_GRID_CONSTANT __grid_constant__
 typedef unsigned long long f2;
@@ -110,6 +114,15 @@ __device__ __forceinline__ void ld_pairs(const float *p, f2 &a, f2 &b) {
 __device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
   *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b);
 }
+// cp.async (LDGSTS): 16 bytes per lane straight from L2 into shared memory, no register staging
+__device__ __forceinline__ void cp_async16(void *smem, const float *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
 #endif
 
 __device__ __forceinline__ f2 bc2(float s) { return mk2(s, s); }
@@ -129,6 +142,17 @@ constexpr int LANE_COLS = 4;
 #define NPDE_L2_AHEAD 4
 #endif
 constexpr int L2_AHEAD = NPDE_L2_AHEAD;  // rows of L2 prefetch distance (0: no prefetch instructions)
+#ifndef NPDE_RING
+#define NPDE_RING 8
+#endif
+// Rows of x kept in flight per warp by cp.async in the fast loops (a ring of 512-byte slots in
+// shared memory; RING_D - 1 rows are under way while one is consumed).  0: plain loads + L2 prefetch.
+constexpr int RING_D = NPDE_RING;
+static_assert((RING_D & (RING_D - 1)) == 0, "the ring size must be a power of two (slot offsets wrap with a mask)");
+#ifndef NPDE_RING_PF
+#define NPDE_RING_PF 0
+#endif
+constexpr int RING_PF = NPDE_RING_PF;  // additional L2 prefetch distance (rows beyond the ring), 0 = none
 
 // Column bookkeeping of one lane: bit q <-> column c0 + q
 // (bit0 = lo(Q0), bit1 = lo(Q1), bit2 = hi(Q0), bit3 = hi(Q1)).
@@ -337,29 +361,13 @@ __device__ __forceinline__ void conv_taps(f2 c0p, f2 c1p, float hl, float hr, fl
   a1 = fma2(bc2(wc), c1p, a1);
   a1 = fma_lohi(wr, hi(c0p), hr, a1);
 }
-__device__ __forceinline__ void conv_feed(f2 c0p, f2 c1p, float hl, float hr, const float *w, f2 (&fin)[2],
-                                          f2 (&mid)[2], f2 (&top)[2]) {
-  conv_taps(c0p, c1p, hl, hr, w[6], w[7], w[8], fin[0], fin[1]);
-  conv_taps(c0p, c1p, hl, hr, w[3], w[4], w[5], mid[0], mid[1]);
-  top[0] = mul_lohi(w[0], hl, lo(c1p));
-  top[0] = fma2(bc2(w[1]), c0p, top[0]);
-  top[0] = fma2(bc2(w[2]), c1p, top[0]);
-  top[1] = mul2(bc2(w[0]), c0p);
-  top[1] = fma2(bc2(w[1]), c1p, top[1]);
-  top[1] = fma_lohi(w[2], hi(c0p), hr, top[1]);
-}
-
 template <int L>
 struct ConvState {
-  f2 X[3][2];      // x rows, slot = row index modulo 3 (relative to the band): row `it` (loaded during the
-                   // previous step), row it-1 (centre row of Psi) and the slot the load of row it+1 fills
+  f2 X[2][2];      // X[P]: x row `it` (loaded during the previous step), X[P^1]: row it-1 (centre row of Psi)
   float xhl, xhr;  // outer neighbours of x row it-1
   f2 yu[2];        // 0.25 * x[it-2]: first tap of Psi for output row it-1
-  f2 r0c[2];       // the r_0 row stage 0 produced in the previous step
-  float r0l, r0r;  // ... and its outer neighbours
-  f2 A[L][3][2];   // A[k-1]: the three partial-sum rows of conv stage k; the row finished in the
-                   // previous step stays in its slot as the next stage's input
-  float rl[L], rr[L];  // rl/rr[k-1]: outer neighbours of the row stage k finished in the previous step
+  f2 S[L][2][2];   // S[k-1]: the two live partial-sum rows of conv stage k.  S[k-1][P] has seen taps
+                   // w0..w5 of its output row (this step finishes it), S[k-1][P^1] taps w0..w2.
   f2 pff[2];       // f row it-1, fetched one step earlier
 };
 
@@ -373,6 +381,8 @@ struct ConvLaneCtx {
   const float *pfin; // same for f
   float *pout;       // this lane's group of four in the output row of the current step
   char *delay;       // this lane's slot 0 of the y delay line (shared memory)
+  char *ring;        // this lane's 16 bytes in slot 0 of the x row ring (shared memory)
+  unsigned rslot;    // ring slot (byte offset) that holds x row it+1
   float top, bottom;
   int N, i0, i1, x_last, in_pitch, out_pitch, f_pitch, lane, lane_l, lane_r;
 };
@@ -386,86 +396,38 @@ __device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)
 __device__ __forceinline__ void pin_reg(unsigned &) {}
 #endif
 
-// One step: input row `it` has arrived in s.X[J].  Stage k (0..L) works on row it-1-2k.
-// MAIN:   every stage row (it-1-2k, k=0..L) is an interior row of the grid, the output row
+// One step: input row `it` has arrived in s.X[P].  Stage 0 (Psi, residual) works on row it-1 and
+// conv stage k (1..L) on row it-1-k, each consuming the row the previous stage produced in THIS
+// step, so no finished rows stay live across steps; latency between the stages is covered by
+// the other warps of the scheduler.
+// MAIN:   every stage row (it-1-k, k=0..L) is an interior row of the grid, the output row
 //         belongs to this band and the rows to fetch exist: no row tests at all.
 // !MAIN:  generic step (band warm-up / drain, ring rows): uniform row tests everywhere.
 // EDGE:   the strip contains ring or out-of-grid columns: loads are predicated per lane or
 //         column, stage outputs are masked to the interior columns and G fixes the ring columns.
 // PERM:   all fields are in the pair-permuted padded layout (128-bit accesses); otherwise the
 //         layout of each field is a run-time flag.
-// J:      step index modulo 3: roles of the partial-sum rows and of the x row slots.  Everything
-//         that rotates has period 3, so a 3x unrolled loop needs no register moves and its body
-//         (~370 instructions) stays inside the 6 KB L0 instruction cache.
-// DS = delay-line slots (power of two >= 2L+1), 512 bytes per slot and warp.
-template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM, int J>
+// P:      step parity.  The two x row slots and the two partial-sum rows of every stage swap
+//         roles each step, so a 2x unrolled loop needs no register moves and its body
+//         (~260 instructions) stays inside the 6 KB L0 instruction cache.
+// DS = delay-line slots (power of two >= L+1), 512 bytes per slot and warp.
+// RINGED: (fast loops on permuted fields only) x rows arrive through the cp.async ring.
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM, int P, bool RINGED = false>
 __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
                                           unsigned &woff) {
-  constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
   constexpr unsigned RING = DS * 512u - 1u;
-  constexpr int JF = J % 3, JM = (J + 1) % 3, JT = (J + 2) % 3;  // slots: finishing, continuing, starting
   const int N = x.N;
-  const unsigned roff = (woff + (DS - 2 * L) * 512u) & RING;  // y written 2L steps ago
+  const unsigned roff = (woff + (DS - L) * 512u) & RING;  // y written L steps ago
   const bool in_perm = PERM || x.in_perm, out_perm = PERM || x.out_perm, f_perm = PERM || x.f_perm;
   const bool ld_ok = !EDGE || x.ld_ok;
-  const f2 (&D)[2] = s.X[JF];  // row it: the Psi "down" tap now, the centre row of the next step
-  const f2 (&C)[2] = s.X[JT];  // centre row it-1
-
-  // ---- fetch x row it+1 into the slot that held row it-2 (consumed by the next step) ----
-  {
-    const int nx = it + 1;
-    if (MAIN || nx <= x.x_last) {
-      load_row(x.pin, in_perm, ld_ok, EDGE ? x.in_img : 15u, s.X[JM][0], s.X[JM][1]);
-      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
-        prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, x.lane, EDGE ? x.in_img : 15u);
-      x.pin += x.in_pitch;
-    } else {
-      s.X[JM][0] = s.X[JM][1] = zero2();
-    }
-  }
-
-  // ---- stages L .. 1 (reverse order: each reads the row its producer finished LAST step) ----
-#pragma unroll
-  for (int k = L; k >= 1; --k) {
-    const int rk = it - 1 - 2 * k;
-    f2 (&fin)[2] = s.A[k - 1][JF];
-    if (k == 1) conv_feed(s.r0c[0], s.r0c[1], s.r0l, s.r0r, p.w[0], fin, s.A[0][JM], s.A[0][JT]);
-    else conv_feed(s.A[k - 2][JT][0], s.A[k - 2][JT][1], s.rl[k - 2], s.rr[k - 2], p.w[k - 1], fin, s.A[k - 1][JM],
-                   s.A[k - 1][JT]);
-    if (k == L) {
-      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
-        float o0, o1, o2, o3;  // columns c0..c3
-        if (MAIN || (rk >= 1 && rk <= N - 2)) {
-          // delay slot = (y.c0, y.c2, y.c1, y.c3): the register pairs of stage 0, stored as they are
-          const float4 yv = *reinterpret_cast<const float4 *>(x.delay + roff);
-          o0 = add_act<ACT>(yv.x, lo(fin[0]));
-          o2 = add_act<ACT>(yv.y, hi(fin[0]));
-          o1 = add_act<ACT>(yv.z, lo(fin[1]));
-          o3 = add_act<ACT>(yv.w, hi(fin[1]));
-        } else {
-          o0 = o1 = o2 = o3 = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
-        }
-        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value
-          o0 = sel_bits(o0, x.keep[0], x.gval[0]);
-          o1 = sel_bits(o1, x.keep[1], x.gval[1]);
-          o2 = sel_bits(o2, x.keep[2], x.gval[2]);
-          o3 = sel_bits(o3, x.keep[3], x.gval[3]);
-        }
-        store_cols(x.pout, out_perm, x.st_ok, EDGE ? x.store : 15u, o0, o1, o2, o3);
-      }
-      if (MAIN || rk >= 0) x.pout += x.out_pitch;  // invariant: pout points at row max(rk, 0)
-    } else {
-      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = zero2();
-      if (EDGE) {
-        fin[0] = and2(fin[0], x.keep[0], x.keep[2]);
-        fin[1] = and2(fin[1], x.keep[1], x.keep[3]);
-      }
-      halo_scalars(fin[0], fin[1], x.lane_l, x.lane_r, s.rl[k - 1], s.rr[k - 1]);
-    }
-  }
+  f2 rc0, rc1;    // the row travelling down the stages: centre pairs ...
+  float rl, rr;   // ... and outer neighbours
 
   // ---- stage 0: y = Psi(x) - f and r_0 = y - x for row it-1 ------------------------------
   {
+    const f2 (&D)[2] = s.X[P];      // row it: the "down" tap
+    f2 (&C)[2] = s.X[P ^ 1];        // centre row it-1
     const int r0 = it - 1;
     const f2 q = bc2(0.25f);
     f2 y0 = fma_lohi(0.25f, s.xhl, lo(C[1]), s.yu[0]);  // taps: up (in yu), left, right, down
@@ -487,34 +449,101 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
         prefetch_row(x.pfin + (size_t)L2_AHEAD * x.f_pitch, x.lane, EDGE ? x.in_img : 15u);
       x.pfin += x.f_pitch;
     }
-    f2 q0 = sub2(y0, C[0]);
-    f2 q1 = sub2(y1, C[1]);
-    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) q0 = q1 = zero2();
+    rc0 = sub2(y0, C[0]);
+    rc1 = sub2(y1, C[1]);
+    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc0 = rc1 = zero2();
     if (EDGE) {
-      q0 = and2(q0, x.keep[0], x.keep[2]);
-      q1 = and2(q1, x.keep[1], x.keep[3]);
+      rc0 = and2(rc0, x.keep[0], x.keep[2]);
+      rc1 = and2(rc1, x.keep[1], x.keep[3]);
     }
-    // two 64-bit stores: y0 and y1 stay independent register pairs (a 128-bit store would need
-    // them in one aligned quad and costs four register moves)
+    halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
+    // y waits L steps in the delay line; the two pairs go to separate 256-byte halves of the slot so
+    // that they stay independent 64-bit stores (one 128-bit store would need them in one aligned quad)
     *reinterpret_cast<f2 *>(x.delay + woff) = y0;
-    *reinterpret_cast<f2 *>(x.delay + woff + 8) = y1;
+    *reinterpret_cast<f2 *>(x.delay + woff + 256) = y1;
     s.yu[0] = mul2(q, C[0]);  // first tap of the next output row (row it): up = x[it-1]
     s.yu[1] = mul2(q, C[1]);
-    s.r0c[0] = q0;
-    s.r0c[1] = q1;
-    halo_scalars(q0, q1, x.lane_l, x.lane_r, s.r0l, s.r0r);
     halo_scalars(D[0], D[1], x.lane_l, x.lane_r, s.xhl, s.xhr);  // row `it` is the next centre row
+    // ---- row it-1 is dead: fetch x row it+1 into its slot (consumed by the next step) ----
+    const int nx = it + 1;
+    if (RINGED) {
+      // x.pin points at row it + RING_D: start its copy into the slot that was read one step ago
+      constexpr unsigned RMASK = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
+      if (it + RING_D <= x.x_last) {
+        if (ld_ok) cp_async16(x.ring + ((x.rslot + (RING_D - 1) * 512u) & RMASK), x.pin);
+        if (RING_PF > 0 && it + RING_D + RING_PF <= x.x_last)
+          prefetch_row(x.pin + (size_t)RING_PF * x.in_pitch, x.lane, EDGE ? x.in_img : 15u);
+        x.pin += x.in_pitch;
+      }
+      cp_async_commit();
+    } else if (MAIN || nx <= x.x_last) {
+      load_row(x.pin, in_perm, ld_ok, EDGE ? x.in_img : 15u, C[0], C[1]);
+      if (L2_AHEAD > 0 && nx + L2_AHEAD <= x.x_last)  // never prefetch past the rows this band may read
+        prefetch_row(x.pin + (size_t)L2_AHEAD * x.in_pitch, x.lane, EDGE ? x.in_img : 15u);
+      x.pin += x.in_pitch;
+    } else {
+      C[0] = C[1] = zero2();
+    }
+  }
+
+  // ---- conv stages 1 .. L on rows it-2 .. it-1-L ------------------------------------------
+#pragma unroll
+  for (int k = 1; k <= L; ++k) {
+    const int rk = it - 1 - k;
+    const float *w = p.w[k - 1];
+    f2 (&mid)[2] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
+    f2 (&top)[2] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
+    f2 fin0 = mid[0], fin1 = mid[1];
+    conv_taps(rc0, rc1, rl, rr, w[6], w[7], w[8], fin0, fin1);
+    conv_taps(rc0, rc1, rl, rr, w[3], w[4], w[5], top[0], top[1]);  // becomes the "mid" row of the next step
+    mid[0] = mul_lohi(w[0], rl, lo(rc1));                            // fresh "top" row of the next step
+    mid[0] = fma2(bc2(w[1]), rc0, mid[0]);
+    mid[0] = fma2(bc2(w[2]), rc1, mid[0]);
+    mid[1] = mul2(bc2(w[0]), rc0);
+    mid[1] = fma2(bc2(w[1]), rc1, mid[1]);
+    mid[1] = fma_lohi(w[2], hi(rc0), rr, mid[1]);
+    if (k < L) {
+      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin0 = fin1 = zero2();
+      if (EDGE) {
+        fin0 = and2(fin0, x.keep[0], x.keep[2]);
+        fin1 = and2(fin1, x.keep[1], x.keep[3]);
+      }
+      rc0 = fin0;
+      rc1 = fin1;
+      halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
+    } else {
+      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+        float o0, o1, o2, o3;  // columns c0..c3
+        if (MAIN || (rk >= 1 && rk <= N - 2)) {
+          const f2 ya = *reinterpret_cast<const f2 *>(x.delay + roff);
+          const f2 yb = *reinterpret_cast<const f2 *>(x.delay + roff + 256);
+          o0 = add_act<ACT>(lo(ya), lo(fin0));
+          o2 = add_act<ACT>(hi(ya), hi(fin0));
+          o1 = add_act<ACT>(lo(yb), lo(fin1));
+          o3 = add_act<ACT>(hi(yb), hi(fin1));
+        } else {
+          o0 = o1 = o2 = o3 = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+        }
+        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value
+          o0 = sel_bits(o0, x.keep[0], x.gval[0]);
+          o1 = sel_bits(o1, x.keep[1], x.gval[1]);
+          o2 = sel_bits(o2, x.keep[2], x.gval[2]);
+          o3 = sel_bits(o3, x.keep[3], x.gval[3]);
+        }
+        store_cols(x.pout, out_perm, x.st_ok, EDGE ? x.store : 15u, o0, o1, o2, o3);
+      }
+      if (MAIN || rk >= 0) x.pout += x.out_pitch;  // invariant: pout points at row max(rk, 0)
+    }
+  }
+  if (RINGED) {  // row it+1 has landed (at most RING_D - 1 younger copies pending): move it to registers
+    constexpr unsigned RMASK = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
+    cp_async_wait<(RING_D > 0 ? RING_D - 1 : 0)>();
+    const float4 v = *reinterpret_cast<const float4 *>(x.ring + x.rslot);
+    s.X[P ^ 1][0] = mk2(v.x, v.y);
+    s.X[P ^ 1][1] = mk2(v.z, v.w);
+    x.rslot = (x.rslot + 512u) & RMASK;
   }
   woff = (woff + 512u) & RING;
-}
-
-// three consecutive steps = one period of the slot rotation
-template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM>
-__device__ __forceinline__ void conv_three(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
-                                           int it_last, unsigned &woff) {
-  conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 0>(s, x, p, it, woff);
-  if (MAIN || it + 1 <= it_last) conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 1>(s, x, p, it + 1, woff);
-  if (MAIN || it + 2 <= it_last) conv_step<L, ACT, HASF, MAIN, EDGE, PERM, 2>(s, x, p, it + 2, woff);
 }
 
 #ifndef NPDE_CONV_MIN_CTAS
@@ -525,8 +554,8 @@ __global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_CONV_MIN_CTAS)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
   constexpr int RC = (R + 3) & ~3;   // column halo: whole lanes
-  constexpr int DS = (2 * L + 1 <= 8) ? 8 : 16;
-  NPDE_DYN_SMEM(float4, ydl);        // [DS][32]: per-lane private slots
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  NPDE_DYN_SMEM(float4, ydl);        // [DS] slots of 512 bytes: two 256-byte halves, 8 bytes per lane each
 
   StripItem item;
   if (!decode_item(p.B, p.N, p.split, item)) return;
@@ -535,7 +564,9 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.lane = lane;
   x.lane_l = (lane + 31) & 31;
   x.lane_r = (lane + 1) & 31;
-  x.delay = reinterpret_cast<char *>(ydl + lane);
+  x.delay = reinterpret_cast<char *>(ydl) + 8 * lane;
+  x.ring = reinterpret_cast<char *>(ydl) + DS * 512 + 16 * lane;  // behind the delay line
+  x.rslot = 0;
   x.N = p.N;
   const int N = p.N;
   const int vs = item.strip * p.split.wv, ve = min(vs + p.split.wv, N);
@@ -573,55 +604,73 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
 
   ConvState<L> s;
 #pragma unroll
-  for (int h = 0; h < 3; ++h) s.X[h][0] = s.X[h][1] = zero2();
+  for (int h = 0; h < 2; ++h) {
+    s.X[h][0] = s.X[h][1] = zero2();
+    s.yu[h] = s.pff[h] = zero2();
 #pragma unroll
-  for (int h = 0; h < 2; ++h) s.yu[h] = s.r0c[h] = s.pff[h] = zero2();
-  s.xhl = s.xhr = s.r0l = s.r0r = 0.0f;
-#pragma unroll
-  for (int k = 0; k < L; ++k) {
-    s.rl[k] = s.rr[k] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) s.A[k][j][0] = s.A[k][j][1] = zero2();
+    for (int k = 0; k < L; ++k) s.S[k][h][0] = s.S[k][h][1] = zero2();
   }
+  s.xhl = s.xhr = 0.0f;
 #pragma unroll
-  for (int d = 0; d < DS; ++d) *reinterpret_cast<float4 *>(x.delay + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < DS * 2; ++d) *reinterpret_cast<f2 *>(x.delay + d * 256) = zero2();
+#pragma unroll
+  for (int d = 0; d < RING_D; ++d) *reinterpret_cast<float4 *>(x.ring + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  // input rows it = it_first .. it_last; the output row of a step is it - 1 - 2L
+  // input rows it = it_first .. it_last; the output row of a step is it - 1 - L
   const int it_first = max(x.i0 - R, 0);  // rows above the grid are zeros == the initial state
-  const int it_last = x.i1 + 2 * L;
+  const int it_last = x.i1 + L;
   x.x_last = min(x.i1 - 1 + R, N - 1);    // last input row that exists and matters
   const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
   const float *fimg = HASF ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
-  // slot 0 receives row it_first (the first step runs with J = 0); f: one row behind
+  // slot 0 receives row it_first (the first step runs with P = 0); f: one row behind
   load_row(xin + (size_t)it_first * p.in_pitch, x.in_perm, x.ld_ok, c.in_img, s.X[0][0], s.X[0][1]);
   if (HASF && it_first - 1 >= 1)
     load_row(fimg + (size_t)(it_first - 1) * p.f_pitch, x.f_perm, x.ld_ok, c.in_img, s.pff[0], s.pff[1]);
-  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-2L (clamped at 0)
+  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-L (clamped at 0)
   x.pin = xin + (size_t)(it_first + 1) * p.in_pitch;
   x.pfin = HASF ? fimg + (size_t)it_first * p.f_pitch : nullptr;
-  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - 2 * L, 0) * p.out_pitch + c.c0;
+  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - L, 0) * p.out_pitch + c.c0;
   unsigned woff = 0;
 
-  // MAIN range of `it`: stage rows it-1-2L .. it-1 interior, output row it-1-2L inside the band,
+  // MAIN range of `it`: stage rows it-1-L .. it-1 interior, output row it-1-L inside the band,
   // x row it+1 exists and f row `it` is an interior row
-  const int main_lo = max(2 + 2 * L, x.i0 + 1 + 2 * L);
+  const int main_lo = max(L + 2, x.i0 + L + 1);
   const int main_hi = min(N - 2, x.x_last - 1);
   int it = it_first;
   while (it <= it_last) {
-    if (it >= main_lo && it + 2 <= main_hi) {
+    if (it >= main_lo && it + 1 <= main_hi) {
       // the fast loops iterate in place: the register assignment of a variant is set up once per band
-#define NPDE_MAIN_LOOP(EDGE_, PERM_)                                              \
-  do {                                                                            \
-    conv_three<L, ACT, HASF, true, EDGE_, PERM_>(s, x, p, it, it_last, woff);     \
-    it += 3;                                                                      \
-  } while (it + 2 <= main_hi)
-      if (!all_perm) NPDE_MAIN_LOOP(true, false);
-      else if (edge_strip) NPDE_MAIN_LOOP(true, true);
-      else NPDE_MAIN_LOOP(false, true);
+#define NPDE_MAIN_LOOP(EDGE_, PERM_, RINGED_)                                            \
+  do {                                                                                   \
+    conv_step<L, ACT, HASF, true, EDGE_, PERM_, 0, RINGED_>(s, x, p, it, woff);          \
+    conv_step<L, ACT, HASF, true, EDGE_, PERM_, 1, RINGED_>(s, x, p, it + 1, woff);      \
+    it += 2;                                                                             \
+  } while (it + 1 <= main_hi)
+      if (!all_perm) {
+        NPDE_MAIN_LOOP(true, false, false);
+      } else if (RING_D > 0) {
+        // fill the ring: x row `it` is in registers, rows it+1 .. it+RING_D-1 start now
+        x.rslot = 0;
+#pragma unroll
+        for (int d = 0; d < RING_D - 1; ++d) {
+          if (it + 1 + d <= x.x_last && x.ld_ok) cp_async16(x.ring + d * 512, x.pin + (size_t)d * x.in_pitch);
+          cp_async_commit();
+        }
+        x.pin += (size_t)min(RING_D - 1, max(x.x_last - it, 0)) * x.in_pitch;
+        if (edge_strip) NPDE_MAIN_LOOP(true, true, true);
+        else NPDE_MAIN_LOOP(false, true, true);
+        cp_async_wait<0>();
+        // back to plain loads: x.pin must point at row it+1 again; row `it` is in registers (slot of parity 0)
+        x.pin = xin + (size_t)(it + 1) * p.in_pitch;
+      } else {
+        if (edge_strip) NPDE_MAIN_LOOP(true, true, false);
+        else NPDE_MAIN_LOOP(false, true, false);
+      }
 #undef NPDE_MAIN_LOOP
     } else {
-      conv_three<L, ACT, HASF, false, true, false>(s, x, p, it, it_last, woff);
-      it += 3;
+      conv_step<L, ACT, HASF, false, true, false, 0>(s, x, p, it, woff);
+      if (it + 1 <= it_last) conv_step<L, ACT, HASF, false, true, false, 1>(s, x, p, it + 1, woff);
+      it += 2;
     }
   }
 }
@@ -776,8 +825,8 @@ int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaS
 
 template <int L>
 int launch_conv(ConvStreamParams &p, cudaStream_t st) {
-  constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (2 * L + 1 <= 8) ? 8 : 16;
-  const size_t smem = sizeof(float4) * DS * 32 * (npde::STREAM_THREADS / 32);
+  constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
+  const size_t smem = (size_t)512 * (DS + RING_D) * (npde::STREAM_THREADS / 32);  // y delay line + x row ring
   static int cache = 0;
   int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache);
   p.split = make_split(p.B, p.N, RC, R, resident);
