@@ -131,10 +131,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     import oracle
     oracle.build()
+    cores = oracle.set_threads(os.cpu_count() or 1)  # all host cores, whatever OMP_NUM_THREADS torchrun exported
     B, N = BATCH_PER_GPU, GRID_N
     x, bc, w = make_problem(B, N, 666)
     cur = x
@@ -290,8 +289,9 @@ def run_gpu(args):
                      "cell_updates_per_s_kernel": B * N * N / (kernel_ms * 1e-3)},
     }
     if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        import oracle
+        oracle.build()
+        cores = oracle.set_threads(os.cpu_count() or 1)
         v, k, dt = cpu_oracle_throughput(x_np, bc_np, w_np, args.cpu_budget)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d Phi_H iterations on the full %dx%d^2 batch (%.1f s)" % (k, B, N, dt)}

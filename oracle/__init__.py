@@ -42,6 +42,14 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """Use n OpenMP threads for the batch loops (n <= 0: only query).  Returns the thread count in effect."""
+    fn = lib().orc_set_threads
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int]
+    return int(fn(int(n)))
+
+
 def _f(a):
     if a is None:
         return None, None
