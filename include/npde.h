@@ -59,6 +59,7 @@ extern "C" {
 
 #define NPDE_MAX_CONV_LAYERS 8
 #define NPDE_MAX_LEVELS 12
+#define NPDE_MAX_UNET_SMOOTH 8 /* npde_unet_step_bwd: pre / post smoothing convs per level (the reference uses <= 4) */
 
 /* operations for npde_workspace_bytes */
 #define NPDE_WS_REDUCE 0     /* npde_fd_error, npde_l2_error */
@@ -147,7 +148,10 @@ int npde_unet_step_fwd(const float *x, const float *bc, int bc_kind, const float
                        const float *w_pool, const float *w_second, int n_layers, int pre, int post, int act,
                        float *y, int B, int N, void *ws, size_t ws_bytes, void *stream);
 
-/* Backward of one UNetIterator.forward; gradients OVERWRITE gw_first/gw_pool/gw_second. gx may be NULL. */
+/* Backward of one UNetIterator.forward (autograd in the reference, models/heat_model.py:52-53,71-72 with
+ * --iterator unet): recomputes the forward with a tape of every layer input, then walks it back.
+ * gout = dL/dy (B,N,N); gradients OVERWRITE gw_first/gw_pool/gw_second; gx (B,N,N) may be NULL.
+ * pre, post <= NPDE_MAX_UNET_SMOOTH. */
 int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float *f, const float *w_first,
                        const float *w_pool, const float *w_second, int n_layers, int pre, int post, int act,
                        const float *gout, float *gw_first, float *gw_pool, float *gw_second, float *gx, int B,

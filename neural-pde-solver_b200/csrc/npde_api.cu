@@ -257,6 +257,34 @@ struct UnetWs {
   }
 };
 
+// Tape + gradient buffers of npde_unet_step_bwd.
+struct UnetBwdWs {
+  UnetWs base;                                        // level sizes, masks, y_int (skip / t0 / t1 unused)
+  float *F[NPDE_MAX_LEVELS][NPDE_MAX_UNET_SMOOTH + 1];   // F[l][j]: input of pre-smoothing conv j; F[l][pre] = skip_l
+  float *Sx[NPDE_MAX_LEVELS][NPDE_MAX_UNET_SMOOTH + 1];  // Sx[l][j]: input of post-smoothing conv j
+  float *A[NPDE_MAX_LEVELS];                          // Sx[l][post] + skip_l
+  float *gskip[NPDE_MAX_LEVELS];
+  float *gz, *g[2];
+  void *wg;
+  size_t wg_bytes;
+  void carve(Bump &b, int B, int N, int L, int pre, int post, bool is_mask) {
+    base.carve(b, B, N, L, is_mask);
+    for (int l = 0; l < L; ++l) {
+      size_t n = (size_t)B * base.s[l] * base.s[l];
+      for (int j = 0; j <= pre; ++j) F[l][j] = b.take<float>(n);
+      for (int j = 0; j <= post; ++j) Sx[l][j] = (j == 0 && l == L - 1) ? F[l][pre] : b.take<float>(n);
+      A[l] = b.take<float>(n);
+      gskip[l] = b.take<float>(n);
+    }
+    size_t n0 = (size_t)B * (N - 2) * (N - 2);
+    gz = b.take<float>(n0);
+    g[0] = b.take<float>(n0);
+    g[1] = b.take<float>(n0);
+    wg_bytes = npde::weight_grad_ws_bytes(B, N - 2);
+    wg = b.take_bytes(wg_bytes);
+  }
+};
+
 int unet_build_masks(UnetWs &u, const float *bc, int bc_kind, int B, int N, int L, cudaStream_t st) {
   if (bc_kind != NPDE_BC_MASK || !bc) {
     for (int l = 0; l < L; ++l) u.mask[l] = nullptr;
@@ -561,10 +589,97 @@ int npde_unet_step_fwd(const float *x, const float *bc, int bc_kind, const float
   return npde::combine(u.y_int, h, bc, bc_kind, act, y, B, N, st);
 }
 
-int npde_unet_step_bwd(const float *, const float *, int, const float *, const float *, const float *,
-                       const float *, int, int, int, int, const float *, float *, float *, float *, float *, int,
-                       int, void *, size_t, void *) {
-  return NPDE_ERR_ARG;  // not built yet (next row)
+int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float *f, const float *w_first,
+                       const float *w_pool, const float *w_second, int n_layers, int pre, int post, int act,
+                       const float *gout, float *gw_first, float *gw_pool, float *gw_second, float *gx, int B,
+                       int N, void *ws, size_t ws_bytes, void *stream) {
+  TRY(npde::check_common(x, gout, B, N));
+  TRY(npde::check_bc(bc, bc_kind));
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  if (n_layers < 1 || n_layers > NPDE_MAX_LEVELS || pre < 0 || post < 0 || pre > NPDE_MAX_UNET_SMOOTH ||
+      post > NPDE_MAX_UNET_SMOOTH)
+    return NPDE_ERR_LAYERS;
+  if (!level_sizes_ok(N, n_layers)) return NPDE_ERR_SIZE;
+  if ((pre > 0 && (!w_first || !gw_first)) || (post > 0 && (!w_second || !gw_second)) ||
+      (n_layers > 1 && (!w_pool || !gw_pool)))
+    return NPDE_ERR_NULL;
+  TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_UNET_BWD, B, N, bc_kind, n_layers, pre, post, 0)));
+  cudaStream_t st = S(stream);
+  const int L = n_layers;
+  Bump b(ws);
+  UnetBwdWs u;
+  u.carve(b, B, N, L, pre, post, bc_kind == NPDE_BC_MASK);
+  TRY(unet_build_masks(u.base, bc, bc_kind, B, N, L, st));
+  float *const *mask = u.base.mask;
+  const size_t *mbs = u.base.mbs;
+  const int *sz = u.base.s;
+  auto cells = [&](int l) { return (size_t)B * sz[l] * sz[l]; };
+
+  // ---- forward with tape (unet_iterator.py:36-85): every layer input is kept -------------------
+  TRY(npde::psi_residual(x, f, mask[0], mbs[0], u.base.y_int, u.F[0][0], B, N, st));
+  for (int l = 0; l < L; ++l) {
+    for (int j = 0; j < pre; ++j)
+      TRY(npde::conv3x3(u.F[l][j], sz[l], w_first + 9 * (l * pre + j), 1, 1, mask[l], mbs[l], u.F[l][j + 1], sz[l], B,
+                        st));
+    if (l < L - 1)
+      TRY(npde::conv3x3(u.F[l][pre], sz[l], w_pool + 9 * l, 2, 0, mask[l + 1], mbs[l + 1], u.F[l + 1][0], sz[l + 1], B,
+                        st));
+  }
+  for (int i = 0; i < L; ++i) {
+    const int l = L - 1 - i;
+    for (int j = 0; j < post; ++j)
+      TRY(npde::conv3x3(u.Sx[l][j], sz[l], w_second + 9 * (i * post + j), 1, 1, mask[l], mbs[l], u.Sx[l][j + 1], sz[l],
+                        B, st));
+    TRY(d2d(u.A[l], u.Sx[l][post], sizeof(float) * cells(l), st));
+    TRY(npde::add_inplace(u.A[l], u.F[l][pre], cells(l), st));  // :76 skip connection
+    if (i < L - 1) TRY(npde::pad_up_crop(u.A[l], sz[l], mask[l - 1], mbs[l - 1], u.Sx[l - 1][0], B, st));
+  }
+  const float *h = u.A[0];
+
+  // ---- backward ---------------------------------------------------------------------------------
+  TRY(npde::bwd_gz(gout, u.base.y_int, h, mask[0], mbs[0], act, u.gz, B, N, st));
+  float *g = u.g[0], *other = u.g[1];
+  auto swap = [&]() { float *t = g; g = other; other = t; };
+  TRY(d2d(g, u.gz, sizeof(float) * cells(0), st));
+  for (int i = L - 1; i >= 0; --i) {
+    const int l = L - 1 - i;
+    if (i < L - 1) {  // undo "* fg, crop, upsample, pad" that followed this level (:78-83)
+      if (mask[l - 1]) TRY(npde::mul_fg(g, mask[l - 1], mbs[l - 1], sz[l - 1], B, st));
+      TRY(npde::pad_up_crop_transpose(g, sz[l], other, B, st));
+      swap();
+    }
+    TRY(d2d(u.gskip[l], g, sizeof(float) * cells(l), st));
+    for (int j = post - 1; j >= 0; --j) {
+      if (mask[l]) TRY(npde::mul_fg(g, mask[l], mbs[l], sz[l], B, st));
+      TRY(npde::weight_grad(g, sz[l], u.Sx[l][j], sz[l], 1, 1, gw_second + 9 * (i * post + j), B, u.wg, u.wg_bytes,
+                            st));
+      TRY(npde::conv3x3_transpose(g, sz[l], w_second + 9 * (i * post + j), 1, 1, other, sz[l], B, st));
+      swap();
+    }
+  }
+  // g = dL/dT_{L-1} through the post-smoothing path of the deepest level; add the skip path
+  TRY(npde::add_inplace(g, u.gskip[L - 1], cells(L - 1), st));
+  for (int l = L - 1; l >= 0; --l) {
+    for (int j = pre - 1; j >= 0; --j) {
+      if (mask[l]) TRY(npde::mul_fg(g, mask[l], mbs[l], sz[l], B, st));
+      TRY(npde::weight_grad(g, sz[l], u.F[l][j], sz[l], 1, 1, gw_first + 9 * (l * pre + j), B, u.wg, u.wg_bytes, st));
+      TRY(npde::conv3x3_transpose(g, sz[l], w_first + 9 * (l * pre + j), 1, 1, other, sz[l], B, st));
+      swap();
+    }
+    if (l > 0) {  // the stride-2 pooling conv that produced this level's input (:63-66)
+      if (mask[l]) TRY(npde::mul_fg(g, mask[l], mbs[l], sz[l], B, st));
+      TRY(npde::weight_grad(g, sz[l], u.F[l - 1][pre], sz[l - 1], 2, 0, gw_pool + 9 * (l - 1), B, u.wg, u.wg_bytes,
+                            st));
+      TRY(npde::conv3x3_transpose(g, sz[l], w_pool + 9 * (l - 1), 2, 0, other, sz[l - 1], B, st));
+      swap();
+      TRY(npde::add_inplace(g, u.gskip[l - 1], cells(l - 1), st));
+    }
+  }
+  if (gx) {
+    if (mask[0]) TRY(npde::mul_fg(g, mask[0], mbs[0], sz[0], B, st));
+    TRY(npde::bwd_gx(u.gz, g, gx, B, N, st));
+  }
+  return NPDE_OK;
 }
 
 size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int pre, int post, int k) {
@@ -597,6 +712,14 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
       u.carve(b, B, N, n_layers, bc_kind == NPDE_BC_MASK);
       b.take<float>((size_t)B * (N - 2) * (N - 2));
       b.take<float>((size_t)B * (N - 2) * (N - 2));
+      return b.off;
+    }
+    case NPDE_WS_UNET_BWD: {
+      if (n_layers < 1 || n_layers > NPDE_MAX_LEVELS || pre < 0 || post < 0 || pre > NPDE_MAX_UNET_SMOOTH ||
+          post > NPDE_MAX_UNET_SMOOTH)
+        return 0;
+      UnetBwdWs u;
+      u.carve(b, B, N, n_layers, pre, post, bc_kind == NPDE_BC_MASK);
       return b.off;
     }
     case NPDE_WS_ITERATE + NPDE_IT_JACOBI:

@@ -290,6 +290,46 @@ def unet_step(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act):
     return y
 
 
+def unet_step_bwd(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act, gout, need_gx):
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    wf, wp, wsn = _opt(w_first, "w_first"), _opt(w_pool, "w_pool"), _opt(w_second, "w_second")
+    gout = _field(gout, "gout")
+    B, N, _ = x.shape
+    kind = bc_kind(x, bc)
+    gwf, gwp, gws = torch.zeros_like(wf), torch.zeros_like(wp), torch.zeros_like(wsn)
+    gx = torch.empty_like(x) if need_gx else None
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_UNET_BWD, B, N, kind, n_layers, pre, post, 0), x)
+    check(lib().npde_unet_step_bwd(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wf), _ptr(wp), _ptr(wsn), n_layers, pre,
+                                   post, _act(act), _ptr(gout), _ptr(gwf), _ptr(gwp), _ptr(gws), _ptr(gx), B, N, ws,
+                                   wsb, _stream(x)), "npde_unet_step_bwd")
+    return gwf, gwp, gws, gx
+
+
+class UNetStepFn(torch.autograd.Function):
+    """Differentiable UNetIterator.forward (the reference gets it from autograd, models/heat_model.py:52-53)."""
+
+    @staticmethod
+    def forward(ctx, x, bc, f, w, n_first, n_pool, n_layers, pre, post, act):
+        ctx.save_for_backward(x, bc, f if f is not None else x.new_empty(0), w)
+        ctx.has_f = f is not None
+        ctx.cfg = (n_first, n_pool, n_layers, pre, post, act)
+        wd = w.detach()
+        return unet_step(x, bc, f, wd[:n_first], wd[n_first:n_first + n_pool], wd[n_first + n_pool:], n_layers, pre,
+                         post, act)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, bc, f, w = ctx.saved_tensors
+        n_first, n_pool, n_layers, pre, post, act = ctx.cfg
+        wd = w.detach()
+        gwf, gwp, gws, gx = unet_step_bwd(x, bc, f if ctx.has_f else None, wd[:n_first],
+                                          wd[n_first:n_first + n_pool], wd[n_first + n_pool:], n_layers, pre, post,
+                                          act, gout, ctx.needs_input_grad[0])
+        return gx, None, None, torch.cat([gwf, gwp, gws]), None, None, None, None, None, None
+
+
 # -------------------------------------------------------------- k-step loop --
 def iterate(iterator, x, bc, f, k, *, w=None, w_host=None, n_layers=0, pre=0, post=0, act="none", gt=None,
             want_l2=False, want_fd=False, temporal_depth=0, out=None):

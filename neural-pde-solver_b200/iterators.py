@@ -209,8 +209,9 @@ class UNetIterator(Iterator):
             raise NotImplementedError("is_bc_mask does not match the bc tensor shape")
         params = self._params()
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
-            raise NotImplementedError("UNetIterator backward is not built yet (npde_unet_step_bwd); "
-                                      "call under torch.no_grad()")
+            w = torch.stack([p.reshape(3, 3) for p in params])
+            return F_.UNetStepFn.apply(x, bc, f, w, self.n_layers * self.pre_smoothing, self.n_layers - 1,
+                                       self.n_layers, self.pre_smoothing, self.post_smoothing, self.act)
         w, _ = self._cache.get(params)
         wf, wp, ws = self._split(w)
         return F_.unet_step(x, bc, f, wf, wp, ws, self.n_layers, self.pre_smoothing, self.post_smoothing, self.act)

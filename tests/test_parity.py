@@ -247,6 +247,27 @@ def test_conv_backward(be, name):
     assert rel_err(be.n(xg.grad), g["gx"]) <= 2e-5
 
 
+@pytest.mark.parametrize("name", golden_names("bwd_unet_"))
+def test_unet_backward(be, name):
+    """One differentiable UNetIterator step + MSE vs the reference's autograd (square and cylinder geometries,
+    none / clamp / sigmoid).  Reduction order differs: 2e-5 of the largest entry per gradient tensor."""
+    g = load_golden(name)
+    it = make_unet(be, g)
+    x, bc, f, gt = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f")), be.t(g["gt"])
+    xg = x.clone().requires_grad_(True)
+    y = it(xg, bc, f)
+    loss = torch.nn.MSELoss()(y, gt)
+    loss.backward()
+    assert rel_err(be.n(y), g["y"]) <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for ml, key in ((it.first_layers, "gw_first"), (it.pooling_layers, "gw_pool"), (it.second_layers, "gw_second")):
+        if len(ml) == 0:
+            continue
+        gw = np.stack([be.n(l.weight.grad)[0, 0] for l in ml])
+        assert rel_err(gw, g[key]) <= 2e-5, (key, gw, g[key])
+    assert rel_err(be.n(xg.grad), g["gx"]) <= 2e-5
+
+
 # ------------------------------------------------------------------- drivers --
 def make_opt(**kw):
     import argparse
@@ -299,11 +320,12 @@ def test_driver_evaluate(be):
     assert_bitwise(be.n(xf), g["x_final"], "final iterate of evaluate")
 
 
-@pytest.mark.parametrize("tag", ["conv_adam", "conv_sgd"])
+@pytest.mark.parametrize("tag", ["conv_adam", "conv_sgd", "unet_adam"])
 def test_driver_train(be, tag):
     """HeatModel.train: three optimiser steps reproduce the reference's losses and updated weights."""
     g = load_golden("driver_train_" + tag)
-    opt = make_opt(lambda_gt=0.3) if tag == "conv_adam" else make_opt(optimizer="sgd", lr_init=1e-2)
+    opt = {"conv_adam": make_opt(lambda_gt=0.3), "conv_sgd": make_opt(optimizer="sgd", lr_init=1e-2),
+           "unet_adam": make_opt(iterator="unet", mg_n_layers=2, lambda_gt=0.0)}[tag]
     model = be.npde.HeatModel(opt)
     model.iterator.to(be.device)
     with torch.no_grad():
