@@ -764,12 +764,16 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   const size_t cells = (size_t)B * N * N;
   const bool want_err = d->err_l2 || d->err_fd;
 
-  // ---- fast path: fused stream kernels, padded ping-pong buffers, no per-step norms ----
+  // ---- fast path: fused stream kernels on pair-permuted ping-pong buffers.  Error rows, if asked for,
+  // come from the reduction kernels reading the same buffers (one launch per row, no host round trip);
+  // they force one iterator application per launch.
   const bool conv_fast = it == NPDE_IT_CONV && npde::conv_stream_supported(d->bc_kind, d->n_layers, d->w_host);
   const bool jac_fast = it == NPDE_IT_JACOBI && d->bc_kind == NPDE_BC_SQUARE;
-  if ((conv_fast || jac_fast) && !want_err) {
-    if (d->k == 0) return d2d(d->x_out, d->x_in, sizeof(float) * cells, st);
+  if (conv_fast || jac_fast) {
     npde::FieldView cur = npde::ref_view(d->x_in, N);
+    if (d->err_fd)
+      TRY(npde::fd_error_view(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd, B, N, w.red, w.red_bytes, st));
+    if (d->k == 0) return d2d(d->x_out, d->x_in, sizeof(float) * cells, st);
     npde::FieldViewMut pad[2] = {{w.buf[0], w.pitch, w.bstride, 1}, {w.buf[1], w.pitch, w.bstride, 1}};
     npde::FieldViewMut last = npde::ref_view_mut(d->x_out, N);
     // the source is read in every step: give it 16-byte aligned rows once (128-bit loads)
@@ -779,10 +783,10 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       TRY(npde::copy_field(fv, fp, B, N, st));
       fv = npde::as_const(fp);
     }
-    int left = d->k, flip = 0;
+    int left = d->k, flip = 0, done = 0;
     while (left > 0) {
       int adv = 1;
-      if (jac_fast && !d->f) {
+      if (jac_fast && !d->f && !want_err) {
         adv = depth;
         while (adv > left) adv >>= 1;
       }
@@ -795,9 +799,18 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       else
         TRY(npde::jacobi_stream(cur, dst, d->bc, fv, adv, B, N, st));
       left -= adv;
-      if (final_launch && alias) TRY(npde::copy_field(npde::as_const(dst), last, B, N, st));
+      done += adv;
+      if (final_launch && alias) {
+        TRY(npde::copy_field(npde::as_const(dst), last, B, N, st));
+        dst = last;
+      }
       cur = npde::as_const(dst);
       flip ^= 1;
+      if (d->err_l2)
+        TRY(npde::l2_error_view(cur, d->gt, d->err_l2 + (size_t)(done - 1) * B, B, N, w.red, w.red_bytes, st));
+      if (d->err_fd)
+        TRY(npde::fd_error_view(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd + (size_t)done * B, B, N, w.red,
+                                w.red_bytes, st));
     }
     return NPDE_OK;
   }

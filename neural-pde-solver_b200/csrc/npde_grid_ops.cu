@@ -62,6 +62,12 @@ __global__ void k_fd_step(const float *__restrict__ x, BcView bc, const float *_
   y[(size_t)b * N * N + o] = npde_apply_G(v, bc, b, i, j, N);
 }
 
+// column j inside a row of a field view: the pair-permuted layout stores every aligned group of
+// four columns (c0,c1,c2,c3) as (c0,c2,c1,c3) (npde_internal.h FieldView)
+__device__ __forceinline__ int view_col(int j, int perm) {
+  return perm ? ((j & ~3) | ((j & 1) << 1) | ((j >> 1) & 1)) : j;
+}
+
 // -------------------------------------------------------- reductions ------
 // grid (chunks, B); every CTA reduces a band of rows, writes one partial, and
 // the last CTA of each problem folds the partials in index order, so the
@@ -108,10 +114,10 @@ __device__ __forceinline__ void block_reduce_finish(double v, ReduceWs ws, int c
 
 template <bool IS_MAX>
 __global__ void __launch_bounds__(RED_THREADS)
-k_fd_error(const float *__restrict__ x, BcView bc, const float *__restrict__ f, float *err, ReduceWs ws,
-           int N, int rows_per_chunk) {
+k_fd_error(const float *__restrict__ x, int xp, long xbs, int xperm, BcView bc, const float *__restrict__ f,
+           float *err, ReduceWs ws, int N, int rows_per_chunk) {
   int b = blockIdx.y, chunks = gridDim.x;
-  const float *xb = x + (size_t)b * N * N;
+  const float *xb = x + (size_t)b * xbs;
   const float *fb = f ? f + (size_t)b * N * N : nullptr;
   const bool mask = bc.kind == NPDE_BC_MASK;
   const float *m = mask ? bc.bc + ((size_t)b * 2 + 1) * N * N : nullptr;
@@ -122,11 +128,13 @@ k_fd_error(const float *__restrict__ x, BcView bc, const float *__restrict__ f, 
   for (int idx = threadIdx.x; idx < (r1 - r0) * W; idx += RED_THREADS) {
     int i = r0 + idx / W, j = lo + idx % W;
     size_t o = (size_t)i * N + j;
-    float u = i > 0 ? __ldg(xb + o - N) : 0.0f;
-    float l = j > 0 ? __ldg(xb + o - 1) : 0.0f;
-    float c = __ldg(xb + o);
-    float r = j < N - 1 ? __ldg(xb + o + 1) : 0.0f;
-    float d = i < N - 1 ? __ldg(xb + o + N) : 0.0f;
+    const float *row = xb + (size_t)i * xp;
+    const int jc = view_col(j, xperm);
+    float u = i > 0 ? __ldg(row - xp + jc) : 0.0f;
+    float l = j > 0 ? __ldg(row + view_col(j - 1, xperm)) : 0.0f;
+    float c = __ldg(row + jc);
+    float r = j < N - 1 ? __ldg(row + view_col(j + 1, xperm)) : 0.0f;
+    float d = i < N - 1 ? __ldg(row + xp + jc) : 0.0f;
     float v = npde_residual(u, l, c, r, d);
     if (fb) v = __fsub_rn(v, __ldg(fb + o));
     if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + o)));
@@ -137,26 +145,27 @@ k_fd_error(const float *__restrict__ x, BcView bc, const float *__restrict__ f, 
 }
 
 __global__ void __launch_bounds__(RED_THREADS)
-k_l2_error(const float *__restrict__ x, const float *__restrict__ gt, float *err, ReduceWs ws, int N,
-           int cells_per_chunk) {
+k_l2_error(const float *__restrict__ x, int xp, long xbs, int xperm, const float *__restrict__ gt, float *err,
+           ReduceWs ws, int N, int cells_per_chunk) {
   int b = blockIdx.y, chunks = gridDim.x;
   size_t n = (size_t)N * N;
   size_t c0 = (size_t)blockIdx.x * cells_per_chunk;
   size_t c1 = c0 + cells_per_chunk < n ? c0 + cells_per_chunk : n;
-  const float *xb = x + (size_t)b * n, *gb = gt + (size_t)b * n;
+  const float *xb = x + (size_t)b * xbs, *gb = gt + (size_t)b * n;
+  const bool plain = xp == N && !xperm;
   double acc = 0.0;
   for (size_t o = c0 + threadIdx.x; o < c1; o += RED_THREADS) {
-    float d = __fsub_rn(__ldg(xb + o), __ldg(gb + o));
+    size_t xo = o;  // same cell -> thread mapping (and hence summation order) for every layout
+    if (!plain) {
+      const int i = (int)(o / N), j = (int)(o - (size_t)i * N);
+      xo = (size_t)i * xp + view_col(j, xperm);
+    }
+    float d = __fsub_rn(__ldg(xb + xo), __ldg(gb + o));
     acc += (double)__fmul_rn(d, d);
   }
   block_reduce_finish<false>(acc, ws, chunks, err, b, (double)n, true);
 }
 
-// column j inside a row of a field view: the pair-permuted layout stores every aligned group of
-// four columns (c0,c1,c2,c3) as (c0,c2,c1,c3) (npde_internal.h FieldView)
-__device__ __forceinline__ int view_col(int j, int perm) {
-  return perm ? ((j & ~3) | ((j & 1) << 1) | ((j >> 1) & 1)) : j;
-}
 __global__ void k_copy_field(const float *__restrict__ src, int sp, long sb, int sperm, float *__restrict__ dst,
                              int dp, long db, int dperm, int N) {
   int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
@@ -279,6 +288,11 @@ int fd_step_simple(const float *x, const float *bc, int bc_kind, const float *f,
 
 int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int aggregate, float *err, int B,
              int N, void *ws, size_t ws_bytes, cudaStream_t st) {
+  return fd_error_view(ref_view(x, N), bc, bc_kind, f, aggregate, err, B, N, ws, ws_bytes, st);
+}
+
+int fd_error_view(const FieldView &xv, const float *bc, int bc_kind, const float *f, int aggregate, float *err,
+                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st) {
   ReduceWs r;
   int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
   if (rc) return rc;
@@ -288,9 +302,11 @@ int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int a
   int rpc = (rows + chunks - 1) / chunks;
   chunks = (rows + rpc - 1) / rpc;  // no empty trailing chunks
   if (aggregate == NPDE_AGG_MAX) {
-    NPDE_LAUNCH(k_fd_error<true>, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, v, f, err, r, N, rpc);
+    NPDE_LAUNCH(k_fd_error<true>, dim3(chunks, B), dim3(RED_THREADS), 0, st, xv.p, xv.pitch, xv.bstride, xv.perm, v,
+                f, err, r, N, rpc);
   } else {
-    NPDE_LAUNCH(k_fd_error<false>, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, v, f, err, r, N, rpc);
+    NPDE_LAUNCH(k_fd_error<false>, dim3(chunks, B), dim3(RED_THREADS), 0, st, xv.p, xv.pitch, xv.bstride, xv.perm, v,
+                f, err, r, N, rpc);
   }
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
@@ -298,6 +314,11 @@ int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int a
 
 int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
              cudaStream_t st) {
+  return l2_error_view(ref_view(x, N), gt, err, B, N, ws, ws_bytes, st);
+}
+
+int l2_error_view(const FieldView &xv, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
   ReduceWs r;
   int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
   if (rc) return rc;
@@ -305,7 +326,8 @@ int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws
   long n = (long)N * N;
   int cpc = (int)((n + chunks - 1) / chunks);
   chunks = (int)((n + cpc - 1) / cpc);
-  NPDE_LAUNCH(k_l2_error, dim3(chunks, B), dim3(RED_THREADS), 0, st, x, gt, err, r, N, cpc);
+  NPDE_LAUNCH(k_l2_error, dim3(chunks, B), dim3(RED_THREADS), 0, st, xv.p, xv.pitch, xv.bstride, xv.perm, gt, err, r,
+              N, cpc);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -8,6 +8,32 @@ namespace npde {
 int check_common(const void *a, const void *b, int B, int N);
 int check_bc(const float *bc, int bc_kind);
 
+// A (B,N,N) field with an arbitrary row pitch / batch stride (floats).  The reference layout
+// is {p, N, N*N, perm = 0}.  The internal ping-pong buffers of the k-step loop use the
+// "pair-permuted padded layout" (perm = 1): 16-byte aligned rows of pitch >= round_up(N, 4)
+// in which every aligned group of four columns (c0,c1,c2,c3) is stored as (c0,c2,c1,c3), the
+// register-pair order of the stream kernels (npde_stream.cu), so a lane moves its four
+// columns with one 128-bit access.
+struct FieldView {
+  const float *p;
+  int pitch;
+  long bstride;
+  int perm;
+};
+struct FieldViewMut {
+  float *p;
+  int pitch;
+  long bstride;
+  int perm;
+};
+inline FieldView ref_view(const float *p, int N) { return FieldView{p, N, (long)N * N, 0}; }  // p may be nullptr
+inline FieldViewMut ref_view_mut(float *p, int N) { return FieldViewMut{p, N, (long)N * N, 0}; }
+// layout conversion / copy between any two views
+int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st);  // npde_grid_ops.cu
+inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch, v.bstride, v.perm}; }
+
+// square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
+bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
 // npde_grid_ops.cu
 int reduce_chunks(int N);
 size_t reduce_ws_bytes(int B, int N);
@@ -19,6 +45,11 @@ int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int a
              int N, void *ws, size_t ws_bytes, cudaStream_t st);
 int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
              cudaStream_t st);
+// same on any field view (the internal buffers of the k-step loop); bc, f and gt stay in the reference layout
+int fd_error_view(const FieldView &x, const float *bc, int bc_kind, const float *f, int aggregate, float *err,
+                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st);
+int l2_error_view(const FieldView &x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
 int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t st);
 // same, input images `x_bstride` floats apart (the mask plane of a (B,2,N,N) bc tensor)
 int subsample_strided(const float *x, size_t x_bstride, float *y, int B, int N, float scale, cudaStream_t st);
@@ -51,32 +82,6 @@ int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream
 // npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)
 constexpr int STREAM_THREADS = 32;  // one warp strip per CTA (see decode_item in npde_stream.cu)
 
-// A (B,N,N) field with an arbitrary row pitch / batch stride (floats).  The reference layout
-// is {p, N, N*N, perm = 0}.  The internal ping-pong buffers of the k-step loop use the
-// "pair-permuted padded layout" (perm = 1): 16-byte aligned rows of pitch >= round_up(N, 4)
-// in which every aligned group of four columns (c0,c1,c2,c3) is stored as (c0,c2,c1,c3), the
-// register-pair order of the stream kernels (npde_stream.cu), so a lane moves its four
-// columns with one 128-bit access.
-struct FieldView {
-  const float *p;
-  int pitch;
-  long bstride;
-  int perm;
-};
-struct FieldViewMut {
-  float *p;
-  int pitch;
-  long bstride;
-  int perm;
-};
-inline FieldView ref_view(const float *p, int N) { return FieldView{p, N, (long)N * N, 0}; }  // p may be nullptr
-inline FieldViewMut ref_view_mut(float *p, int N) { return FieldViewMut{p, N, (long)N * N, 0}; }
-// layout conversion / copy between any two views
-int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cudaStream_t st);  // npde_grid_ops.cu
-inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch, v.bstride, v.perm}; }
-
-// square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
-bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
 // f.p == nullptr: Laplace.  perm views are accessed with 128-bit loads / stores, natural ones with 32-bit.
 int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f,
                 const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st);

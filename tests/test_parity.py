@@ -346,6 +346,49 @@ def test_driver_train(be, tag):
             assert np.allclose(got, v, rtol=0, atol=2e-5), (k, got, v)
 
 
+def test_solve_to_tolerance_counts(be, oracle):
+    """generation.py:72-99 as a device-side driver: identical iteration counts to the oracle's
+    per-step loop (BASELINE: "identical iterations-to-tolerance"), Jacobi and Conv, tol 1e-4 at 17^2."""
+    rng = np.random.RandomState(5)
+    B, N = 5, 17
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    w = np.zeros((2, 3, 3), np.float32)
+    w[0, 1, 1], w[1, 1, 1] = 0.3, -0.3  # H = -0.09 * identity: Phi = 0.91 Psi + 0.09 I, a contraction
+    tol = 1e-4
+    for kind in ("jacobi", "conv"):
+        if kind == "jacobi":
+            it = be.npde.JacobiIterator()
+        else:
+            it = be.npde.ConvIterator("none", 2)
+            with torch.no_grad():
+                for l, wl in zip(it.layers, w):
+                    l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+            it = it.to(be.device)
+        res = be.utils.solve_to_tolerance(it, be.t(x), be.t(bc), None, tol=tol, check_every=50, max_iters=2000,
+                                          per_problem=True)
+        # oracle: step by step
+        cur = x.copy()
+        first = np.full(B, -1)
+        n_done = 0
+        for t in range(1, 2001):
+            cur = oracle.fd_step(cur, bc, None) if kind == "jacobi" else oracle.conv_step(cur, bc, None, w, "none")
+            e = oracle.fd_error(cur, bc, None, "max")
+            for b in range(B):
+                if first[b] < 0 and e[b] < tol:
+                    first[b] = t
+            if t % 50 == 0 and e.max() < tol:
+                n_done = t
+                break
+        assert res["converged"] and res["iterations"] == n_done, (kind, res["iterations"], n_done)
+        assert np.array_equal(res["first_below"].numpy(), first), (kind, res["first_below"], first)
+        assert_bitwise(be.n(res["x"]), cur, "solution at the stopping iteration")
+        # the cheap variant (no per-iteration rows) stops at the same check
+        res2 = be.utils.solve_to_tolerance(it, be.t(x), be.t(bc), None, tol=tol, check_every=50, max_iters=2000)
+        assert res2["iterations"] == n_done
+        assert_bitwise(be.n(res2["x"]), cur, "solution, cheap variant")
+
+
 # --------------------------------------------------------------- error paths --
 def test_error_behaviour(be):
     x = torch.zeros(2, 17, 17, device=be.device)
