@@ -169,7 +169,7 @@ typedef struct npde_iterate_desc {
   int pre, post;       /* multigrid / unet smoothing counts */
   int act;             /* NPDE_ACT_* (conv, unet) */
   int k;               /* number of applications, >= 0 */
-  int temporal_depth;  /* Jacobi steps fused per HBM round trip (1,2,4,8); 0 = library default (8) */
+  int temporal_depth;  /* Jacobi steps fused per HBM round trip (1,2,4,8); 0 = library default (4) */
   const float *x_in;   /* (B,N,N) */
   float *x_out;        /* (B,N,N); may alias x_in */
   const float *bc;

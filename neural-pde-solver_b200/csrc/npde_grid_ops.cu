@@ -123,24 +123,30 @@ k_fd_error(const float *__restrict__ x, int xp, long xbs, int xperm, BcView bc, 
   const float *m = mask ? bc.bc + ((size_t)b * 2 + 1) * N * N : nullptr;
   int lo = mask ? 0 : 1, hi = mask ? N : N - 1;  // heat_utils.py:113-121
   int r0 = lo + blockIdx.x * rows_per_chunk, r1 = min(r0 + rows_per_chunk, hi);
-  double acc = 0.0;
   int W = hi - lo;
-  for (int idx = threadIdx.x; idx < (r1 - r0) * W; idx += RED_THREADS) {
-    int i = r0 + idx / W, j = lo + idx % W;
-    size_t o = (size_t)i * N + j;
+  // a warp walks along a row (coalesced, neighbours served by L1), the 8 warps of the CTA take
+  // rows r0+w, r0+w+8, ...; max is accumulated in fp32 (exact, order independent), sums in fp64
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float vmax = 0.0f;
+  double vsum = 0.0;
+  for (int i = r0 + ty; i < r1; i += RED_THREADS / 32) {
     const float *row = xb + (size_t)i * xp;
-    const int jc = view_col(j, xperm);
-    float u = i > 0 ? __ldg(row - xp + jc) : 0.0f;
-    float l = j > 0 ? __ldg(row + view_col(j - 1, xperm)) : 0.0f;
-    float c = __ldg(row + jc);
-    float r = j < N - 1 ? __ldg(row + view_col(j + 1, xperm)) : 0.0f;
-    float d = i < N - 1 ? __ldg(row + xp + jc) : 0.0f;
-    float v = npde_residual(u, l, c, r, d);
-    if (fb) v = __fsub_rn(v, __ldg(fb + o));
-    if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + o)));
-    double a = (double)fabsf(v);
-    acc = IS_MAX ? fmax(acc, a) : acc + a;
+    for (int j = lo + tx; j < hi; j += 32) {
+      size_t o = (size_t)i * N + j;
+      const int jc = view_col(j, xperm);
+      float u = i > 0 ? __ldg(row - xp + jc) : 0.0f;
+      float l = j > 0 ? __ldg(row + view_col(j - 1, xperm)) : 0.0f;
+      float c = __ldg(row + jc);
+      float r = j < N - 1 ? __ldg(row + view_col(j + 1, xperm)) : 0.0f;
+      float d = i < N - 1 ? __ldg(row + xp + jc) : 0.0f;
+      float v = npde_residual(u, l, c, r, d);
+      if (fb) v = __fsub_rn(v, __ldg(fb + o));
+      if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + o)));
+      if (IS_MAX) vmax = fmaxf(vmax, fabsf(v));
+      else vsum += (double)fabsf(v);
+    }
   }
+  double acc = IS_MAX ? (double)vmax : vsum;
   block_reduce_finish<IS_MAX>(acc, ws, chunks, err, b, (double)W * (double)W, false);
 }
 

@@ -384,7 +384,7 @@ struct ConvLaneCtx {
   char *ring;        // this lane's 16 bytes in slot 0 of the x row ring (shared memory)
   unsigned rslot;    // ring slot (byte offset) that holds x row it+1
   float top, bottom;
-  int N, i0, i1, x_last, in_pitch, out_pitch, f_pitch, lane, lane_l, lane_r;
+  int N, i0, i1, x_last, f_last, in_pitch, out_pitch, f_pitch, lane, lane_l, lane_r;
 };
 
 #ifndef NPDE_EMU
@@ -440,14 +440,23 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
       y0 = sub2(y0, s.pff[0]);
       y1 = sub2(y1, s.pff[1]);
       const int nf = it;  // f row used by the stage 0 of the next step
-      if (MAIN || (nf <= x.x_last && nf >= 1 && nf <= N - 2)) {
-        load_row(x.pfin, f_perm, ld_ok, EDGE ? x.in_img : 15u, s.pff[0], s.pff[1]);
+      if (RINGED) {
+        // x.pfin points at f row it + RING_D - 1: it joins the copy group of x row it + RING_D below
+        if (it + RING_D - 1 <= x.f_last) {
+          constexpr unsigned RMASK_F = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
+          if (ld_ok) cp_async16(x.ring + RING_D * 512 + ((x.rslot + (RING_D - 1) * 512u) & RMASK_F), x.pfin);
+          x.pfin += x.f_pitch;
+        }
       } else {
-        s.pff[0] = s.pff[1] = zero2();
+        if (MAIN || (nf <= x.x_last && nf >= 1 && nf <= N - 2)) {
+          load_row(x.pfin, f_perm, ld_ok, EDGE ? x.in_img : 15u, s.pff[0], s.pff[1]);
+        } else {
+          s.pff[0] = s.pff[1] = zero2();
+        }
+        if (L2_AHEAD > 0 && nf + L2_AHEAD <= x.x_last)
+          prefetch_row(x.pfin + (size_t)L2_AHEAD * x.f_pitch, x.lane, EDGE ? x.in_img : 15u);
+        x.pfin += x.f_pitch;
       }
-      if (L2_AHEAD > 0 && nf + L2_AHEAD <= x.x_last)
-        prefetch_row(x.pfin + (size_t)L2_AHEAD * x.f_pitch, x.lane, EDGE ? x.in_img : 15u);
-      x.pfin += x.f_pitch;
     }
     rc0 = sub2(y0, C[0]);
     rc1 = sub2(y1, C[1]);
@@ -541,6 +550,11 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     const float4 v = *reinterpret_cast<const float4 *>(x.ring + x.rslot);
     s.X[P ^ 1][0] = mk2(v.x, v.y);
     s.X[P ^ 1][1] = mk2(v.z, v.w);
+    if (HASF) {  // f row `it` travelled in the same copy group
+      const float4 fv = *reinterpret_cast<const float4 *>(x.ring + RING_D * 512 + x.rslot);
+      s.pff[0] = mk2(fv.x, fv.y);
+      s.pff[1] = mk2(fv.z, fv.w);
+    }
     x.rslot = (x.rslot + 512u) & RMASK;
   }
   woff = (woff + 512u) & RING;
@@ -614,12 +628,14 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
 #pragma unroll
   for (int d = 0; d < DS * 2; ++d) *reinterpret_cast<f2 *>(x.delay + d * 256) = zero2();
 #pragma unroll
-  for (int d = 0; d < RING_D; ++d) *reinterpret_cast<float4 *>(x.ring + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int d = 0; d < (HASF ? 2 : 1) * RING_D; ++d)
+    *reinterpret_cast<float4 *>(x.ring + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // input rows it = it_first .. it_last; the output row of a step is it - 1 - L
   const int it_first = max(x.i0 - R, 0);  // rows above the grid are zeros == the initial state
   const int it_last = x.i1 + L;
   x.x_last = min(x.i1 - 1 + R, N - 1);    // last input row that exists and matters
+  x.f_last = min(x.x_last, N - 2);        // last row of f that is ever read
   const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
   const float *fimg = HASF ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
   // slot 0 receives row it_first (the first step runs with P = 0); f: one row behind
@@ -654,14 +670,18 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
 #pragma unroll
         for (int d = 0; d < RING_D - 1; ++d) {
           if (it + 1 + d <= x.x_last && x.ld_ok) cp_async16(x.ring + d * 512, x.pin + (size_t)d * x.in_pitch);
+          if (HASF && it + d <= x.f_last && x.ld_ok)  // f runs one row behind x
+            cp_async16(x.ring + (RING_D + d) * 512, x.pfin + (size_t)d * x.f_pitch);
           cp_async_commit();
         }
         x.pin += (size_t)min(RING_D - 1, max(x.x_last - it, 0)) * x.in_pitch;
+        if (HASF) x.pfin += (size_t)min(RING_D - 1, max(x.f_last - it + 1, 0)) * x.f_pitch;
         if (edge_strip) NPDE_MAIN_LOOP(true, true, true);
         else NPDE_MAIN_LOOP(false, true, true);
         cp_async_wait<0>();
         // back to plain loads: x.pin must point at row it+1 again; row `it` is in registers (slot of parity 0)
         x.pin = xin + (size_t)(it + 1) * p.in_pitch;
+        if (HASF) x.pfin = fimg + (size_t)it * p.f_pitch;
       } else {
         if (edge_strip) NPDE_MAIN_LOOP(true, true, false);
         else NPDE_MAIN_LOOP(false, true, false);
@@ -826,9 +846,15 @@ int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaS
 template <int L>
 int launch_conv(ConvStreamParams &p, cudaStream_t st) {
   constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
-  const size_t smem = (size_t)512 * (DS + RING_D) * (npde::STREAM_THREADS / 32);  // y delay line + x row ring
-  static int cache = 0;
-  int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache);
+  // y delay line + x row ring (+ f row ring)
+  const size_t smem = (size_t)512 * (DS + (p.f ? 2 : 1) * RING_D) * (npde::STREAM_THREADS / 32);
+  static int cache[2] = {0, 0};
+#ifdef NPDE_DEV_ONLY_CONV3
+  int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache[0]);
+#else
+  int resident = p.f ? resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, true>, smem, &cache[1])
+                     : resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache[0]);
+#endif
   p.split = make_split(p.B, p.N, RC, R, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
 #ifdef NPDE_DEV_ONLY_CONV3  // tools/ab_bench.py: quick-to-compile tuning builds, clamp / no source only
