@@ -299,6 +299,8 @@ int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int a
 
 int fd_error_view(const FieldView &xv, const float *bc, int bc_kind, const float *f, int aggregate, float *err,
                   int B, int N, void *ws, size_t ws_bytes, cudaStream_t st) {
+  if (bc_kind == NPDE_BC_SQUARE && aggregate == NPDE_AGG_MAX && N >= 3)  // the streaming kernel (npde_stream.cu)
+    return fd_error_max_stream(xv, ref_view(f, N), err, B, N, st);
   ReduceWs r;
   int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
   if (rc) return rc;

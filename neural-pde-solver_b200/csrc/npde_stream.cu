@@ -801,6 +801,103 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   }
 }
 
+// ------------------------------------------------- residual (fd_error) ---
+// utils/heat_utils.py:108-132 on the square domain with aggregate 'max': per problem
+// max_{interior} |1/4 u + 1/4 l - c + 1/4 r + 1/4 d - f| (the loss-kernel fmaf chain, oracle orc_fd_error).
+// Same strip / band streaming as the Jacobi kernel, nothing is stored: every warp folds its maximum
+// into err[b] with an integer atomicMax on the float bits (non-negative floats order like integers,
+// a maximum is order independent, so the result is deterministic).  err must be zeroed beforehand.
+struct ResidStreamParams {
+  const float *in;
+  const float *f;  // NULL or the source
+  float *err;      // (B)
+  long in_bstride, f_bstride;
+  int in_pitch, f_pitch;
+  int in_perm, f_perm;
+  int B, N;
+  Split split;
+};
+
+__global__ void __launch_bounds__(npde::STREAM_THREADS)
+k_resid_stream(const NPDE_GRID_CONSTANT ResidStreamParams p) {
+  constexpr int RC = 4;
+  StripItem item;
+  if (!decode_item(p.B, p.N, p.split, item)) return;
+  const int lane = threadIdx.x & 31;
+  const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
+  const int N = p.N;
+  const int vs = item.strip * p.split.wv, ve = min(vs + p.split.wv, N);
+  const LaneCols c = make_cols(vs - RC, lane, N, vs, ve);
+  const int o0 = max(item.i0, 1), o1 = min(item.i1, N - 1);  // rows whose residual this band owns
+  if (o0 >= o1) return;
+  const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
+  const float *fin = p.f ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
+  const bool in_perm = p.in_perm != 0, f_perm = p.f_perm != 0;
+  const bool ld_ok = c.c0 >= 0 && c.c0 < N;
+  const unsigned own = c.store & c.interior;  // columns this lane contributes
+  const unsigned k0 = (own & 1u) ? 0xffffffffu : 0u, k1 = (own & 2u) ? 0xffffffffu : 0u,
+                 k2 = (own & 4u) ? 0xffffffffu : 0u, k3 = (own & 8u) ? 0xffffffffu : 0u;
+
+  f2 win[3][2];
+  float wl[3], wr[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    win[r][0] = win[r][1] = zero2();
+    wl[r] = wr[r] = 0.0f;
+  }
+  const int it_first = o0 - 1, it_last = o1;  // input rows o0-1 .. o1 (all exist: 0 <= o0-1, o1 <= N-1)
+  f2 pf[2], pff[2];
+  pff[0] = pff[1] = zero2();
+  load_row(xin + (size_t)it_first * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
+  float vmax = 0.0f;
+  const f2 q = bc2(0.25f), neg1 = bc2(-1.0f);
+  for (int it_base = it_first; it_base <= it_last; it_base += 3) {
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+      const int it = it_base + ph;
+      if (it > it_last) break;
+      const int s_new = ph, s_m1 = (ph + 2) % 3, s_m2 = (ph + 1) % 3;
+      win[s_new][0] = pf[0];
+      win[s_new][1] = pf[1];
+      const int row = it - 1;  // centre row of this step
+      if (row >= o0) {
+        const f2 m0 = win[s_m1][0], m1 = win[s_m1][1];
+        f2 a0 = mul2(q, win[s_m2][0]);
+        a0 = fma_lohi(0.25f, wl[s_m1], lo(m1), a0);
+        a0 = fma2(neg1, m0, a0);
+        a0 = fma2(q, m1, a0);
+        a0 = fma2(q, win[s_new][0], a0);
+        f2 a1 = mul2(q, win[s_m2][1]);
+        a1 = fma2(q, m0, a1);
+        a1 = fma2(neg1, m1, a1);
+        a1 = fma_lohi(0.25f, hi(m0), wr[s_m1], a1);
+        a1 = fma2(q, win[s_new][1], a1);
+        if (fin) {
+          a0 = sub2(a0, pff[0]);
+          a1 = sub2(a1, pff[1]);
+        }
+        a0 = and2(a0, k0 & 0x7fffffffu, k2 & 0x7fffffffu);  // |.| and column ownership in one mask
+        a1 = and2(a1, k1 & 0x7fffffffu, k3 & 0x7fffffffu);
+        vmax = fmaxf(vmax, fmaxf(fmaxf(lo(a0), hi(a0)), fmaxf(lo(a1), hi(a1))));
+      }
+      halo_scalars(win[s_new][0], win[s_new][1], lane_l, lane_r, wl[s_new], wr[s_new]);
+      const int nx = it + 1;
+      if (nx <= it_last) {
+        load_row(xin + (size_t)nx * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
+        if (L2_AHEAD > 0 && nx + L2_AHEAD <= it_last)
+          prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch, lane, c.in_img);
+      }
+      if (fin && it >= o0 && it < o1) {  // f row of the next step's centre row
+        load_row(fin + (size_t)it * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
+        if (L2_AHEAD > 0 && it + L2_AHEAD < o1) prefetch_row(fin + (size_t)(it + L2_AHEAD) * p.f_pitch, lane, c.in_img);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(NPDE_FULL_MASK, vmax, o));
+  if (lane == 0) atomicMax(reinterpret_cast<int *>(p.err) + item.b, __float_as_int(vmax));
+}
+
 // ------------------------------------------------------------- host side ---
 // Bands exist only to fill the machine when B * strips is small; every band re-streams
 // 2 * halo_rows rows and pays the pipeline fill, so bands are kept >= 8 * halo_rows rows long.
@@ -923,6 +1020,23 @@ int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, 
 }
 
 int jacobi_stream_max_depth(const float *f) { return f ? 1 : 8; }
+
+int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int B, int N, cudaStream_t st) {
+  ResidStreamParams p;
+  p.in = x.p; p.in_pitch = x.pitch; p.in_bstride = x.bstride; p.in_perm = x.perm;
+  p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride; p.f_perm = f.p ? f.perm : 0;
+  p.err = err; p.B = B; p.N = N;
+  if (!perm_ok(x.p, x.pitch, x.bstride, x.perm, N) || !perm_ok(f.p, f.pitch, f.bstride, f.perm, N)) return NPDE_ERR_ARG;
+  static int cache = 0;
+  int resident = resident_warps_cached((const void *)k_resid_stream, 0, &cache);
+  p.split = make_split(B, N, 4, 1, resident);
+  cudaError_t e = cudaMemsetAsync(err, 0, sizeof(float) * (size_t)B, st);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)((long)B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
+  NPDE_LAUNCH(k_resid_stream, grid, block, 0, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
 
 int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f, int depth,
                   int B, int N, cudaStream_t st) {
