@@ -357,6 +357,7 @@ int level_sizes_ok(int N, int L) {
 struct IterWs {
   float *buf[2];
   float *fpad;  // the source in the padded layout (Jacobi / Conv fast path)
+  float *vpad, *mpad;  // mask geometry: the two bc planes in the padded layout (Conv fast path)
   int pitch;
   long bstride;
   void *red;
@@ -370,6 +371,9 @@ struct IterWs {
     buf[0] = b.take<float>(cells);
     buf[1] = b.take<float>(cells);
     fpad = (iterator == NPDE_IT_JACOBI || iterator == NPDE_IT_CONV) ? b.take<float>(cells) : nullptr;
+    const bool mask_conv = iterator == NPDE_IT_CONV && bc_kind == NPDE_BC_MASK;
+    vpad = mask_conv ? b.take<float>(cells) : nullptr;
+    mpad = mask_conv ? b.take<float>(cells) : nullptr;
     red_bytes = npde::reduce_ws_bytes(B, N);
     red = b.take_bytes(red_bytes);
     step_bytes = 0;
@@ -460,8 +464,8 @@ int npde_conv_step_fwd(const float *x, const float *bc, int bc_kind, const float
   if (n_layers > 0 && !w) return NPDE_ERR_NULL;
   if (x == y) return NPDE_ERR_ARG;
   if (npde::conv_stream_supported(bc_kind, n_layers, w_host))
-    return npde::conv_stream(npde::ref_view(x, N), npde::ref_view_mut(y, N), bc, npde::ref_view(f, N), w_host,
-                             n_layers, act, B, N, S(stream));
+    return npde::conv_stream(npde::ref_view(x, N), npde::ref_view_mut(y, N), npde::bc_fields(bc, bc_kind, N),
+                             npde::ref_view(f, N), w_host, n_layers, act, B, N, S(stream));
   TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_CONV_FWD, B, N, bc_kind, n_layers, 0, 0, 0)));
   return conv_step_layered(x, bc, bc_kind, f, w, n_layers, act, y, B, N, ws, S(stream));
 }
@@ -783,6 +787,15 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       TRY(npde::copy_field(fv, fp, B, N, st));
       fv = npde::as_const(fp);
     }
+    // same for the two planes of a mask-geometry bc tensor
+    npde::BcFields bcf = npde::bc_fields(d->bc, d->bc_kind, N);
+    if (conv_fast && d->bc_kind == NPDE_BC_MASK && d->k >= 3) {
+      npde::FieldViewMut vp = {w.vpad, w.pitch, w.bstride, 1}, mp = {w.mpad, w.pitch, w.bstride, 1};
+      TRY(npde::copy_field(bcf.values, vp, B, N, st));
+      TRY(npde::copy_field(bcf.mask, mp, B, N, st));
+      bcf.values = npde::as_const(vp);
+      bcf.mask = npde::as_const(mp);
+    }
     int left = d->k, flip = 0, done = 0;
     while (left > 0) {
       int adv = 1;
@@ -795,7 +808,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       bool alias = final_launch && (const void *)d->x_out == (const void *)cur.p;  // k == 1 in place
       npde::FieldViewMut dst = (final_launch && !alias) ? last : pad[flip];
       if (conv_fast)
-        TRY(npde::conv_stream(cur, dst, d->bc, fv, d->w_host, d->n_layers, d->act, B, N, st));
+        TRY(npde::conv_stream(cur, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, st));
       else
         TRY(npde::jacobi_stream(cur, dst, d->bc, fv, adv, B, N, st));
       left -= adv;

@@ -82,8 +82,19 @@ int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream
 // npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)
 constexpr int STREAM_THREADS = 32;  // one warp strip per CTA (see decode_item in npde_stream.cu)
 
+// Boundary data of the stream kernels: the (B,4) scalars of the square domain, or the two planes of a
+// (B,2,N,N) mask-geometry bc tensor as field views (reference layout: pitch N, batch stride 2*N*N).
+struct BcFields {
+  const float *bc4;
+  FieldView values, mask;
+};
+inline BcFields bc_fields(const float *bc, int bc_kind, int N) {
+  if (bc_kind == NPDE_BC_MASK)
+    return BcFields{nullptr, FieldView{bc, N, 2L * N * N, 0}, FieldView{bc + (size_t)N * N, N, 2L * N * N, 0}};
+  return BcFields{bc, FieldView{nullptr, 0, 0, 0}, FieldView{nullptr, 0, 0, 0}};
+}
 // f.p == nullptr: Laplace.  perm views are accessed with 128-bit loads / stores, natural ones with 32-bit.
-int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f,
+int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f,
                 const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st);
 // depth in {1,2,4,8} Jacobi steps per launch (1 when f != NULL); square domain only
 int jacobi_stream_max_depth(const float *f);

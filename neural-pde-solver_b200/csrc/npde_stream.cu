@@ -316,6 +316,10 @@ struct ConvStreamParams {
   long in_bstride, out_bstride, f_bstride;
   int in_pitch, out_pitch, f_pitch;
   int in_perm, out_perm, f_perm;  // field is in the pair-permuted padded layout (128-bit accesses)
+  // mask geometry (bc = [values, mask], heat_utils.py:29-42): the two planes as field views, else NULL
+  const float *bv, *bm;
+  long bv_bstride, bm_bstride;
+  int bv_pitch, bm_pitch, bv_perm, bm_perm;
   int B, N, act;
   Split split;
   float w[4][9];
@@ -369,6 +373,8 @@ struct ConvState {
   f2 S[L][2][2];   // S[k-1]: the two live partial-sum rows of conv stage k.  S[k-1][P] has seen taps
                    // w0..w5 of its output row (this step finishes it), S[k-1][P^1] taps w0..w2.
   f2 pff[2];       // f row it-1, fetched one step earlier
+  f2 pm[2];        // mask geometry: mask row it-1, fetched one step earlier
+  f2 pv[2][2];     // mask geometry: pv[P] = value row it-1-L (this step's output row), pv[P^1] is being fetched
 };
 
 struct ConvLaneCtx {
@@ -379,12 +385,14 @@ struct ConvLaneCtx {
   bool ld_ok, st_ok; // permuted layout: this lane's 128-bit load / store is enabled
   const float *pin;  // this lane's group of four in the NEXT input row to fetch
   const float *pfin; // same for f
+  const float *pmin, *pvin;  // mask geometry: next mask row / value row to fetch
   float *pout;       // this lane's group of four in the output row of the current step
   char *delay;       // this lane's slot 0 of the y delay line (shared memory)
   char *ring;        // this lane's 16 bytes in slot 0 of the x row ring (shared memory)
   unsigned rslot;    // ring slot (byte offset) that holds x row it+1
   float top, bottom;
-  int N, i0, i1, x_last, f_last, in_pitch, out_pitch, f_pitch, lane, lane_l, lane_r;
+  int N, i0, i1, x_last, f_last, in_pitch, out_pitch, f_pitch, bm_pitch, bv_pitch, lane, lane_l, lane_r;
+  bool bm_perm, bv_perm;
 };
 
 #ifndef NPDE_EMU
@@ -412,11 +420,17 @@ __device__ __forceinline__ void pin_reg(unsigned &) {}
 //         (~260 instructions) stays inside the 6 KB L0 instruction cache.
 // DS = delay-line slots (power of two >= L+1), 512 bytes per slot and warp.
 // RINGED: (fast loops on permuted fields only) x rows arrive through the cp.async ring.
-template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, bool PERM, int P, bool RINGED = false>
+// MASK:   mask geometry (L-shape, cylinders, ...): bc = [values v, mask m], m in {0,1}.  G is
+//         x*(1-m)+v at every cell and every stage output is multiplied by the foreground 1-m
+//         (conv_iterator.py:23-30).  Per row the kernel builds the AND-masks "interior cell and
+//         m == 0" once (stage 0) and keeps them L steps in a second shared-memory delay line; they
+//         replace the column masks of EDGE (MASK implies EDGE) and the ring-row tests.
+template <int L, int ACT, bool HASF, bool MASK, bool MAIN, bool EDGE, bool PERM, int P, bool RINGED = false>
 __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
                                           unsigned &woff) {
   constexpr int DS = (L + 1 <= 4) ? 4 : 8;
   constexpr unsigned RING = DS * 512u - 1u;
+  constexpr unsigned KEEP_OFF = DS * 512u;  // the keep-mask delay line sits behind the y delay line (MASK only)
   const int N = x.N;
   const unsigned roff = (woff + (DS - L) * 512u) & RING;  // y written L steps ago
   const bool in_perm = PERM || x.in_perm, out_perm = PERM || x.out_perm, f_perm = PERM || x.f_perm;
@@ -460,10 +474,40 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     }
     rc0 = sub2(y0, C[0]);
     rc1 = sub2(y1, C[1]);
-    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc0 = rc1 = zero2();
-    if (EDGE) {
-      rc0 = and2(rc0, x.keep[0], x.keep[2]);
-      rc1 = and2(rc1, x.keep[1], x.keep[3]);
+    if (MASK) {
+      // keep masks of row it-1: interior cell (row and column) and not a Dirichlet cell
+      const bool row_in = MAIN || (r0 >= 1 && r0 <= N - 2);
+      uint4 kq;
+      kq.x = (row_in && lo(s.pm[0]) == 0.0f) ? x.keep[0] : 0u;
+      kq.y = (row_in && lo(s.pm[1]) == 0.0f) ? x.keep[1] : 0u;
+      kq.z = (row_in && hi(s.pm[0]) == 0.0f) ? x.keep[2] : 0u;
+      kq.w = (row_in && hi(s.pm[1]) == 0.0f) ? x.keep[3] : 0u;
+      *reinterpret_cast<uint4 *>(x.delay + KEEP_OFF + woff + 8 * x.lane) = kq;  // 16 bytes per lane and slot
+      rc0 = and2(rc0, kq.x, kq.z);
+      rc1 = and2(rc1, kq.y, kq.w);
+      // fetch mask row `it` (next step) and value row it-L (epilogue row of the next step)
+      const int nm = it, nv = it - L;
+      if (MAIN || (nm >= 1 && nm <= min(x.x_last, N - 2))) {
+        load_row(x.pmin, PERM || x.bm_perm, ld_ok, x.in_img, s.pm[0], s.pm[1]);
+        if (L2_AHEAD > 0 && nm + L2_AHEAD <= x.x_last)
+          prefetch_row(x.pmin + (size_t)L2_AHEAD * x.bm_pitch, x.lane, x.in_img);
+      } else {
+        s.pm[0] = s.pm[1] = bc2(1.0f);
+      }
+      x.pmin += x.bm_pitch;
+      if (MAIN || (nv >= 0 && nv <= N - 1 && nv < x.i1)) {
+        load_row(x.pvin, PERM || x.bv_perm, ld_ok, x.in_img, s.pv[P ^ 1][0], s.pv[P ^ 1][1]);
+        if (L2_AHEAD > 0 && nv + L2_AHEAD < x.i1) prefetch_row(x.pvin + (size_t)L2_AHEAD * x.bv_pitch, x.lane, x.in_img);
+      } else {
+        s.pv[P ^ 1][0] = s.pv[P ^ 1][1] = zero2();
+      }
+      if (MAIN || nv >= 0) x.pvin += x.bv_pitch;  // invariant: pvin points at row max(nv + 1, 0)
+    } else {
+      if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc0 = rc1 = zero2();
+      if (EDGE) {
+        rc0 = and2(rc0, x.keep[0], x.keep[2]);
+        rc1 = and2(rc1, x.keep[1], x.keep[3]);
+      }
     }
     halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
     // y waits L steps in the delay line; the two pairs go to separate 256-byte halves of the slot so
@@ -512,10 +556,17 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     mid[1] = fma2(bc2(w[1]), rc1, mid[1]);
     mid[1] = fma_lohi(w[2], hi(rc0), rr, mid[1]);
     if (k < L) {
-      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin0 = fin1 = zero2();
-      if (EDGE) {
-        fin0 = and2(fin0, x.keep[0], x.keep[2]);
-        fin1 = and2(fin1, x.keep[1], x.keep[3]);
+      if (MASK) {  // keep masks of row it-1-k, built k steps ago
+        const uint4 kq = *reinterpret_cast<const uint4 *>(x.delay + KEEP_OFF + 8 * x.lane +
+                                                          ((woff + (DS - k) * 512u) & RING));
+        fin0 = and2(fin0, kq.x, kq.z);
+        fin1 = and2(fin1, kq.y, kq.w);
+      } else {
+        if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin0 = fin1 = zero2();
+        if (EDGE) {
+          fin0 = and2(fin0, x.keep[0], x.keep[2]);
+          fin1 = and2(fin1, x.keep[1], x.keep[3]);
+        }
       }
       rc0 = fin0;
       rc1 = fin1;
@@ -523,7 +574,17 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
     } else {
       if (MAIN || (rk >= x.i0 && rk < x.i1)) {
         float o0, o1, o2, o3;  // columns c0..c3
-        if (MAIN || (rk >= 1 && rk <= N - 2)) {
+        if (MASK) {
+          // G on the mask geometry: pad(act(y + h)) * (1 - m) + v at every cell (heat_utils.py:51-53);
+          // m is 0 or 1, so the product is a select: keep == 0 on ring cells and Dirichlet cells
+          const f2 ya = *reinterpret_cast<const f2 *>(x.delay + roff);
+          const f2 yb = *reinterpret_cast<const f2 *>(x.delay + roff + 256);
+          const uint4 kq = *reinterpret_cast<const uint4 *>(x.delay + KEEP_OFF + 8 * x.lane + roff);
+          o0 = __fadd_rn(sel_bits(add_act<ACT>(lo(ya), lo(fin0)), kq.x, 0u), lo(s.pv[P][0]));
+          o2 = __fadd_rn(sel_bits(add_act<ACT>(hi(ya), hi(fin0)), kq.z, 0u), hi(s.pv[P][0]));
+          o1 = __fadd_rn(sel_bits(add_act<ACT>(lo(yb), lo(fin1)), kq.y, 0u), lo(s.pv[P][1]));
+          o3 = __fadd_rn(sel_bits(add_act<ACT>(hi(yb), hi(fin1)), kq.w, 0u), hi(s.pv[P][1]));
+        } else if (MAIN || (rk >= 1 && rk <= N - 2)) {
           const f2 ya = *reinterpret_cast<const f2 *>(x.delay + roff);
           const f2 yb = *reinterpret_cast<const f2 *>(x.delay + roff + 256);
           o0 = add_act<ACT>(lo(ya), lo(fin0));
@@ -533,7 +594,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
         } else {
           o0 = o1 = o2 = o3 = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
         }
-        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value
+        if (EDGE && !MASK) {  // pad + G on the columns: non-interior columns take the Dirichlet value
           o0 = sel_bits(o0, x.keep[0], x.gval[0]);
           o1 = sel_bits(o1, x.keep[1], x.gval[1]);
           o2 = sel_bits(o2, x.keep[2], x.gval[2]);
@@ -563,7 +624,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
 #ifndef NPDE_CONV_MIN_CTAS
 #define NPDE_CONV_MIN_CTAS 16
 #endif
-template <int L, int ACT, bool HASF>
+template <int L, int ACT, bool HASF, bool MASK>
 __global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_CONV_MIN_CTAS)
 k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   constexpr int R = L + 1;           // dependency radius of Phi_H
@@ -579,7 +640,7 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.lane_l = (lane + 31) & 31;
   x.lane_r = (lane + 1) & 31;
   x.delay = reinterpret_cast<char *>(ydl) + 8 * lane;
-  x.ring = reinterpret_cast<char *>(ydl) + DS * 512 + 16 * lane;  // behind the delay line
+  x.ring = reinterpret_cast<char *>(ydl) + (MASK ? 2 : 1) * DS * 512 + 16 * lane;  // behind the delay line(s)
   x.rslot = 0;
   x.N = p.N;
   const int N = p.N;
@@ -600,10 +661,19 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.in_pitch = p.in_pitch;
   x.out_pitch = p.out_pitch;
   x.f_pitch = p.f_pitch;
-  const float *bcb = p.bc4 + (size_t)item.b * 4;
-  x.top = __ldg(bcb + 0);
-  x.bottom = __ldg(bcb + 1);
-  const float left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+  float left = 0.0f, right = 0.0f;
+  x.top = x.bottom = 0.0f;
+  if (!MASK) {
+    const float *bcb = p.bc4 + (size_t)item.b * 4;
+    x.top = __ldg(bcb + 0);
+    x.bottom = __ldg(bcb + 1);
+    left = __ldg(bcb + 2);
+    right = __ldg(bcb + 3);
+  }
+  x.bm_pitch = p.bm_pitch;
+  x.bv_pitch = p.bv_pitch;
+  x.bm_perm = p.bm_perm != 0;
+  x.bv_perm = p.bv_perm != 0;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col = c.c0 + q;
@@ -613,20 +683,22 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
     pin_reg(x.gval[q]);
   }
   // the strip needs the EDGE code iff one of its 128 columns is not an interior column
-  const bool edge_strip = strip_is_edge(item.strip, p.split.wv, RC, N);
-  const bool all_perm = x.in_perm && x.out_perm && (!HASF || x.f_perm);
+  const bool edge_strip = MASK || strip_is_edge(item.strip, p.split.wv, RC, N);
+  const bool all_perm = x.in_perm && x.out_perm && (!HASF || x.f_perm) && (!MASK || (x.bm_perm && x.bv_perm));
 
   ConvState<L> s;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     s.X[h][0] = s.X[h][1] = zero2();
     s.yu[h] = s.pff[h] = zero2();
+    s.pm[h] = bc2(1.0f);
+    s.pv[h][0] = s.pv[h][1] = zero2();
 #pragma unroll
     for (int k = 0; k < L; ++k) s.S[k][h][0] = s.S[k][h][1] = zero2();
   }
   s.xhl = s.xhr = 0.0f;
 #pragma unroll
-  for (int d = 0; d < DS * 2; ++d) *reinterpret_cast<f2 *>(x.delay + d * 256) = zero2();
+  for (int d = 0; d < (MASK ? 2 : 1) * DS * 2; ++d) *reinterpret_cast<f2 *>(x.delay + d * 256) = zero2();
 #pragma unroll
   for (int d = 0; d < (HASF ? 2 : 1) * RING_D; ++d)
     *reinterpret_cast<float4 *>(x.ring + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -645,6 +717,15 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-L (clamped at 0)
   x.pin = xin + (size_t)(it_first + 1) * p.in_pitch;
   x.pfin = HASF ? fimg + (size_t)it_first * p.f_pitch : nullptr;
+  x.pmin = x.pvin = nullptr;
+  if (MASK) {
+    const float *mimg = p.bm + (size_t)item.b * p.bm_bstride + c.c0;
+    const float *vimg = p.bv + (size_t)item.b * p.bv_bstride + c.c0;
+    if (it_first - 1 >= 1)
+      load_row(mimg + (size_t)(it_first - 1) * p.bm_pitch, x.bm_perm, x.ld_ok, c.in_img, s.pm[0], s.pm[1]);
+    x.pmin = mimg + (size_t)it_first * p.bm_pitch;               // mask row `it`
+    x.pvin = vimg + (size_t)max(it_first - L, 0) * p.bv_pitch;   // value row max(it - L, 0)
+  }
   x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - L, 0) * p.out_pitch + c.c0;
   unsigned woff = 0;
 
@@ -658,8 +739,8 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
       // the fast loops iterate in place: the register assignment of a variant is set up once per band
 #define NPDE_MAIN_LOOP(EDGE_, PERM_, RINGED_)                                            \
   do {                                                                                   \
-    conv_step<L, ACT, HASF, true, EDGE_, PERM_, 0, RINGED_>(s, x, p, it, woff);          \
-    conv_step<L, ACT, HASF, true, EDGE_, PERM_, 1, RINGED_>(s, x, p, it + 1, woff);      \
+    conv_step<L, ACT, HASF, MASK, true, EDGE_, PERM_, 0, RINGED_>(s, x, p, it, woff);    \
+    conv_step<L, ACT, HASF, MASK, true, EDGE_, PERM_, 1, RINGED_>(s, x, p, it + 1, woff);\
     it += 2;                                                                             \
   } while (it + 1 <= main_hi)
       if (!all_perm) {
@@ -677,19 +758,19 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
         x.pin += (size_t)min(RING_D - 1, max(x.x_last - it, 0)) * x.in_pitch;
         if (HASF) x.pfin += (size_t)min(RING_D - 1, max(x.f_last - it + 1, 0)) * x.f_pitch;
         if (edge_strip) NPDE_MAIN_LOOP(true, true, true);
-        else NPDE_MAIN_LOOP(false, true, true);
+        else if (!MASK) NPDE_MAIN_LOOP(false, true, true);
         cp_async_wait<0>();
         // back to plain loads: x.pin must point at row it+1 again; row `it` is in registers (slot of parity 0)
         x.pin = xin + (size_t)(it + 1) * p.in_pitch;
         if (HASF) x.pfin = fimg + (size_t)it * p.f_pitch;
       } else {
         if (edge_strip) NPDE_MAIN_LOOP(true, true, false);
-        else NPDE_MAIN_LOOP(false, true, false);
+        else if (!MASK) NPDE_MAIN_LOOP(false, true, false);
       }
 #undef NPDE_MAIN_LOOP
     } else {
-      conv_step<L, ACT, HASF, false, true, false, 0>(s, x, p, it, woff);
-      if (it + 1 <= it_last) conv_step<L, ACT, HASF, false, true, false, 1>(s, x, p, it + 1, woff);
+      conv_step<L, ACT, HASF, MASK, false, true, false, 0>(s, x, p, it, woff);
+      if (it + 1 <= it_last) conv_step<L, ACT, HASF, MASK, false, true, false, 1>(s, x, p, it + 1, woff);
       it += 2;
     }
   }
@@ -934,8 +1015,13 @@ int resident_warps_cached(const void *kernel, size_t smem, int *cache) {
 
 template <int L, int ACT>
 int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
-  if (p.f) NPDE_LAUNCH((k_conv_stream<L, ACT, true>), grid, block, smem, st, p);
-  else NPDE_LAUNCH((k_conv_stream<L, ACT, false>), grid, block, smem, st, p);
+  if (p.bm) {
+    if (p.f) NPDE_LAUNCH((k_conv_stream<L, ACT, true, true>), grid, block, smem, st, p);
+    else NPDE_LAUNCH((k_conv_stream<L, ACT, false, true>), grid, block, smem, st, p);
+  } else {
+    if (p.f) NPDE_LAUNCH((k_conv_stream<L, ACT, true, false>), grid, block, smem, st, p);
+    else NPDE_LAUNCH((k_conv_stream<L, ACT, false, false>), grid, block, smem, st, p);
+  }
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
@@ -943,20 +1029,23 @@ int launch_conv_f(ConvStreamParams &p, dim3 grid, dim3 block, size_t smem, cudaS
 template <int L>
 int launch_conv(ConvStreamParams &p, cudaStream_t st) {
   constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
-  // y delay line + x row ring (+ f row ring)
-  const size_t smem = (size_t)512 * (DS + (p.f ? 2 : 1) * RING_D) * (npde::STREAM_THREADS / 32);
-  static int cache[2] = {0, 0};
+  // y delay line (+ keep-mask delay line) + x row ring (+ f row ring)
+  const size_t smem = (size_t)512 * ((p.bm ? 2 : 1) * DS + (p.f ? 2 : 1) * RING_D) * (npde::STREAM_THREADS / 32);
+  static int cache[4] = {0, 0, 0, 0};
 #ifdef NPDE_DEV_ONLY_CONV3
-  int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache[0]);
+  int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false, false>, smem, &cache[0]);
 #else
-  int resident = p.f ? resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, true>, smem, &cache[1])
-                     : resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false>, smem, &cache[0]);
+  int resident =
+      p.bm ? (p.f ? resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, true, true>, smem, &cache[3])
+                  : resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false, true>, smem, &cache[2]))
+           : (p.f ? resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, true, false>, smem, &cache[1])
+                  : resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false, false>, smem, &cache[0]));
 #endif
   p.split = make_split(p.B, p.N, RC, R, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
 #ifdef NPDE_DEV_ONLY_CONV3  // tools/ab_bench.py: quick-to-compile tuning builds, clamp / no source only
-  if (p.act != NPDE_ACT_CLAMP || p.f) return NPDE_ERR_ARG;
-  NPDE_LAUNCH((k_conv_stream<L, NPDE_ACT_CLAMP, false>), grid, block, smem, st, p);
+  if (p.act != NPDE_ACT_CLAMP || p.f || p.bm) return NPDE_ERR_ARG;
+  NPDE_LAUNCH((k_conv_stream<L, NPDE_ACT_CLAMP, false, false>), grid, block, smem, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 #else
@@ -986,7 +1075,8 @@ int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
 namespace npde {
 
 bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host) {
-  return bc_kind == NPDE_BC_SQUARE && n_layers >= 1 && n_layers <= 4 && w_host != nullptr;
+  return (bc_kind == NPDE_BC_SQUARE || bc_kind == NPDE_BC_MASK) && n_layers >= 1 && n_layers <= 4 &&
+         w_host != nullptr;
 }
 
 // the pair-permuted layout needs 16-byte aligned rows and room for a whole lane at the right edge
@@ -995,13 +1085,20 @@ static bool perm_ok(const void *p, int pitch, long bstride, int perm, int N) {
   return ((uintptr_t)p & 15) == 0 && (pitch & 3) == 0 && (bstride & 3) == 0 && pitch >= ((N + 3) & ~3);
 }
 
-int conv_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f,
+int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f,
                 const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st) {
   ConvStreamParams p;
+  p.bc4 = bc.bc4;
+  p.bv = bc.values.p; p.bv_pitch = bc.values.pitch; p.bv_bstride = bc.values.bstride; p.bv_perm = bc.values.perm;
+  p.bm = bc.mask.p; p.bm_pitch = bc.mask.pitch; p.bm_bstride = bc.mask.bstride; p.bm_perm = bc.mask.perm;
+  if ((bc.bc4 == nullptr) == (bc.mask.p == nullptr) || (bc.mask.p == nullptr) != (bc.values.p == nullptr))
+    return NPDE_ERR_BC;
+  if (!perm_ok(p.bv, p.bv_pitch, p.bv_bstride, p.bv_perm, N) || !perm_ok(p.bm, p.bm_pitch, p.bm_bstride, p.bm_perm, N))
+    return NPDE_ERR_ARG;
   p.in = in.p; p.in_pitch = in.pitch; p.in_bstride = in.bstride;
   p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride;
   p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride;
-  p.bc4 = bc4; p.B = B; p.N = N; p.act = act;
+  p.B = B; p.N = N; p.act = act;
   p.in_perm = in.perm; p.out_perm = out.perm; p.f_perm = f.p ? f.perm : 0;
   if (!perm_ok(in.p, in.pitch, in.bstride, in.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
       !perm_ok(f.p, f.pitch, f.bstride, f.perm, N))

@@ -188,6 +188,55 @@ def test_stream_partition_vs_oracle(be, oracle, B, N, L, has_f):
     assert_bitwise(be.n(j11), oracle.iterate("jacobi", x, bc, f, None, "none", 11)[0], "11 jacobi steps")
 
 
+def _mask_geometry(rng, B, N):
+    """Random obstacle geometries: ring + an L-shaped cut-out + discs, values in [0,1) on Dirichlet cells
+    and 0 elsewhere (utils/geometries.py conventions: bc = [values, mask])."""
+    m = np.zeros((B, N, N), np.float32)
+    m[:, 0, :] = m[:, -1, :] = m[:, :, 0] = m[:, :, -1] = 1
+    yy, xx = np.mgrid[0:N, 0:N]
+    for b in range(B):
+        if b % 2 == 0:
+            m[b, : N // 2, N // 2:] = 1
+        for _ in range(2):
+            cy, cx = rng.randint(N // 5, 4 * N // 5, 2)
+            r = rng.randint(max(N // 16, 1), max(N // 8, 2))
+            m[b][(yy - cy) ** 2 + (xx - cx) ** 2 <= r * r] = 1
+    v = (rng.rand(B, N, N).astype(np.float32)) * m
+    return np.stack([v, m], 1)
+
+
+@pytest.mark.parametrize("B,N,L,has_f,act", [(3, 129, 3, False, "clamp"), (2, 257, 3, True, "none"),
+                                             (5, 65, 2, True, "clamp"), (3, 33, 4, False, "none"),
+                                             (2, 129, 1, False, "clamp")])
+def test_mask_geometry_stream_vs_oracle(be, oracle, B, N, L, has_f, act):
+    """Fused Phi_H on mask geometries (bc = [values, mask]): single steps on the reference layout and
+    k-step loops on the permuted buffers, several strips and bands per image, against the CPU oracle."""
+    rng = np.random.RandomState(B * 77 + N + L)
+    bc = _mask_geometry(rng, B, N)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator(act, L)
+    it.is_bc_mask = True
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    with torch.no_grad():
+        y1 = it(xd, bcd, fd)
+        y6, _, efd = it.iterate(xd, bcd, fd, 6, want_fd=True)
+        y2, _, _ = it.iterate(xd, bcd, fd, 2)
+    assert_bitwise(be.n(y1), oracle.conv_step(x, bc, f, w, act), "mask conv step")
+    ref6, _, ref_fd = oracle.iterate("conv", x, bc, f, w, act, 6, want_fd=True)
+    assert_bitwise(be.n(y6), ref6, "6 mask conv steps")
+    assert_bitwise(be.n(efd), ref_fd, "fd_error rows on the mask geometry")
+    assert_bitwise(be.n(y2), oracle.iterate("conv", x, bc, f, w, act, 2)[0], "2 mask conv steps (reference layout)")
+
+
 # ------------------------------------------------------------ Multigrid / UNet --
 @pytest.mark.parametrize("name", golden_names("mg_"))
 def test_multigrid_iterator(be, name):

@@ -155,6 +155,8 @@ def main():
             cv.is_bc_mask = True
             ms = timed(lambda: cv(x, bc, None))
             emit("conv3_%s_257_b%d_step" % (kind, B), ms, B * N * N, bytes_per_cell=16)
+            ms = timed(lambda: cv.iterate(x, bc, None, 40))
+            emit("conv3_%s_257_b%d_iterate" % (kind, B), ms / 40, B * N * N, bytes_per_cell=16)
             jm = npde.JacobiIterator()
             jm.is_bc_mask = True
             ms = timed(lambda: jm.iterate(x, bc, None, 20))
