@@ -207,7 +207,8 @@ int jacobi_steps(const float *src, float *buf0, float *buf1, const float *bc, in
     if (bc_kind == NPDE_BC_SQUARE) {
       int depth = 1;
       if (!f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
-      TRY(jacobi_stream(ref_view(cur, N), ref_view_mut(dst, N), bc, ref_view(f, N), depth, B, N, st));
+      TRY(jacobi_stream(ref_view(cur, N), ref_view_mut(dst, N), bc_fields(bc, bc_kind, N), ref_view(f, N), depth, B,
+                        N, st));
       left -= depth;
     } else {
       TRY(fd_step_simple(cur, bc, bc_kind, f, dst, B, N, st));
@@ -371,9 +372,9 @@ struct IterWs {
     buf[0] = b.take<float>(cells);
     buf[1] = b.take<float>(cells);
     fpad = (iterator == NPDE_IT_JACOBI || iterator == NPDE_IT_CONV) ? b.take<float>(cells) : nullptr;
-    const bool mask_conv = iterator == NPDE_IT_CONV && bc_kind == NPDE_BC_MASK;
-    vpad = mask_conv ? b.take<float>(cells) : nullptr;
-    mpad = mask_conv ? b.take<float>(cells) : nullptr;
+    const bool mask_fast = (iterator == NPDE_IT_CONV || iterator == NPDE_IT_JACOBI) && bc_kind == NPDE_BC_MASK;
+    vpad = mask_fast ? b.take<float>(cells) : nullptr;
+    mpad = mask_fast ? b.take<float>(cells) : nullptr;
     red_bytes = npde::reduce_ws_bytes(B, N);
     red = b.take_bytes(red_bytes);
     step_bytes = 0;
@@ -772,7 +773,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   // come from the reduction kernels reading the same buffers (one launch per row, no host round trip);
   // they force one iterator application per launch.
   const bool conv_fast = it == NPDE_IT_CONV && npde::conv_stream_supported(d->bc_kind, d->n_layers, d->w_host);
-  const bool jac_fast = it == NPDE_IT_JACOBI && d->bc_kind == NPDE_BC_SQUARE;
+  const bool jac_fast = it == NPDE_IT_JACOBI;  // mask geometries: one step per launch
   if (conv_fast || jac_fast) {
     npde::FieldView cur = npde::ref_view(d->x_in, N);
     if (d->err_fd)
@@ -789,7 +790,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     }
     // same for the two planes of a mask-geometry bc tensor
     npde::BcFields bcf = npde::bc_fields(d->bc, d->bc_kind, N);
-    if (conv_fast && d->bc_kind == NPDE_BC_MASK && d->k >= 3) {
+    if (d->bc_kind == NPDE_BC_MASK && d->k >= 3) {
       npde::FieldViewMut vp = {w.vpad, w.pitch, w.bstride, 1}, mp = {w.mpad, w.pitch, w.bstride, 1};
       TRY(npde::copy_field(bcf.values, vp, B, N, st));
       TRY(npde::copy_field(bcf.mask, mp, B, N, st));
@@ -799,7 +800,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     int left = d->k, flip = 0, done = 0;
     while (left > 0) {
       int adv = 1;
-      if (jac_fast && !d->f && !want_err) {
+      if (jac_fast && !d->f && !want_err && d->bc_kind == NPDE_BC_SQUARE) {
         adv = depth;
         while (adv > left) adv >>= 1;
       }
@@ -810,7 +811,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       if (conv_fast)
         TRY(npde::conv_stream(cur, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, st));
       else
-        TRY(npde::jacobi_stream(cur, dst, d->bc, fv, adv, B, N, st));
+        TRY(npde::jacobi_stream(cur, dst, bcf, fv, adv, B, N, st));
       left -= adv;
       done += adv;
       if (final_launch && alias) {

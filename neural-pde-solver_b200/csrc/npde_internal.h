@@ -100,7 +100,8 @@ int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc
 int jacobi_stream_max_depth(const float *f);
 // fd_error(x, 'max') on the square domain, streaming (any view of x and f); zeroes and fills err (B)
 int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int B, int N, cudaStream_t st);
-int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f, int depth,
+// mask geometries (bc.mask.p != nullptr): depth 1 only
+int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f, int depth,
                   int B, int N, cudaStream_t st);
 
 }  // namespace npde

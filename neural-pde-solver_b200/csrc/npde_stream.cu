@@ -781,17 +781,23 @@ struct JacobiStreamParams {
   const float *in;
   float *out;
   const float *f;    // NULL, or the source (only with T == 1)
-  const float *bc4;  // (B,4)
+  const float *bc4;  // (B,4), or NULL on a mask geometry
   long in_bstride, out_bstride, f_bstride;
   int in_pitch, out_pitch, f_pitch;
   int in_perm, out_perm, f_perm;  // field is in the pair-permuted padded layout (128-bit accesses)
+  // mask geometry (only with T == 1): the two planes of bc = [values, mask] as field views
+  const float *bv, *bm;
+  long bv_bstride, bm_bstride;
+  int bv_pitch, bm_pitch, bv_perm, bm_perm;
   int B, N;
   Split split;
 };
 
-template <int T>
+// MASK (T == 1 only): G = y*(1-m)+v at every cell, Psi zero-padded on the whole grid (heat_utils.py:51-53,96-106)
+template <int T, bool MASK = false>
 __global__ void __launch_bounds__(npde::STREAM_THREADS)
 k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
+  static_assert(!MASK || T == 1, "mask geometries run one Jacobi step per launch");
   constexpr int RC = (T + 3) & ~3;  // column halo: whole lanes
   StripItem item;
   if (!decode_item(p.B, p.N, p.split, item)) return;
@@ -804,8 +810,13 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
   float *xout = p.out + (size_t)item.b * p.out_bstride + c.c0;
   const float *fin = (T == 1 && p.f) ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
-  const float *bcb = p.bc4 + (size_t)item.b * 4;
-  const float top = __ldg(bcb + 0), bottom = __ldg(bcb + 1), left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+  float top = 0.f, bottom = 0.f, left = 0.f, right = 0.f;
+  if (!MASK) {
+    const float *bcb = p.bc4 + (size_t)item.b * 4;
+    top = __ldg(bcb + 0), bottom = __ldg(bcb + 1), left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+  }
+  const float *vin = MASK ? p.bv + (size_t)item.b * p.bv_bstride + c.c0 : nullptr;
+  const float *min_ = MASK ? p.bm + (size_t)item.b * p.bm_bstride + c.c0 : nullptr;
   // permuted layout: a lane whose first column exists moves its whole group of four; the pad
   // columns it then touches only feed ring / out-of-grid cells and are rewritten by G or ignored
   const bool in_perm = p.in_perm != 0, out_perm = p.out_perm != 0, f_perm = p.f_perm != 0;
@@ -829,10 +840,15 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const int it_first = max(i0 - T, 0);
   const int it_last = i1 - 1 + T;
   const int x_last = min(it_last, N - 1);
-  f2 pf[2], pff[2];
-  pf[0] = pf[1] = pff[0] = pff[1] = zero2();
+  f2 pf[2], pff[2], pm[2], pv[2];
+  pf[0] = pf[1] = pff[0] = pff[1] = pv[0] = pv[1] = zero2();
+  pm[0] = pm[1] = bc2(1.0f);
   load_row(xin + (size_t)it_first * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
   if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
+  if (MASK && it_first >= 1) {  // mask / value rows of the first output row it_first - 1
+    load_row(min_ + (size_t)(it_first - 1) * p.bm_pitch, p.bm_perm != 0, ld_ok, c.in_img, pm[0], pm[1]);
+    load_row(vin + (size_t)(it_first - 1) * p.bv_pitch, p.bv_perm != 0, ld_ok, c.in_img, pv[0], pv[1]);
+  }
 
   for (int it_base = it_first; it_base <= it_last; it_base += 3) {
 #pragma unroll
@@ -851,7 +867,14 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
           o0 = sub2(o0, pff[0]);
           o1 = sub2(o1, pff[1]);
         }
-        apply_G_square(o0, o1, row, N, c, top, bottom, left, right);
+        if (MASK) {  // m is 0 or 1: x*(1-m) is a select, then + v
+          o0 = and2(o0, lo(pm[0]) == 0.0f ? 0xffffffffu : 0u, hi(pm[0]) == 0.0f ? 0xffffffffu : 0u);
+          o1 = and2(o1, lo(pm[1]) == 0.0f ? 0xffffffffu : 0u, hi(pm[1]) == 0.0f ? 0xffffffffu : 0u);
+          o0 = mk2(__fadd_rn(lo(o0), lo(pv[0])), __fadd_rn(hi(o0), hi(pv[0])));
+          o1 = mk2(__fadd_rn(lo(o1), lo(pv[1])), __fadd_rn(hi(o1), hi(pv[1])));
+        } else {
+          apply_G_square(o0, o1, row, N, c, top, bottom, left, right);
+        }
         if (s < T) {
           // rows above/below the grid must read as zero padding for the next stage's ring
           // cells only, and those are overwritten by G: no masking needed.
@@ -875,6 +898,14 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
         if (it <= N - 1) load_row(fin + (size_t)it * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
         if (L2_AHEAD > 0 && it + L2_AHEAD <= x_last)
           prefetch_row(fin + (size_t)(it + L2_AHEAD) * p.f_pitch, lane, c.in_img);
+      }
+      if (MASK && it <= N - 1 && it < i1) {
+        load_row(min_ + (size_t)it * p.bm_pitch, p.bm_perm != 0, ld_ok, c.in_img, pm[0], pm[1]);
+        load_row(vin + (size_t)it * p.bv_pitch, p.bv_perm != 0, ld_ok, c.in_img, pv[0], pv[1]);
+        if (L2_AHEAD > 0 && it + L2_AHEAD < i1) {
+          prefetch_row(min_ + (size_t)(it + L2_AHEAD) * p.bm_pitch, lane, c.in_img);
+          prefetch_row(vin + (size_t)(it + L2_AHEAD) * p.bv_pitch, lane, c.in_img);
+        }
       }
       if (L2_AHEAD > 0 && nx + L2_AHEAD <= x_last)
         prefetch_row(xin + (size_t)(nx + L2_AHEAD) * p.in_pitch, lane, c.in_img);
@@ -1058,14 +1089,14 @@ int launch_conv(ConvStreamParams &p, cudaStream_t st) {
 #endif
 }
 
-template <int T>
+template <int T, bool MASK = false>
 int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 3) & ~3;
   static int cache = 0;
-  int resident = resident_warps_cached((const void *)k_jacobi_stream<T>, 0, &cache);
+  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>, 0, &cache);
   p.split = make_split(p.B, p.N, RC, T, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
-  NPDE_LAUNCH((k_jacobi_stream<T>), grid, block, 0, st, p);
+  NPDE_LAUNCH((k_jacobi_stream<T, MASK>), grid, block, 0, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
@@ -1135,20 +1166,28 @@ int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int 
   return NPDE_OK;
 }
 
-int jacobi_stream(const FieldView &in, const FieldViewMut &out, const float *bc4, const FieldView &f, int depth,
+int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f, int depth,
                   int B, int N, cudaStream_t st) {
   JacobiStreamParams p;
+  p.bc4 = bc.bc4;
+  p.bv = bc.values.p; p.bv_pitch = bc.values.pitch; p.bv_bstride = bc.values.bstride; p.bv_perm = bc.values.perm;
+  p.bm = bc.mask.p; p.bm_pitch = bc.mask.pitch; p.bm_bstride = bc.mask.bstride; p.bm_perm = bc.mask.perm;
+  if ((bc.bc4 == nullptr) == (bc.mask.p == nullptr) || (bc.mask.p == nullptr) != (bc.values.p == nullptr))
+    return NPDE_ERR_BC;
+  if (!perm_ok(p.bv, p.bv_pitch, p.bv_bstride, p.bv_perm, N) || !perm_ok(p.bm, p.bm_pitch, p.bm_bstride, p.bm_perm, N))
+    return NPDE_ERR_ARG;
+  if (p.bm && depth != 1) return NPDE_ERR_ARG;
   p.in = in.p; p.in_pitch = in.pitch; p.in_bstride = in.bstride;
   p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride;
   p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride;
-  p.bc4 = bc4; p.B = B; p.N = N;
+  p.B = B; p.N = N;
   p.in_perm = in.perm; p.out_perm = out.perm; p.f_perm = f.p ? f.perm : 0;
   if (!perm_ok(in.p, in.pitch, in.bstride, in.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
       !perm_ok(f.p, f.pitch, f.bstride, f.perm, N))
     return NPDE_ERR_ARG;
   if (f.p && depth != 1) return NPDE_ERR_ARG;
   switch (depth) {
-    case 1: return launch_jacobi<1>(p, st);
+    case 1: return p.bm ? launch_jacobi<1, true>(p, st) : launch_jacobi<1>(p, st);
 #ifndef NPDE_DEV_ONLY_CONV3
     case 2: return launch_jacobi<2>(p, st);
     case 4: return launch_jacobi<4>(p, st);

@@ -235,6 +235,13 @@ def test_mask_geometry_stream_vs_oracle(be, oracle, B, N, L, has_f, act):
     assert_bitwise(be.n(y6), ref6, "6 mask conv steps")
     assert_bitwise(be.n(efd), ref_fd, "fd_error rows on the mask geometry")
     assert_bitwise(be.n(y2), oracle.iterate("conv", x, bc, f, w, act, 2)[0], "2 mask conv steps (reference layout)")
+    jac = be.npde.JacobiIterator()
+    jac.is_bc_mask = True
+    j7, _, jfd = jac.iterate(xd, bcd, fd, 7, want_fd=True)
+    refj, _, refj_fd = oracle.iterate("jacobi", x, bc, f, None, "none", 7, want_fd=True)
+    assert_bitwise(be.n(j7), refj, "7 Jacobi steps on the mask geometry (stream kernel)")
+    assert_bitwise(be.n(jfd), refj_fd, "their fd_error rows")
+    assert_bitwise(be.n(jac(xd, bcd, fd)), oracle.fd_step(x, bc, f), "single mask Jacobi step")
 
 
 # ------------------------------------------------------------ Multigrid / UNet --
