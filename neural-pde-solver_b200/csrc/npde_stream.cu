@@ -608,13 +608,13 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
   if (RINGED) {  // row it+1 has landed (at most RING_D - 1 younger copies pending): move it to registers
     constexpr unsigned RMASK = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
     cp_async_wait<(RING_D > 0 ? RING_D - 1 : 0)>();
-    const float4 v = *reinterpret_cast<const float4 *>(x.ring + x.rslot);
-    s.X[P ^ 1][0] = mk2(v.x, v.y);
-    s.X[P ^ 1][1] = mk2(v.z, v.w);
+    // two 64-bit reads: the pairs stay independent registers (a 128-bit read lands in a quad and is
+    // then copied into the two row slots)
+    s.X[P ^ 1][0] = *reinterpret_cast<const f2 *>(x.ring + x.rslot);
+    s.X[P ^ 1][1] = *reinterpret_cast<const f2 *>(x.ring + x.rslot + 8);
     if (HASF) {  // f row `it` travelled in the same copy group
-      const float4 fv = *reinterpret_cast<const float4 *>(x.ring + RING_D * 512 + x.rslot);
-      s.pff[0] = mk2(fv.x, fv.y);
-      s.pff[1] = mk2(fv.z, fv.w);
+      s.pff[0] = *reinterpret_cast<const f2 *>(x.ring + RING_D * 512 + x.rslot);
+      s.pff[1] = *reinterpret_cast<const f2 *>(x.ring + RING_D * 512 + x.rslot + 8);
     }
     x.rslot = (x.rslot + 512u) & RMASK;
   }
