@@ -133,21 +133,26 @@ struct ConvBwdWs {
 };
 
 // ------------------------------------------------------------- V-cycle ---
+// Level fields.  Square domain: pair-permuted padded layout (the Jacobi stream kernel then moves 128 bits
+// per lane; restriction / prolongation read and write the same views).  Mask geometry: reference layout,
+// smoothing by the simple Psi+G kernel.
 struct MgLevel {
   int N;
-  float *p[2];      // ping-pong fields
-  float *f;         // 4^l * injected source (level >= 1), or NULL
-  float *bc;        // injected [values, mask] (mask path, level >= 1)
+  npde::FieldViewMut p[2];  // ping-pong fields
+  float *f;                 // 4^l * injected source (level >= 1), or NULL
+  float *bc;                // injected [values, mask] (mask path, level >= 1)
 };
 struct MgWs {
   MgLevel lv[NPDE_MAX_LEVELS];
-  void carve(Bump &b, int B, int N, int bc_kind, int L, bool has_f, float *y) {
+  void carve(Bump &b, int B, int N, int bc_kind, int L, bool has_f) {
     int n = N;
+    const bool perm = bc_kind == NPDE_BC_SQUARE;
     for (int l = 0; l < L; ++l) {
       size_t cells = (size_t)B * n * n;
+      int pitch = perm ? ((n + 3) & ~3) : n;
+      long bstride = perm ? (long)npde_align_up((size_t)pitch * n, 64) : (long)n * n;
       lv[l].N = n;
-      lv[l].p[0] = (l == 0) ? y : b.take<float>(cells);
-      lv[l].p[1] = b.take<float>(cells);
+      for (int h = 0; h < 2; ++h) lv[l].p[h] = npde::FieldViewMut{b.take<float>((size_t)B * bstride), pitch, bstride, perm ? 1 : 0};
       lv[l].f = (l > 0 && has_f) ? b.take<float>(cells) : nullptr;
       lv[l].bc = (l > 0 && bc_kind == NPDE_BC_MASK) ? b.take<float>(2 * cells) : nullptr;
       n = (n - 1) / 2 + 1;
@@ -155,16 +160,19 @@ struct MgWs {
   }
 };
 
-// n Jacobi steps starting from `cur`, never writing into an external source;
-// returns the buffer holding the result.
-int smooth(const float *&cur, MgLevel &lv, const float *bc, int bc_kind, const float *f, int n, int B,
-           cudaStream_t st);
-int vcycle(MgWs &m, int l, int L, const float *src, const float *bc, const float *f, int bc_kind, int pre,
-           int post, int B, const float **result, cudaStream_t st) {
+// n Jacobi steps starting from `cur` on the level's ping-pong fields (never writing into an external source);
+// `last`, if given, receives the final iterate directly.  cur is updated to the view that holds the result.
+int smooth(npde::FieldView &cur, MgLevel &lv, const float *bc, int bc_kind, const float *f, int n, int B,
+           const npde::FieldViewMut *last, cudaStream_t st);
+
+int vcycle(MgWs &m, int l, int L, const npde::FieldView &src, const float *bc, const float *f, int bc_kind, int pre,
+           int post, int B, const npde::FieldViewMut *out, npde::FieldView *result, cudaStream_t st) {
   MgLevel &lv = m.lv[l];
-  const float *cur = src;
-  TRY(smooth(cur, lv, bc, bc_kind, f, pre, B, st));  // jacobi_iterator.py:41-42
-  if (l < L - 1) {
+  npde::FieldView cur = src;
+  const bool coarsest = l == L - 1;
+  // the very last operation of the level may write the caller's tensor directly
+  TRY(smooth(cur, lv, bc, bc_kind, f, pre, B, (coarsest && post == 0) ? out : nullptr, st));  // jacobi_iterator.py:41-42
+  if (!coarsest) {
     MgLevel &nx = m.lv[l + 1];
     const float *f_sub = nullptr, *bc_sub = bc;
     if (f) {  // :46-47
@@ -175,14 +183,14 @@ int vcycle(MgWs &m, int l, int L, const float *src, const float *bc, const float
       TRY(npde::subsample(bc, nx.bc, 2 * B, lv.N, 1.0f, st));
       bc_sub = nx.bc;
     }
-    TRY(npde::restrict_(cur, bc_sub, bc_kind, nx.p[0], B, lv.N, st));  // :58
-    const float *sub = nullptr;
-    TRY(vcycle(m, l + 1, L, nx.p[0], bc_sub, f_sub, bc_kind, pre, post, B, &sub, st));  // :60
-    float *dst = (cur == lv.p[0]) ? lv.p[1] : lv.p[0];
-    TRY(npde::prolong(sub, bc, bc_kind, dst, B, nx.N, st));  // :62 replaces x
-    cur = dst;
+    TRY(npde::restrict_view(cur, bc_sub, bc_kind, nx.p[0], B, lv.N, st));  // :58
+    npde::FieldView sub;
+    TRY(vcycle(m, l + 1, L, npde::as_const(nx.p[0]), bc_sub, f_sub, bc_kind, pre, post, B, nullptr, &sub, st));  // :60
+    const npde::FieldViewMut &dst = (post == 0 && out) ? *out : ((cur.p == lv.p[0].p) ? lv.p[1] : lv.p[0]);
+    TRY(npde::prolong_view(sub, bc, bc_kind, dst, B, nx.N, st));  // :62 replaces x
+    cur = npde::as_const(dst);
   }
-  TRY(smooth(cur, lv, bc, bc_kind, f, post, B, st));  // :65-66
+  TRY(smooth(cur, lv, bc, bc_kind, f, post, B, out, st));  // :65-66
   *result = cur;
   return NPDE_OK;
 }
@@ -190,47 +198,54 @@ int vcycle(MgWs &m, int l, int L, const float *src, const float *bc, const float
 }  // namespace
 
 namespace npde {
-// n Jacobi steps src -> buf0 / buf1 (ping-pong, reference layout); *result is
-// the buffer that holds the last iterate.  Square domain without a source runs
-// temporally blocked launches of depth 8/4/2/1; otherwise one launch per step.
-int jacobi_steps(const float *src, float *buf0, float *buf1, const float *bc, int bc_kind, const float *f, int n,
-                 int B, int N, const float **result, cudaStream_t st) {
-  const float *cur = src;
-  float *dst = buf0;
-  auto advance = [&]() {
-    cur = dst;
-    dst = (dst == buf0) ? buf1 : buf0;
-  };
-  int left = n;
+// n Jacobi steps src -> buf0 / buf1 (ping-pong views); *result is the view that holds the last iterate; the
+// final launch writes `last` if given.  Square domain without a source runs temporally blocked launches of
+// depth 4/2/1; otherwise one launch per step.
+int jacobi_steps_view(const FieldView &src, const FieldViewMut &buf0, const FieldViewMut &buf1, const float *bc,
+                      int bc_kind, const float *f, int n, int B, int N, const FieldViewMut *last,
+                      FieldView *result, cudaStream_t st) {
+  FieldView cur = src;
+  int flip = 0, left = n;
   while (left > 0) {
-    if (!dst) return NPDE_ERR_ARG;
+    int depth = 1;
+    if (bc_kind == NPDE_BC_SQUARE && !f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+    const bool final_launch = left - depth == 0;
+    const FieldViewMut &dst = (final_launch && last) ? *last : (flip ? buf1 : buf0);
+    if (!dst.p || dst.p == cur.p) return NPDE_ERR_ARG;
     if (bc_kind == NPDE_BC_SQUARE) {
-      int depth = 1;
-      if (!f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
-      TRY(jacobi_stream(ref_view(cur, N), ref_view_mut(dst, N), bc_fields(bc, bc_kind, N), ref_view(f, N), depth, B,
-                        N, st));
-      left -= depth;
+      TRY(jacobi_stream(cur, dst, bc_fields(bc, bc_kind, N), ref_view(f, N), depth, B, N, st));
     } else {
-      TRY(fd_step_simple(cur, bc, bc_kind, f, dst, B, N, st));
-      left -= 1;
+      if (cur.perm || dst.perm || cur.pitch != N || dst.pitch != N) return NPDE_ERR_ARG;
+      TRY(fd_step_simple(cur.p, bc, bc_kind, f, dst.p, B, N, st));
     }
-    advance();
+    left -= depth;
+    cur = as_const(dst);
+    flip ^= 1;
   }
   *result = cur;
+  return NPDE_OK;
+}
+
+int jacobi_steps(const float *src, float *buf0, float *buf1, const float *bc, int bc_kind, const float *f, int n,
+                 int B, int N, const float **result, cudaStream_t st) {
+  FieldView res;
+  TRY(jacobi_steps_view(ref_view(src, N), ref_view_mut(buf0, N), ref_view_mut(buf1, N), bc, bc_kind, f, n, B, N,
+                        nullptr, &res, st));
+  *result = res.p;
   return NPDE_OK;
 }
 }  // namespace npde
 
 namespace {
 
-int smooth(const float *&cur, MgLevel &lv, const float *bc, int bc_kind, const float *f, int n, int B,
-           cudaStream_t st) {
+int smooth(npde::FieldView &cur, MgLevel &lv, const float *bc, int bc_kind, const float *f, int n, int B,
+           const npde::FieldViewMut *last, cudaStream_t st) {
   if (n <= 0) return NPDE_OK;
-  const float *res = nullptr;
   // first destination must not be `cur`
-  float *b0 = (cur == lv.p[0]) ? lv.p[1] : lv.p[0];
-  float *b1 = (b0 == lv.p[0]) ? lv.p[1] : lv.p[0];
-  TRY(npde::jacobi_steps(cur, b0, b1, bc, bc_kind, f, n, B, lv.N, &res, st));
+  const npde::FieldViewMut &b0 = (cur.p == lv.p[0].p) ? lv.p[1] : lv.p[0];
+  const npde::FieldViewMut &b1 = (b0.p == lv.p[0].p) ? lv.p[1] : lv.p[0];
+  npde::FieldView res;
+  TRY(npde::jacobi_steps_view(cur, b0, b1, bc, bc_kind, f, n, B, lv.N, last, &res, st));
   cur = res;
   return NPDE_OK;
 }
@@ -538,10 +553,12 @@ int npde_mg_step(const float *x, const float *bc, int bc_kind, const float *f, i
   cudaStream_t st = S(stream);
   Bump b(ws);
   MgWs m;
-  m.carve(b, B, N, bc_kind, n_layers, f != nullptr, y);
-  const float *res = nullptr;
-  TRY(vcycle(m, 0, n_layers, x, bc, f, bc_kind, pre, post, B, &res, st));
-  return d2d(y, res, sizeof(float) * (size_t)B * N * N, st);
+  m.carve(b, B, N, bc_kind, n_layers, f != nullptr);
+  npde::FieldViewMut out = npde::ref_view_mut(y, N);
+  npde::FieldView res;
+  TRY(vcycle(m, 0, n_layers, npde::ref_view(x, N), bc, f, bc_kind, pre, post, B, &out, &res, st));
+  if (res.p != y) TRY(npde::copy_field(res, out, B, N, st));  // pre == post == 0 on a single level
+  return NPDE_OK;
 }
 
 int npde_unet_H(const float *r, const float *bc, int bc_kind, const float *w_first, const float *w_pool,
@@ -708,7 +725,7 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
     case NPDE_WS_MG: {
       if (n_layers < 1 || n_layers > NPDE_MAX_LEVELS) return 0;
       MgWs m;
-      m.carve(b, B, N, bc_kind, n_layers, true, nullptr);
+      m.carve(b, B, N, bc_kind, n_layers, true);
       return b.off;
     }
     case NPDE_WS_UNET_FWD: {

@@ -190,42 +190,51 @@ __global__ void k_subsample(const float *__restrict__ x, size_t x_bstride, float
   y[((size_t)b * M + I) * M + J] = scale == 1.0f ? v : __fmul_rn(scale, v);
 }
 
-__global__ void k_restrict(const float *__restrict__ x, BcView bc_sub, float *__restrict__ y, int N, int M) {
+__global__ void k_restrict(const float *__restrict__ x, int xp, long xbs, int xperm, BcView bc_sub,
+                           float *__restrict__ y, int yp, long ybs, int yperm, int N, int M) {
   int J = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (I >= M || J >= M) return;
   float v = 0.0f;
   if (I >= 1 && I <= M - 2 && J >= 1 && J <= M - 2) {
-    const float *p = x + ((size_t)b * N + 2 * I) * N + 2 * J;
-    v = __fmul_rn(0.125f, __ldg(p - N));
-    v = __fmaf_rn(0.125f, __ldg(p - 1), v);
-    v = __fmaf_rn(0.5f, __ldg(p), v);
-    v = __fmaf_rn(0.125f, __ldg(p + 1), v);
-    v = __fmaf_rn(0.125f, __ldg(p + N), v);
+    const float *row = x + (size_t)b * xbs + (size_t)(2 * I) * xp;
+    const int jc = view_col(2 * J, xperm);
+    v = __fmul_rn(0.125f, __ldg(row - xp + jc));
+    v = __fmaf_rn(0.125f, __ldg(row + view_col(2 * J - 1, xperm)), v);
+    v = __fmaf_rn(0.5f, __ldg(row + jc), v);
+    v = __fmaf_rn(0.125f, __ldg(row + view_col(2 * J + 1, xperm)), v);
+    v = __fmaf_rn(0.125f, __ldg(row + xp + jc), v);
   }
-  y[((size_t)b * M + I) * M + J] = npde_apply_G(v, bc_sub, b, I, J, M);
+  y[(size_t)b * ybs + (size_t)I * yp + view_col(J, yperm)] = npde_apply_G(v, bc_sub, b, I, J, M);
 }
 
-// bilinear x2, align_corners=True, from an M x M image with row pitch `pitch`
-// (element (I,J) at src[I*pitch+J]); see DESIGN.md for the two centre orders.
-__device__ __forceinline__ float bilinear_up_at(const float *__restrict__ src, int pitch, int i, int j,
-                                                bool nested) {
-  int I = i >> 1, J = j >> 1;
-  const float *p = src + (size_t)I * pitch + J;
-  if (!(i & 1) && !(j & 1)) return __ldg(p);
-  if (!(i & 1)) return __fmul_rn(0.5f, __fadd_rn(__ldg(p), __ldg(p + 1)));
-  if (!(j & 1)) return __fmul_rn(0.5f, __fadd_rn(__ldg(p), __ldg(p + pitch)));
-  float a = __ldg(p), bq = __ldg(p + 1), c = __ldg(p + pitch), d = __ldg(p + pitch + 1);
-  float s = nested ? __fadd_rn(__fadd_rn(a, bq), __fadd_rn(c, d))
-                   : __fadd_rn(__fadd_rn(__fadd_rn(a, bq), c), d);
-  return __fmul_rn(0.25f, s);
-}
-
-__global__ void k_prolong(const float *__restrict__ x, BcView bc, float *__restrict__ y, int M, int N,
-                          int nested) {
-  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
-  if (i >= N || j >= N) return;
-  float v = bilinear_up_at(x + (size_t)b * M * M, M, i, j, nested != 0);
-  y[((size_t)b * N + i) * N + j] = npde_apply_G(v, bc, b, i, j, N);
+// utils/heat_utils.py:340-350 interpolation: bilinear x2, align_corners=True (copy / 2-point / 4-point
+// means; see DESIGN.md for the two centre orders), then G with the fine bc.
+// One thread per COARSE cell (I,J): it loads its 2x2 coarse neighbourhood once and writes the
+// four fine cells (2I,2J), (2I,2J+1), (2I+1,2J), (2I+1,2J+1): no parity divergence, a quarter of the threads.
+// Any field view on both sides (the V-cycle keeps its levels in the pair-permuted layout).
+__global__ void k_prolong4(const float *__restrict__ x, int xp, long xbs, int xperm, BcView bc,
+                           float *__restrict__ y, int yp, long ybs, int yperm, int M, int N, int nested) {
+  int J = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (I >= M || J >= M) return;
+  const float *xb = x + (size_t)b * xbs;
+  const bool hasJ = J + 1 < M, hasI = I + 1 < M;
+  const int c0 = view_col(J, xperm), c1 = hasJ ? view_col(J + 1, xperm) : c0;
+  const float a = __ldg(xb + (size_t)I * xp + c0);
+  const float bq = hasJ ? __ldg(xb + (size_t)I * xp + c1) : 0.0f;
+  const float c = hasI ? __ldg(xb + (size_t)(I + 1) * xp + c0) : 0.0f;
+  const float d = (hasI && hasJ) ? __ldg(xb + (size_t)(I + 1) * xp + c1) : 0.0f;
+  float *yb = y + (size_t)b * ybs;
+  const int i = 2 * I, j = 2 * J;
+  yb[(size_t)i * yp + view_col(j, yperm)] = npde_apply_G(a, bc, b, i, j, N);
+  if (hasJ)
+    yb[(size_t)i * yp + view_col(j + 1, yperm)] = npde_apply_G(__fmul_rn(0.5f, __fadd_rn(a, bq)), bc, b, i, j + 1, N);
+  if (hasI) {
+    yb[(size_t)(i + 1) * yp + view_col(j, yperm)] = npde_apply_G(__fmul_rn(0.5f, __fadd_rn(a, c)), bc, b, i + 1, j, N);
+    if (hasJ) {
+      float sum = nested ? __fadd_rn(__fadd_rn(a, bq), __fadd_rn(c, d)) : __fadd_rn(__fadd_rn(__fadd_rn(a, bq), c), d);
+      yb[(size_t)(i + 1) * yp + view_col(j + 1, yperm)] = npde_apply_G(__fmul_rn(0.25f, sum), bc, b, i + 1, j + 1, N);
+    }
+  }
 }
 
 }  // namespace
@@ -359,18 +368,30 @@ int copy_field(const FieldView &src, const FieldViewMut &dst, int B, int N, cuda
 }
 
 int restrict_(const float *x, const float *bc_sub, int bc_kind, float *y, int B, int N, cudaStream_t st) {
+  return restrict_view(ref_view(x, N), bc_sub, bc_kind, ref_view_mut(y, (N - 1) / 2 + 1), B, N, st);
+}
+
+int restrict_view(const FieldView &x, const float *bc_sub, int bc_kind, const FieldViewMut &y, int B, int N,
+                  cudaStream_t st) {
   int M = (N - 1) / 2 + 1;
   BcView v{bc_sub, bc_kind};
-  NPDE_LAUNCH(k_restrict, grid2d(M, M, B), dim3(TX, TY), 0, st, x, v, y, N, M);
+  NPDE_LAUNCH(k_restrict, grid2d(M, M, B), dim3(TX, TY), 0, st, x.p, x.pitch, x.bstride, x.perm, v, y.p, y.pitch,
+              y.bstride, y.perm, N, M);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
 
 int prolong(const float *x, const float *bc, int bc_kind, float *y, int B, int M, cudaStream_t st) {
+  return prolong_view(ref_view(x, M), bc, bc_kind, ref_view_mut(y, 2 * M - 1), B, M, st);
+}
+
+int prolong_view(const FieldView &x, const float *bc, int bc_kind, const FieldViewMut &y, int B, int M,
+                 cudaStream_t st) {
   int N = 2 * M - 1;
   BcView v{bc, bc_kind};
   int nested = ((long)M * M > 1024) ? 1 : 0;  // ATen CPU bilinear order switch, see DESIGN.md
-  NPDE_LAUNCH(k_prolong, grid2d(N, N, B), dim3(TX, TY), 0, st, x, v, y, M, N, nested);
+  NPDE_LAUNCH(k_prolong4, grid2d(M, M, B), dim3(TX, TY), 0, st, x.p, x.pitch, x.bstride, x.perm, v, y.p, y.pitch,
+              y.bstride, y.perm, M, N, nested);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

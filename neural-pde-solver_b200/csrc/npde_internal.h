@@ -55,6 +55,11 @@ int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t 
 int subsample_strided(const float *x, size_t x_bstride, float *y, int B, int N, float scale, cudaStream_t st);
 int restrict_(const float *x, const float *bc_sub, int bc_kind, float *y, int B, int N, cudaStream_t st);
 int prolong(const float *x, const float *bc, int bc_kind, float *y, int B, int M, cudaStream_t st);
+// same on field views (the V-cycle keeps its levels in the pair-permuted layout); bc in the reference layout
+int restrict_view(const FieldView &x, const float *bc_sub, int bc_kind, const FieldViewMut &y, int B, int N,
+                  cudaStream_t st);
+int prolong_view(const FieldView &x, const float *bc, int bc_kind, const FieldViewMut &y, int B, int M,
+                 cudaStream_t st);
 
 // npde_conv_ops.cu -- layer-by-layer building blocks (UNet, deep conv stacks, backward)
 // mask: level mask (B, S+2, S+2) with batch stride mask_bstride floats, or NULL.
