@@ -91,17 +91,20 @@ class ClockSampler(object):
                  ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
                  ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
                  ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+        n = 0
         while not self._stop.is_set():
             try:
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                for name, bit in names:
-                    if mask & bit:
-                        self.reasons.add(name)
+                if n % 4 == 0:  # throttle reasons: a slower query, every 4th sample
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    for name, bit in names:
+                        if mask & bit:
+                            self.reasons.add(name)
             except Exception as exc:  # noqa: BLE001
                 self.error = repr(exc)
                 return
-            time.sleep(0.005)
+            n += 1
+            time.sleep(0.002)
 
     def stop(self):
         if self.thread is None:
@@ -304,7 +307,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
