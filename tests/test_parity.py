@@ -445,6 +445,80 @@ def test_solve_to_tolerance_counts(be, oracle):
         assert_bitwise(be.n(res2["x"]), cur, "solution, cheap variant")
 
 
+# ------------------------------------------------- BASELINE.json full sizes (GPU) --
+@pytest.mark.gpu
+def test_full_size_headline_vs_oracle(oracle):
+    """The bench workload itself (64 x 1025^2, Conv3, clamp): 3 fused steps and one single step against the
+    CPU oracle, bit for bit, plus the residual row; then size-independent properties over 100 iterations."""
+    be = Backend("cuda")
+    rng = np.random.RandomState(666)
+    B, N, L = 64, 1025, 3
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", L)
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd = be.t(x), be.t(bc)
+    with torch.no_grad():
+        y3, _, efd = it.iterate(xd, bcd, None, 3, want_fd=True)
+        y1 = it(xd, bcd, None)
+    ref3, _, ref_fd = oracle.iterate("conv", x, bc, None, w, "clamp", 3, want_fd=True)
+    assert_bitwise(be.n(y3), ref3, "3 fused Phi_H steps at 64 x 1025^2")
+    assert_bitwise(be.n(efd), ref_fd, "fd_error rows at 64 x 1025^2")
+    assert_bitwise(be.n(y1), oracle.conv_step(x, bc, None, w, "clamp"), "single step at 64 x 1025^2")
+    with torch.no_grad():
+        # k fused steps == k single steps (permuted fast path vs reference-layout path), 100 iterations
+        y100, _, _ = it.iterate(xd, bcd, None, 100)
+        z = xd
+        for _ in range(100):
+            z = it(z, bcd, None)
+        assert torch.equal(y100, z)
+        # problems are independent: a batch slice gives the slice of the batch result (what multi-GPU sharding relies on)
+        ys, _, _ = it.iterate(xd[5:9].contiguous(), bcd[5:9].contiguous(), None, 100)
+        assert torch.equal(ys, y100[5:9])
+        # the Dirichlet ring is reproduced exactly, the clamp keeps the range
+        assert torch.equal(y100[:, 0, 1:-1], bcd[:, 0:1].expand(-1, N - 2))
+        assert torch.equal(y100[:, :, 0], bcd[:, 2:3].expand(-1, N))
+        assert float(y100.min()) >= 0.0 and float(y100.max()) <= 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(2, 4097), (256, 257)])
+def test_full_size_other_configs(oracle, B, N):
+    """BASELINE configs 2 / 5 sizes: 4097^2 (square) and 256 x 257^2 (mask geometry): two fused steps of Conv3,
+    four Jacobi steps (temporal depth 4 on the square domain) and one V-cycle against the oracle, bit for bit."""
+    be = Backend("cuda")
+    rng = np.random.RandomState(N)
+    mask = N == 257
+    if mask:
+        bc = _mask_geometry(rng, B, N)
+    else:
+        bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    w = ((rng.rand(3, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", 3)
+    it.is_bc_mask = mask
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    jac = be.npde.JacobiIterator()
+    jac.is_bc_mask = mask
+    mg = be.npde.MultigridIterator(4, 2, 2)
+    mg.is_bc_mask = mask
+    xd, bcd = be.t(x), be.t(bc)
+    with torch.no_grad():
+        y2, _, _ = it.iterate(xd, bcd, None, 3)
+        j4, _, _ = jac.iterate(xd, bcd, None, 4)
+        v1 = mg(xd, bcd, None)
+    assert_bitwise(be.n(y2), oracle.iterate("conv", x, bc, None, w, "clamp", 3)[0], "3 Conv3 steps")
+    assert_bitwise(be.n(j4), oracle.iterate("jacobi", x, bc, None, None, "none", 4)[0], "4 Jacobi steps")
+    assert_bitwise(be.n(v1), oracle.multigrid_step(x, bc, None, 4, 2, 2), "V-cycle (4,2,2)")
+
+
 # --------------------------------------------------------------- error paths --
 def test_error_behaviour(be):
     x = torch.zeros(2, 17, 17, device=be.device)
