@@ -23,7 +23,11 @@ from .get_iterator import get_iterator
 
 
 class HeatModel(object):
-    def __init__(self, opt, world=None):
+    def __init__(self, opt, world=None, full_bptt=False):
+        """world: None, True (default process group) or a torch.distributed group: data-parallel training.
+        full_bptt: differentiate through ALL unrolled iterations (BASELINE.json config 4) instead of the
+        reference's last-step-only gradient (models/heat_model.py:48-53 detaches the first N-1 steps)."""
+        self.full_bptt = full_bptt
         self.nets, self.optimizers, self.schedulers = {}, {}, []
         self.iterator, self.compare_model, self.operations_ratio, self.is_train = get_iterator(opt)
         self.nets['iterator'] = self.iterator
@@ -77,8 +81,13 @@ class HeatModel(object):
         return [None if t is None else t.to(dev) for t in tensors]
 
     def _unrolled(self, start, bc, f, n_steps):
-        """n_steps-1 detached iterations (fused) + one differentiable iteration."""
+        """n_steps-1 detached iterations (fused) + one differentiable iteration; with full_bptt every
+        iteration is a differentiable step (the autograd tape keeps one field per step)."""
         y = start.detach()
+        if self.full_bptt:
+            for _ in range(n_steps):
+                y = self.iter_step(y, bc, f)
+            return y
         if n_steps > 1:
             y, _, _ = self.iterator.iterate(y, bc, f, n_steps - 1)
         return self.iter_step(y, bc, f)

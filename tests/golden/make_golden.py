@@ -262,6 +262,45 @@ def gen_backward():
                 save("bwd_%s_%s_%s" % (kind, geom, act), **out)
 
 
+def gen_bptt():
+    """Backprop through k unrolled iterations (BASELINE config 4): the reference's own iterator modules
+    chained k times WITHOUT the .detach() of HeatModel.train (models/heat_model.py:48-50), gradients from
+    autograd."""
+    for kind, geom, act, k in (("conv", "square", "clamp", 4), ("conv", "cylinders", "none", 3),
+                               ("unet", "square", "none", 3)):
+        seed()
+        B, N = 3, 33
+        x, bc, f = (square_problem(B, N, True) if geom == "square" else mask_problem(B, N, geom))
+        gt = torch.rand(B, N, N)
+        if kind == "conv":
+            it = ConvIterator(act, 3)
+            rand_conv_weights(it, 0.1)
+        else:
+            it = UNetIterator(act, 2, 1, 1)
+            rand_conv_weights(it, 0.1)
+        it.is_bc_mask = geom != "square"
+        xg = x.clone().requires_grad_(True)
+        y = xg
+        for _ in range(k):
+            y = it(y, bc, f)
+        loss = torch.nn.MSELoss()(y, gt)
+        loss.backward()
+        out = dict(x=npy(x), bc=npy(bc), f=None if f is None else npy(f), gt=npy(gt), y=npy(y),
+                   loss=np.float32(loss.item()), gx=npy(xg.grad), k=np.int64(k))
+        actc = {"none": 0, "clamp": 1, "sigmoid": 2}[act]
+        if kind == "conv":
+            out["w"] = np.stack([npy(l.weight)[0, 0] for l in it.layers])
+            out["gw"] = np.stack([npy(l.weight.grad)[0, 0] for l in it.layers])
+            out["meta"] = np.array([3, actc, int(geom != "square")])
+        else:
+            wf, wp, ws = unet_weights(it)
+            gg = lambda ml: np.stack([npy(l.weight.grad)[0, 0] for l in ml])
+            out.update(w_first=wf, w_pool=wp, w_second=ws, gw_first=gg(it.first_layers),
+                       gw_pool=gg(it.pooling_layers), gw_second=gg(it.second_layers),
+                       meta=np.array([2, 1, 1, actc, int(geom != "square")]))
+        save("bptt_%s_%s_%s_k%d" % (kind, geom, act, k), **out)
+
+
 def make_opt(**kw):
     d = dict(iterator="conv", activation="clamp", conv_n_layers=3, mg_n_layers=3,
              mg_pre_smoothing=2, mg_post_smoothing=2, cg_n_iters=4, geometry="square",
@@ -334,4 +373,5 @@ if __name__ == "__main__":
     gen_multigrid()
     gen_unet()
     gen_backward()
+    gen_bptt()
     gen_drivers()

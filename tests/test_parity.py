@@ -324,6 +324,48 @@ def test_unet_backward(be, name):
     assert rel_err(be.n(xg.grad), g["gx"]) <= 2e-5
 
 
+@pytest.mark.parametrize("name", golden_names("bptt_"))
+def test_backprop_through_k_steps(be, name):
+    """BASELINE config 4: gradients through k unrolled iterations, vs the reference's iterator modules chained
+    k times under autograd (no detach).  Tolerance 5e-5 of the largest entry (k reductions re-associated)."""
+    g = load_golden(name)
+    it = make_unet(be, g) if "w_first" in g else make_conv(be, g)
+    x, bc, f, gt = be.t(g["x"]), be.t(g["bc"]), be.t(g.get("f")), be.t(g["gt"])
+    xg = x.clone().requires_grad_(True)
+    y = xg
+    for _ in range(int(g["k"])):
+        y = it(y, bc, f)
+    loss = torch.nn.MSELoss()(y, gt)
+    loss.backward()
+    assert rel_err(be.n(y), g["y"]) <= 1e-5
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    if "w_first" in g:
+        for ml, key in ((it.first_layers, "gw_first"), (it.pooling_layers, "gw_pool"), (it.second_layers, "gw_second")):
+            gw = np.stack([be.n(l.weight.grad)[0, 0] for l in ml])
+            assert rel_err(gw, g[key]) <= 5e-5, (key, gw, g[key])
+    else:
+        gw = np.stack([be.n(l.weight.grad)[0, 0] for l in it.layers])
+        assert rel_err(gw, g["gw"]) <= 5e-5, (gw, g["gw"])
+    assert rel_err(be.n(xg.grad), g["gx"]) <= 5e-5
+
+
+def test_full_bptt_training_option(be):
+    """HeatModel(full_bptt=True) trains through every unrolled step; the default keeps the reference's
+    last-step-only gradient.  Same start, same N: the two weight updates must differ, the losses must agree."""
+    g = load_golden("driver_train_conv_sgd")
+    outs = []
+    for flag in (False, True):
+        model = be.npde.HeatModel(make_opt(optimizer="sgd", lr_init=1e-2, max_iter_steps=5), full_bptt=flag)
+        model.iterator.to(be.device)
+        with torch.no_grad():
+            model.iterator.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w0/")})
+        np.random.seed(3)
+        out = model.train(be.t(g["x"]), be.t(g["gt"]), be.t(g["bc"]), be.t(g["f"]))
+        outs.append((out["loss"]["loss_x"], np.stack([be.n(l.weight)[0, 0] for l in model.iterator.layers])))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[0][0])
+    assert np.abs(outs[0][1] - outs[1][1]).max() > 0
+
+
 # ------------------------------------------------------------------- drivers --
 def make_opt(**kw):
     import argparse
