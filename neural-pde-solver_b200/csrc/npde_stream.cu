@@ -64,6 +64,10 @@ __device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
 }
 // asynchronous 16-byte global -> shared copy and its group bookkeeping: synchronous in the emulator
 __device__ __forceinline__ void cp_async16(void *smem, const float *g) { memcpy(smem, g, 16); }
+__device__ __forceinline__ void cp_async4_zfill(void *smem, const float *g, bool valid) {
+  float v = valid ? *g : 0.0f;
+  memcpy(smem, &v, 4);
+}
 __device__ __forceinline__ void cp_async_commit() {}
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() {}
 #else
@@ -117,6 +121,13 @@ __device__ __forceinline__ void st_pairs(float *p, f2 a, f2 b) {
 // cp.async (LDGSTS): 16 bytes per lane straight from L2 into shared memory, no register staging
 __device__ __forceinline__ void cp_async16(void *smem, const float *g) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g)
+               : "memory");
+}
+// 4-byte variant with zero fill (src-size 0 writes zeros): coalesced element-wise copies of a row that is
+// only 4-byte aligned (reference layout)
+__device__ __forceinline__ void cp_async4_zfill(void *smem, const float *g, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g),
+               "r"(valid ? 4 : 0)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -390,6 +401,8 @@ struct ConvLaneCtx {
   char *delay;       // this lane's slot 0 of the y delay line (shared memory)
   char *ring;        // this lane's 16 bytes in slot 0 of the x row ring (shared memory)
   unsigned rslot;    // ring slot (byte offset) that holds x row it+1
+  unsigned nat_off;  // reference-layout ring fill: byte offset of column cs + lane inside a slot
+  unsigned nat_img;  // ... and bit k = column cs + lane + 32k exists
   float top, bottom;
   int N, i0, i1, x_last, f_last, in_pitch, out_pitch, f_pitch, bm_pitch, bv_pitch, lane, lane_l, lane_r;
   bool bm_perm, bv_perm;
@@ -403,6 +416,27 @@ __device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)
 #else
 __device__ __forceinline__ void pin_reg(unsigned &) {}
 #endif
+
+// Start the asynchronous copy of one row segment (this strip's 128 columns) into a ring slot, which always
+// holds the pair-permuted order.  p = this lane's group of four in that row.
+//   permuted field:  one 16-byte copy per lane;
+//   reference layout (rows only 4-byte aligned): four coalesced 4-byte copies per lane -- lane l moves columns
+//   cs + l + 32k, k = 0..3, each straight to its permuted position; out-of-image columns are zero-filled.
+__device__ __forceinline__ void ring_fill(char *slot_lane0 /* slot base + 16 * lane */, const float *p, bool perm,
+                                          bool ld_ok, const ConvLaneCtx &x) {
+  if (perm) {
+    if (ld_ok) cp_async16(slot_lane0, p);
+  } else {
+    // lanes write each other's bytes here: every lane must be done reading the slot's previous row
+    // (converged warps are; the barrier makes it explicit)
+    __syncwarp();
+    char *slot = slot_lane0 - 16 * x.lane;
+    const float *row = p - 3 * x.lane;  // column cs + lane
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      cp_async4_zfill(slot + x.nat_off + 128 * k, row + 32 * k, (x.nat_img >> k) & 1u);
+  }
+}
 
 // One step: input row `it` has arrived in s.X[P].  Stage 0 (Psi, residual) works on row it-1 and
 // conv stage k (1..L) on row it-1-k, each consuming the row the previous stage produced in THIS
@@ -458,7 +492,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
         // x.pfin points at f row it + RING_D - 1: it joins the copy group of x row it + RING_D below
         if (it + RING_D - 1 <= x.f_last) {
           constexpr unsigned RMASK_F = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
-          if (ld_ok) cp_async16(x.ring + RING_D * 512 + ((x.rslot + (RING_D - 1) * 512u) & RMASK_F), x.pfin);
+          ring_fill(x.ring + RING_D * 512 + ((x.rslot + (RING_D - 1) * 512u) & RMASK_F), x.pfin, f_perm, ld_ok, x);
           x.pfin += x.f_pitch;
         }
       } else {
@@ -523,7 +557,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
       // x.pin points at row it + RING_D: start its copy into the slot that was read one step ago
       constexpr unsigned RMASK = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
       if (it + RING_D <= x.x_last) {
-        if (ld_ok) cp_async16(x.ring + ((x.rslot + (RING_D - 1) * 512u) & RMASK), x.pin);
+        ring_fill(x.ring + ((x.rslot + (RING_D - 1) * 512u) & RMASK), x.pin, in_perm, ld_ok, x);
         if (RING_PF > 0 && it + RING_D + RING_PF <= x.x_last)
           prefetch_row(x.pin + (size_t)RING_PF * x.in_pitch, x.lane, EDGE ? x.in_img : 15u);
         x.pin += x.in_pitch;
@@ -608,6 +642,7 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
   if (RINGED) {  // row it+1 has landed (at most RING_D - 1 younger copies pending): move it to registers
     constexpr unsigned RMASK = (RING_D > 0 ? RING_D : 1) * 512u - 1u;
     cp_async_wait<(RING_D > 0 ? RING_D - 1 : 0)>();
+    if (!PERM) __syncwarp();  // reference-layout fills: a lane's bytes were copied by four other lanes
     // two 64-bit reads: the pairs stay independent registers (a 128-bit read lands in a quad and is
     // then copied into the two row slots)
     s.X[P ^ 1][0] = *reinterpret_cast<const f2 *>(x.ring + x.rslot);
@@ -655,6 +690,17 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
   x.out_perm = p.out_perm != 0;
   x.f_perm = p.f_perm != 0;
   x.ld_ok = c.c0 >= 0 && c.c0 < N;  // c0 is a multiple of 4 and a permuted pitch is >= round_up(N, 4)
+  {
+    // column cs + lane (+ 32k) lives in lane (lane / 4 + 8k)'s group, at the permuted position of lane % 4
+    const int q = lane & 3;
+    x.nat_off = (unsigned)((lane >> 2) * 16 + (((q & 1) << 1) | (q >> 1)) * 4);
+    x.nat_img = 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int col = cs + lane + 32 * k;
+      if (col >= 0 && col < N) x.nat_img |= 1u << k;
+    }
+  }
   x.st_ok = c.store != 0u;          // strip ranges are multiples of 4: a lane stores all of its columns or none
   x.i0 = item.i0;
   x.i1 = item.i1;
@@ -743,28 +789,28 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
     conv_step<L, ACT, HASF, MASK, true, EDGE_, PERM_, 1, RINGED_>(s, x, p, it + 1, woff);\
     it += 2;                                                                             \
   } while (it + 1 <= main_hi)
-      if (!all_perm) {
-        NPDE_MAIN_LOOP(true, false, false);
-      } else if (RING_D > 0) {
+      if (RING_D > 0) {
         // fill the ring: x row `it` is in registers, rows it+1 .. it+RING_D-1 start now
         x.rslot = 0;
 #pragma unroll
         for (int d = 0; d < RING_D - 1; ++d) {
-          if (it + 1 + d <= x.x_last && x.ld_ok) cp_async16(x.ring + d * 512, x.pin + (size_t)d * x.in_pitch);
-          if (HASF && it + d <= x.f_last && x.ld_ok)  // f runs one row behind x
-            cp_async16(x.ring + (RING_D + d) * 512, x.pfin + (size_t)d * x.f_pitch);
+          if (it + 1 + d <= x.x_last) ring_fill(x.ring + d * 512, x.pin + (size_t)d * x.in_pitch, x.in_perm, x.ld_ok, x);
+          if (HASF && it + d <= x.f_last)  // f runs one row behind x
+            ring_fill(x.ring + (RING_D + d) * 512, x.pfin + (size_t)d * x.f_pitch, x.f_perm, x.ld_ok, x);
           cp_async_commit();
         }
         x.pin += (size_t)min(RING_D - 1, max(x.x_last - it, 0)) * x.in_pitch;
         if (HASF) x.pfin += (size_t)min(RING_D - 1, max(x.f_last - it + 1, 0)) * x.f_pitch;
-        if (edge_strip) NPDE_MAIN_LOOP(true, true, true);
+        if (!all_perm) NPDE_MAIN_LOOP(true, false, true);  // any mix of layouts: run-time flags per field
+        else if (edge_strip) NPDE_MAIN_LOOP(true, true, true);
         else if (!MASK) NPDE_MAIN_LOOP(false, true, true);
         cp_async_wait<0>();
         // back to plain loads: x.pin must point at row it+1 again; row `it` is in registers (slot of parity 0)
         x.pin = xin + (size_t)(it + 1) * p.in_pitch;
         if (HASF) x.pfin = fimg + (size_t)it * p.f_pitch;
       } else {
-        if (edge_strip) NPDE_MAIN_LOOP(true, true, false);
+        if (!all_perm) NPDE_MAIN_LOOP(true, false, false);
+        else if (edge_strip) NPDE_MAIN_LOOP(true, true, false);
         else if (!MASK) NPDE_MAIN_LOOP(false, true, false);
       }
 #undef NPDE_MAIN_LOOP
