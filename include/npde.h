@@ -148,6 +148,14 @@ int npde_unet_step_fwd(const float *x, const float *bc, int bc_kind, const float
                        const float *w_pool, const float *w_second, int n_layers, int pre, int post, int act,
                        float *y, int B, int N, void *ws, size_t ws_bytes, void *stream);
 
+/* Same with an optional HOST copy of the weights, w_host = first | pool | second concatenated as in
+ * npde_iterate_desc.w.  With it (and 1 <= pre, post <= 4) the finest level runs as two fused streaming kernels
+ * (Psi + residual + pre-smoothing convs; post-smoothing convs + skip + y + act + G); without it this is
+ * npde_unet_step_fwd. */
+int npde_unet_step_fwd_hw(const float *x, const float *bc, int bc_kind, const float *f, const float *w_first,
+                          const float *w_pool, const float *w_second, const float *w_host, int n_layers, int pre,
+                          int post, int act, float *y, int B, int N, void *ws, size_t ws_bytes, void *stream);
+
 /* Backward of one UNetIterator.forward (autograd in the reference, models/heat_model.py:52-53,71-72 with
  * --iterator unet): recomputes the forward with a tape of every layer input, then walks it back.
  * gout = dL/dy (B,N,N); gradients OVERWRITE gw_first/gw_pool/gw_second; gx (B,N,N) may be NULL.

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "npde_unet_H": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_unet_step_fwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _int, _int,
                                   _vp, _size, _vp]),
+    "npde_unet_step_fwd_hw": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _int,
+                                     _int, _vp, _size, _vp]),
     "npde_unet_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp,
                                   _vp, _int, _int, _vp, _size, _vp]),
     "npde_iterate": (_int, [ctypes.POINTER(IterateDesc), _vp]),

@@ -318,11 +318,15 @@ int unet_build_masks(UnetWs &u, const float *bc, int bc_kind, int B, int N, int 
 }
 
 // unet_iterator.py:52-85 on a tensor already multiplied by masks[0]; src (B,s0,s0) -> out
-int unet_core(UnetWs &u, const float *src, const float *wf, const float *wp, const float *wsnd, int L, int pre,
-              int post, float *out, int B, cudaStream_t st) {
+// unet_iterator.py:52-85 from level `l0` down and back up to level l0, on a tensor that is already multiplied
+// by masks[l0]; src (B,s_l0,s_l0).  *result = the level-l0 tensor after its post-smoothing convs and skip add
+// (what the reference upsamples next, or h when l0 == 0); it lives in u.t0 / u.t1.
+// skip0: where the level-l0 skip tensor is kept (u.skip[l0] unless the caller already has it).
+int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const float *wp, const float *wsnd, int L,
+                int pre, int post, const float **result, int B, cudaStream_t st) {
   const float *cur = src;
   auto other = [&](const float *c) -> float * { return (c == u.t0) ? u.t1 : u.t0; };
-  for (int l = 0; l < L; ++l) {
+  for (int l = l0; l < L; ++l) {
     int s = u.s[l];
     for (int j = 0; j < pre; ++j) {
       float *dst = other(cur);
@@ -336,7 +340,7 @@ int unet_core(UnetWs &u, const float *src, const float *wf, const float *wp, con
       cur = dst;
     }
   }
-  for (int i = 0; i < L; ++i) {
+  for (int i = 0; i < L - l0; ++i) {
     int l = L - 1 - i, s = u.s[l];
     for (int j = 0; j < post; ++j) {
       float *dst = other(cur);
@@ -345,19 +349,42 @@ int unet_core(UnetWs &u, const float *src, const float *wf, const float *wp, con
     }
     float *acc = const_cast<float *>(cur);
     if (cur == src) {  // pre == post == 0 on a single level: do not write into the caller's input
-      acc = u.t0;
+      acc = other(cur);
       TRY(d2d(acc, cur, sizeof(float) * (size_t)B * s * s, st));
     }
     TRY(npde::add_inplace(acc, u.skip[l], (size_t)B * s * s, st));  // :76
     cur = acc;
-    if (i < L - 1) {
+    if (l > l0) {
       float *dst = other(cur);
       TRY(npde::pad_up_crop(cur, s, u.mask[l - 1], u.mbs[l - 1], dst, B, st));  // :78-83
       cur = dst;
     }
   }
-  return d2d(out, cur, sizeof(float) * (size_t)B * u.s[0] * u.s[0], st);
+  *result = cur;
+  return NPDE_OK;
 }
+
+int unet_core(UnetWs &u, const float *src, const float *wf, const float *wp, const float *wsnd, int L, int pre,
+              int post, float *out, int B, cudaStream_t st) {
+  const float *res = nullptr;
+  TRY(unet_levels(u, 0, src, wf, wp, wsnd, L, pre, post, &res, B, st));
+  return d2d(out, res, sizeof(float) * (size_t)B * u.s[0] * u.s[0], st);
+}
+
+// Frames of the fused finest level (npde_unet_step_fwd with host weights): skip_0, y and the upsampled
+// coarse correction, all in the pair-permuted padded layout.
+struct UnetFusedWs {
+  float *skip0, *y0, *up0;
+  int pitch;
+  long bstride;
+  void carve(Bump &b, int B, int N) {
+    pitch = (N + 3) & ~3;
+    bstride = (long)npde_align_up((size_t)pitch * N, 64);
+    skip0 = b.take<float>((size_t)B * bstride);
+    y0 = b.take<float>((size_t)B * bstride);
+    up0 = b.take<float>((size_t)B * bstride);
+  }
+};
 
 int level_sizes_ok(int N, int L) {
   int n = N;
@@ -611,6 +638,58 @@ int npde_unet_step_fwd(const float *x, const float *bc, int bc_kind, const float
   return npde::combine(u.y_int, h, bc, bc_kind, act, y, B, N, st);
 }
 
+// The finest level of a U-Net step fused into two streaming kernels (head: Psi, residual and the
+// pre-smoothing convs; tail: post-smoothing convs, + skip, + y, act, G); the coarser levels run layer by layer
+// in between.  Needs host copies of the weights (they travel as kernel parameters).
+static bool unet_fused_ok(int n_layers, int pre, int post, const float *w_host) {
+  return w_host != nullptr && pre >= 1 && pre <= 4 && post >= 1 && post <= 4 && n_layers >= 1;
+}
+
+int npde_unet_step_fwd_hw(const float *x, const float *bc, int bc_kind, const float *f, const float *w_first,
+                          const float *w_pool, const float *w_second, const float *w_host, int n_layers, int pre,
+                          int post, int act, float *y, int B, int N, void *ws, size_t ws_bytes, void *stream) {
+  if (!unet_fused_ok(n_layers, pre, post, w_host))
+    return npde_unet_step_fwd(x, bc, bc_kind, f, w_first, w_pool, w_second, n_layers, pre, post, act, y, B, N, ws,
+                              ws_bytes, stream);
+  TRY(npde::check_common(x, y, B, N));
+  TRY(npde::check_bc(bc, bc_kind));
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  if (n_layers > NPDE_MAX_LEVELS) return NPDE_ERR_LAYERS;
+  if (!level_sizes_ok(N, n_layers)) return NPDE_ERR_SIZE;
+  if (!w_first || !w_second || (n_layers > 1 && !w_pool)) return NPDE_ERR_NULL;
+  if (x == y) return NPDE_ERR_ARG;
+  TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_UNET_FWD, B, N, bc_kind, n_layers, pre, post, 0)));
+  cudaStream_t st = S(stream);
+  const int L = n_layers;
+  Bump b(ws);
+  UnetWs u;
+  u.carve(b, B, N, L, bc_kind == NPDE_BC_MASK);
+  b.take<float>((size_t)B * u.s[0] * u.s[0]);  // (layout of the layered path: h, r0)
+  b.take<float>((size_t)B * u.s[0] * u.s[0]);
+  UnetFusedWs fw;
+  fw.carve(b, B, N);
+  TRY(unet_build_masks(u, bc, bc_kind, B, N, L, st));
+  const float *wh_first = w_host, *wh_second = w_host + 9 * ((size_t)L * pre + (L - 1));
+  npde::BcFields bcf = npde::bc_fields(bc, bc_kind, N);
+  npde::FieldViewMut skipv = {fw.skip0, fw.pitch, fw.bstride, 1};
+  // head: x -> y (frame), skip_0 = pre-smoothed masked residual (frame)
+  TRY(npde::conv_head_stream(npde::ref_view(x, N), bcf, npde::ref_view(f, N), wh_first, pre, skipv, fw.y0, B, N, st));
+  npde::FieldView rin = npde::as_const(skipv);  // single level: the post convs start from skip_0 itself
+  if (L > 1) {
+    // pooling conv of level 0 reads the skip frame, then levels 1 .. L-1 layer by layer
+    float *lvl1 = u.t0;
+    TRY(npde::conv3x3_view(ArrView{fw.skip0, fw.pitch, fw.bstride, 1, 1}, u.s[0], w_pool, 2, 0, u.mask[1], u.mbs[1], lvl1,
+                           u.s[1], B, st));
+    const float *res = nullptr;
+    TRY(unet_levels(u, 1, lvl1, w_first, w_pool, w_second, L, pre, post, &res, B, st));
+    TRY(npde::pad_up_crop_view(res, u.s[1], u.mask[0], u.mbs[0], ArrViewMut{fw.up0, fw.pitch, fw.bstride, 1, 1}, B, st));
+    rin = npde::FieldView{fw.up0, fw.pitch, fw.bstride, 1};
+  }
+  // tail: post-smoothing convs of level 0, + skip_0, + y, act, pad, G
+  return npde::conv_tail_stream(rin, fw.skip0, fw.y0, bcf, wh_second + 9 * (size_t)(L - 1) * post, post, act,
+                                npde::ref_view_mut(y, N), B, N, st);
+}
+
 int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float *f, const float *w_first,
                        const float *w_pool, const float *w_second, int n_layers, int pre, int post, int act,
                        const float *gout, float *gw_first, float *gw_pool, float *gw_second, float *gx, int B,
@@ -734,6 +813,8 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
       u.carve(b, B, N, n_layers, bc_kind == NPDE_BC_MASK);
       b.take<float>((size_t)B * (N - 2) * (N - 2));
       b.take<float>((size_t)B * (N - 2) * (N - 2));
+      UnetFusedWs fw;  // frames of the fused finest level (npde_unet_step_fwd_hw)
+      fw.carve(b, B, N);
       return b.off;
     }
     case NPDE_WS_UNET_BWD: {
@@ -874,8 +955,8 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
                          w.step_bytes, stream));
         break;
       default:
-        TRY(npde_unet_step_fwd(cur, d->bc, d->bc_kind, d->f, wf, wp, wsnd, d->n_layers, d->pre, d->post, d->act,
-                               nxt, B, N, w.step, w.step_bytes, stream));
+        TRY(npde_unet_step_fwd_hw(cur, d->bc, d->bc_kind, d->f, wf, wp, wsnd, d->w_host, d->n_layers, d->pre, d->post,
+                                  d->act, nxt, B, N, w.step, w.step_bytes, stream));
         break;
     }
     cur = nxt;

@@ -54,6 +54,27 @@ __device__ __forceinline__ float npde_act_grad(float z, int act) {
   return 1.0f;
 }
 
+// column j inside a row of a field view: the pair-permuted layout stores every aligned group of four
+// columns (c0,c1,c2,c3) as (c0,c2,c1,c3) (npde_internal.h FieldView)
+__device__ __forceinline__ int npde_view_col(int j, int perm) {
+  return perm ? ((j & ~3) | ((j & 1) << 1) | ((j >> 1) & 1)) : j;
+}
+
+// An H x H array that may live inside a frame: element (i,j) at p[b*bstride + (i+off)*pitch + col(j+off)].
+// A plain (B,H,H) array is {p, H, H*H, 0, 0}; the interior of a (B,N,N) frame is {p, pitch, bstride, perm, 1}.
+struct ArrView {
+  const float *p;
+  int pitch;
+  long bstride;
+  int perm, off;
+};
+struct ArrViewMut {
+  float *p;
+  int pitch;
+  long bstride;
+  int perm, off;
+};
+
 // Jacobi 5-point average, taps in the oracle's order: up, left, right, down.
 __device__ __forceinline__ float npde_psi(float u, float l, float r, float d) {
   float acc = __fmul_rn(0.25f, u);

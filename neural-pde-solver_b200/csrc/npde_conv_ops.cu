@@ -15,6 +15,12 @@ inline dim3 grid2d(int W, int H, int B) { return dim3((W + TX - 1) / TX, (H + TY
 __device__ __forceinline__ float ldz(const float *__restrict__ p, int H, int i, int j) {
   return (i < 0 || j < 0 || i >= H || j >= H) ? 0.0f : __ldg(p + (size_t)i * H + j);
 }
+// same through an array view (pb = view base of this image)
+__device__ __forceinline__ float ldzv(const float *__restrict__ pb, const ArrView &v, int H, int i, int j) {
+  return (i < 0 || j < 0 || i >= H || j >= H)
+             ? 0.0f
+             : __ldg(pb + (size_t)(i + v.off) * v.pitch + npde_view_col(j + v.off, v.perm));
+}
 
 // foreground multiplier of cell (i,j) of an S x S interior: 1 - mask[(i+1),(j+1)]
 // with mask the (S+2) x (S+2) level mask  (conv_iterator.py:24, unet_iterator.py:43-48).
@@ -23,22 +29,21 @@ __device__ __forceinline__ float fg_at(const float *__restrict__ mask, int S, in
 }
 
 // out = conv3x3(in) [* fg]: row-major fmaf chain, first tap a plain product.
-__global__ void k_conv3x3(const float *__restrict__ in, int Hi, const float *__restrict__ w, int stride,
-                          int pad, const float *__restrict__ mask, size_t mask_bstride,
-                          float *__restrict__ out, int Ho) {
+__global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int stride, int pad,
+                          const float *__restrict__ mask, size_t mask_bstride, float *__restrict__ out, int Ho) {
   int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (i >= Ho || j >= Ho) return;
-  const float *p = in + (size_t)b * Hi * Hi;
+  const float *p = in.p + (size_t)b * in.bstride;
   int i0 = i * stride - pad, j0 = j * stride - pad;
-  float acc = __fmul_rn(__ldg(w + 0), ldz(p, Hi, i0, j0));
-  acc = __fmaf_rn(__ldg(w + 1), ldz(p, Hi, i0, j0 + 1), acc);
-  acc = __fmaf_rn(__ldg(w + 2), ldz(p, Hi, i0, j0 + 2), acc);
-  acc = __fmaf_rn(__ldg(w + 3), ldz(p, Hi, i0 + 1, j0), acc);
-  acc = __fmaf_rn(__ldg(w + 4), ldz(p, Hi, i0 + 1, j0 + 1), acc);
-  acc = __fmaf_rn(__ldg(w + 5), ldz(p, Hi, i0 + 1, j0 + 2), acc);
-  acc = __fmaf_rn(__ldg(w + 6), ldz(p, Hi, i0 + 2, j0), acc);
-  acc = __fmaf_rn(__ldg(w + 7), ldz(p, Hi, i0 + 2, j0 + 1), acc);
-  acc = __fmaf_rn(__ldg(w + 8), ldz(p, Hi, i0 + 2, j0 + 2), acc);
+  float acc = __fmul_rn(__ldg(w + 0), ldzv(p, in, Hi, i0, j0));
+  acc = __fmaf_rn(__ldg(w + 1), ldzv(p, in, Hi, i0, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 2), ldzv(p, in, Hi, i0, j0 + 2), acc);
+  acc = __fmaf_rn(__ldg(w + 3), ldzv(p, in, Hi, i0 + 1, j0), acc);
+  acc = __fmaf_rn(__ldg(w + 4), ldzv(p, in, Hi, i0 + 1, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 5), ldzv(p, in, Hi, i0 + 1, j0 + 2), acc);
+  acc = __fmaf_rn(__ldg(w + 6), ldzv(p, in, Hi, i0 + 2, j0), acc);
+  acc = __fmaf_rn(__ldg(w + 7), ldzv(p, in, Hi, i0 + 2, j0 + 1), acc);
+  acc = __fmaf_rn(__ldg(w + 8), ldzv(p, in, Hi, i0 + 2, j0 + 2), acc);
   if (mask) acc = __fmul_rn(acc, fg_at(mask + (size_t)b * mask_bstride, Ho, i, j));
   out[((size_t)b * Ho + i) * Ho + j] = acc;
 }
@@ -114,7 +119,7 @@ __device__ __forceinline__ float padded_at(const float *__restrict__ r, int s, i
 
 // unet_iterator.py:78-83: zero-pad 1, bilinear x2 (align_corners), crop 1, [* fg of the finer level]
 __global__ void k_pad_up_crop(const float *__restrict__ r, int s, const float *__restrict__ mask_out,
-                              size_t mask_bstride, float *__restrict__ out, int nested) {
+                              size_t mask_bstride, ArrViewMut out, int nested) {
   int so = 2 * s + 1;
   int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (i >= so || j >= so) return;
@@ -133,7 +138,7 @@ __global__ void k_pad_up_crop(const float *__restrict__ r, int s, const float *_
     v = __fmul_rn(0.25f, sum);
   }
   if (mask_out) v = __fmul_rn(v, fg_at(mask_out + (size_t)b * mask_bstride, so, i, j));
-  out[((size_t)b * so + i) * so + j] = v;
+  out.p[(size_t)b * out.bstride + (size_t)(i + out.off) * out.pitch + npde_view_col(j + out.off, out.perm)] = v;
 }
 
 // adjoint of k_pad_up_crop (without the mask multiply): g is (2s+1)^2, out is s^2
@@ -252,6 +257,11 @@ namespace npde {
 
 int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const float *mask,
             size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
+  return conv3x3_view(ArrView{in, Hi, (long)Hi * Hi, 0, 0}, Hi, w9, stride, pad, mask, mask_bstride, out, Ho, B, st);
+}
+
+int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
+                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
   NPDE_LAUNCH(k_conv3x3, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, in, Hi, w9, stride, pad, mask, mask_bstride,
               out, Ho);
   NPDE_CHECK_LAUNCH();
@@ -295,6 +305,12 @@ int combine(const float *y_int, const float *h, const float *bc, int bc_kind, in
 
 int pad_up_crop(const float *r, int s, const float *mask_out, size_t mask_bstride, float *out, int B,
                 cudaStream_t st) {
+  int so = 2 * s + 1;
+  return pad_up_crop_view(r, s, mask_out, mask_bstride, ArrViewMut{out, so, (long)so * so, 0, 0}, B, st);
+}
+
+int pad_up_crop_view(const float *r, int s, const float *mask_out, size_t mask_bstride, const ArrViewMut &out, int B,
+                     cudaStream_t st) {
   int M = s + 2, so = 2 * s + 1;
   int nested = ((long)M * M > 1024) ? 1 : 0;
   NPDE_LAUNCH(k_pad_up_crop, grid2d(so, so, B), dim3(TX, TY), 0, st, r, s, mask_out, mask_bstride, out, nested);

@@ -62,11 +62,7 @@ __global__ void k_fd_step(const float *__restrict__ x, BcView bc, const float *_
   y[(size_t)b * N * N + o] = npde_apply_G(v, bc, b, i, j, N);
 }
 
-// column j inside a row of a field view: the pair-permuted layout stores every aligned group of
-// four columns (c0,c1,c2,c3) as (c0,c2,c1,c3) (npde_internal.h FieldView)
-__device__ __forceinline__ int view_col(int j, int perm) {
-  return perm ? ((j & ~3) | ((j & 1) << 1) | ((j >> 1) & 1)) : j;
-}
+__device__ __forceinline__ int view_col(int j, int perm) { return npde_view_col(j, perm); }
 
 // -------------------------------------------------------- reductions ------
 // grid (chunks, B); every CTA reduces a band of rows, writes one partial, and

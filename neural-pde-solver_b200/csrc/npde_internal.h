@@ -67,6 +67,11 @@ int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const
             size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st);
 int conv3x3_transpose(const float *g, int Hg, const float *w9, int stride, int pad, float *out, int Ho, int B,
                       cudaStream_t st);
+// same with the input read through an array view / the output written through one (frames of the fused U-Net path)
+int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
+                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st);
+int pad_up_crop_view(const float *r, int s, const float *mask_out, size_t mask_bstride, const ArrViewMut &out, int B,
+                     cudaStream_t st);
 int mul_fg(float *r, const float *mask, size_t mask_bstride, int S, int B, cudaStream_t st);
 int add_inplace(float *a, const float *b, size_t n, cudaStream_t st);
 int psi_residual(const float *x, const float *f, const float *mask, size_t mask_bstride, float *y_int,
@@ -101,6 +106,14 @@ inline BcFields bc_fields(const float *bc, int bc_kind, int N) {
 // f.p == nullptr: Laplace.  perm views are accessed with 128-bit loads / stores, natural ones with 32-bit.
 int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f,
                 const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st);
+// head of a U-Net step (npde_stream.cu): r = pre-smoothing convs of the masked residual, y = Psi(x) - f; rout and
+// yout are frames with the same pitch / batch stride / layout
+int conv_head_stream(const FieldView &in, const BcFields &bc, const FieldView &f, const float *w_host, int n_layers,
+                     const FieldViewMut &rout, float *yout, int B, int N, cudaStream_t st);
+// tail of a U-Net step: out = G(pad(act(y + (post-smoothing convs(rin) + skip)))); rin, skip and y are frames with
+// rin's pitch / batch stride / layout
+int conv_tail_stream(const FieldView &rin, const float *skip, const float *y, const BcFields &bc, const float *w_host,
+                     int n_layers, int act, const FieldViewMut &out, int B, int N, cudaStream_t st);
 // depth in {1,2,4,8} Jacobi steps per launch (1 when f != NULL); square domain only
 int jacobi_stream_max_depth(const float *f);
 // fd_error(x, 'max') on the square domain, streaming (any view of x and f); zeroes and fills err (B)

@@ -319,9 +319,12 @@ __device__ __forceinline__ bool decode_item(int B, int N, const Split &sp, Strip
 }
 
 // ------------------------------------------------------------ Phi_H (Conv) ---
+constexpr int ACT_HEAD = 3;  // internal "activation": the kernel is the head of a U-Net step (see conv_step)
+
 struct ConvStreamParams {
   const float *in;
   float *out;
+  float *yout;       // ACT_HEAD only: second output (y = Psi(x) - f), same layout as out
   const float *f;    // NULL: Laplace
   const float *bc4;  // (B,4)
   long in_bstride, out_bstride, f_bstride;
@@ -398,6 +401,7 @@ struct ConvLaneCtx {
   const float *pfin; // same for f
   const float *pmin, *pvin;  // mask geometry: next mask row / value row to fetch
   float *pout;       // this lane's group of four in the output row of the current step
+  float *pyout;      // ACT_HEAD: same for the y output
   char *delay;       // this lane's slot 0 of the y delay line (shared memory)
   char *ring;        // this lane's 16 bytes in slot 0 of the x row ring (shared memory)
   unsigned rslot;    // ring slot (byte offset) that holds x row it+1
@@ -459,6 +463,9 @@ __device__ __forceinline__ void ring_fill(char *slot_lane0 /* slot base + 16 * l
 //         (conv_iterator.py:23-30).  Per row the kernel builds the AND-masks "interior cell and
 //         m == 0" once (stage 0) and keeps them L steps in a second shared-memory delay line; they
 //         replace the column masks of EDGE (MASK implies EDGE) and the ring-row tests.
+// ACT == ACT_HEAD: head of a U-Net step (unet_iterator.py:87-97 + the first level's pre-smoothing convs):
+//         instead of act(y + h) and G the epilogue stores r_L (masked like every stage output) to `out`
+//         and y to `yout`, both as frames whose ring is never read.
 template <int L, int ACT, bool HASF, bool MASK, bool MAIN, bool EDGE, bool PERM, int P, bool RINGED = false>
 __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const ConvStreamParams &p, int it,
                                           unsigned &woff) {
@@ -605,6 +612,28 @@ __device__ __forceinline__ void conv_step(ConvState<L> &s, ConvLaneCtx &x, const
       rc0 = fin0;
       rc1 = fin1;
       halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
+    } else if (ACT == ACT_HEAD) {
+      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+        if (MASK) {
+          const uint4 kq = *reinterpret_cast<const uint4 *>(x.delay + KEEP_OFF + 8 * x.lane + roff);
+          fin0 = and2(fin0, kq.x, kq.z);
+          fin1 = and2(fin1, kq.y, kq.w);
+        } else {
+          if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin0 = fin1 = zero2();
+          if (EDGE) {
+            fin0 = and2(fin0, x.keep[0], x.keep[2]);
+            fin1 = and2(fin1, x.keep[1], x.keep[3]);
+          }
+        }
+        const f2 ya = *reinterpret_cast<const f2 *>(x.delay + roff);
+        const f2 yb = *reinterpret_cast<const f2 *>(x.delay + roff + 256);
+        store_row(x.pout, out_perm, x.st_ok, EDGE ? x.store : 15u, fin0, fin1);
+        store_row(x.pyout, out_perm, x.st_ok, EDGE ? x.store : 15u, ya, yb);
+      }
+      if (MAIN || rk >= 0) {
+        x.pout += x.out_pitch;
+        x.pyout += x.out_pitch;
+      }
     } else {
       if (MAIN || (rk >= x.i0 && rk < x.i1)) {
         float o0, o1, o2, o3;  // columns c0..c3
@@ -773,6 +802,9 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
     x.pvin = vimg + (size_t)max(it_first - L, 0) * p.bv_pitch;   // value row max(it - L, 0)
   }
   x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - 1 - L, 0) * p.out_pitch + c.c0;
+  x.pyout = ACT == ACT_HEAD ? p.yout + (size_t)item.b * p.out_bstride +
+                                  (size_t)max(it_first - 1 - L, 0) * p.out_pitch + c.c0
+                            : nullptr;
   unsigned woff = 0;
 
   // MAIN range of `it`: stage rows it-1-L .. it-1 interior, output row it-1-L inside the band,
@@ -819,6 +851,215 @@ k_conv_stream(const NPDE_GRID_CONSTANT ConvStreamParams p) {
       if (it + 1 <= it_last) conv_step<L, ACT, HASF, MASK, false, true, false, 1>(s, x, p, it + 1, woff);
       it += 2;
     }
+  }
+}
+
+// ------------------------------------------------- tail of a U-Net step ---
+// unet_iterator.py:70-76 at the finest level + :99-105: the L post-smoothing convs applied to r (already
+// multiplied by the foreground mask), + skip, then out = G(pad(act(y + h))).  Same strip / band streaming and
+// conv chain as k_conv_stream, without Psi: row `it` of r arrives, stage k (1..L) finishes row it-k, the
+// epilogue handles row it-L.  rin, skip and y are frames with one common layout (their ring is never used:
+// every row is ANDed with the keep masks "interior cell [and m == 0]" on arrival).  One code path with
+// uniform row tests (no MAIN / EDGE versions): this kernel replaces four launches of the layered path and is
+// not the headline.
+struct TailStreamParams {
+  const float *rin, *skip, *y;
+  float *out;
+  const float *bc4;
+  const float *bv, *bm;
+  long in_bstride, out_bstride, bv_bstride, bm_bstride;
+  int in_pitch, out_pitch, bv_pitch, bm_pitch;
+  int in_perm, out_perm, bv_perm, bm_perm;
+  int B, N;
+  Split split;
+  float w[4][9];
+};
+
+template <int L>
+struct TailState {
+  f2 S[L][2][2];  // partial-sum rows of the conv stages, as in ConvState
+  f2 pr[2];       // r row `it` (fetched one step earlier)
+  f2 ps[2], py[2], pv[2], pm[2];  // skip / y / value rows of the next output row, mask row of the next input row
+};
+
+struct TailCtx {
+  unsigned keep[4], gval[4], in_img, store;
+  bool in_perm, out_perm, bv_perm, bm_perm, ld_ok, st_ok;
+  const float *prin, *pskip, *py, *pvin, *pmin;
+  float *pout;
+  char *kdelay;  // this lane's 16 bytes in slot 0 of the keep-mask delay line (MASK)
+  float top, bottom;
+  int N, i0, i1, in_pitch, out_pitch, bv_pitch, bm_pitch, lane, lane_l, lane_r;
+};
+
+template <int L, int ACT, bool MASK, int P>
+__device__ __forceinline__ void tail_step(TailState<L> &s, TailCtx &x, const TailStreamParams &p, int it,
+                                          unsigned &woff) {
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  constexpr unsigned RING = DS * 512u - 1u;
+  const int N = x.N;
+  // ---- arrival of r row `it`: keep masks of that row, mask, halo ----
+  const bool row_in = it >= 1 && it <= N - 2;
+  uint4 kq;
+  kq.x = (row_in && (!MASK || lo(s.pm[0]) == 0.0f)) ? x.keep[0] : 0u;
+  kq.y = (row_in && (!MASK || lo(s.pm[1]) == 0.0f)) ? x.keep[1] : 0u;
+  kq.z = (row_in && (!MASK || hi(s.pm[0]) == 0.0f)) ? x.keep[2] : 0u;
+  kq.w = (row_in && (!MASK || hi(s.pm[1]) == 0.0f)) ? x.keep[3] : 0u;
+  *reinterpret_cast<uint4 *>(x.kdelay + woff) = kq;
+  f2 rc0 = and2(s.pr[0], kq.x, kq.z), rc1 = and2(s.pr[1], kq.y, kq.w);
+  float rl, rr;
+  halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
+  // fetch r row it+1 and (MASK) mask row it+1
+  {
+    const int nx = it + 1;
+    if (nx <= N - 2 && nx <= x.i1 - 1 + L) {
+      load_row(x.prin, x.in_perm, x.ld_ok, x.in_img, s.pr[0], s.pr[1]);
+      if (MASK) load_row(x.pmin, x.bm_perm, x.ld_ok, x.in_img, s.pm[0], s.pm[1]);
+      if (L2_AHEAD > 0 && nx + L2_AHEAD <= N - 2) {
+        prefetch_row(x.prin + (size_t)L2_AHEAD * x.in_pitch, x.lane, x.in_img);
+        if (MASK) prefetch_row(x.pmin + (size_t)L2_AHEAD * x.bm_pitch, x.lane, x.in_img);
+      }
+    } else {
+      s.pr[0] = s.pr[1] = zero2();
+      if (MASK) s.pm[0] = s.pm[1] = bc2(1.0f);
+    }
+    x.prin += x.in_pitch;
+    if (MASK) x.pmin += x.bm_pitch;
+  }
+#pragma unroll
+  for (int k = 1; k <= L; ++k) {
+    const int rk = it - k;
+    const float *w = p.w[k - 1];
+    f2 (&mid)[2] = s.S[k - 1][P];
+    f2 (&top)[2] = s.S[k - 1][P ^ 1];
+    f2 fin0 = mid[0], fin1 = mid[1];
+    conv_taps(rc0, rc1, rl, rr, w[6], w[7], w[8], fin0, fin1);
+    conv_taps(rc0, rc1, rl, rr, w[3], w[4], w[5], top[0], top[1]);
+    mid[0] = mul_lohi(w[0], rl, lo(rc1));
+    mid[0] = fma2(bc2(w[1]), rc0, mid[0]);
+    mid[0] = fma2(bc2(w[2]), rc1, mid[0]);
+    mid[1] = mul2(bc2(w[0]), rc0);
+    mid[1] = fma2(bc2(w[1]), rc1, mid[1]);
+    mid[1] = fma_lohi(w[2], hi(rc0), rr, mid[1]);
+    const uint4 kk = *reinterpret_cast<const uint4 *>(x.kdelay + ((woff + (DS - k) * 512u) & RING));  // row it-k
+    fin0 = and2(fin0, kk.x, kk.z);
+    fin1 = and2(fin1, kk.y, kk.w);
+    if (k < L) {
+      rc0 = fin0;
+      rc1 = fin1;
+      halo_scalars(rc0, rc1, x.lane_l, x.lane_r, rl, rr);
+    } else {
+      if (rk >= x.i0 && rk < x.i1) {
+        // h = r + skip (:76), z = y + h, act, pad, G
+        const float h0 = __fadd_rn(lo(fin0), lo(s.ps[0])), h2 = __fadd_rn(hi(fin0), hi(s.ps[0]));
+        const float h1 = __fadd_rn(lo(fin1), lo(s.ps[1])), h3 = __fadd_rn(hi(fin1), hi(s.ps[1]));
+        float o0 = add_act<ACT>(lo(s.py[0]), h0), o2 = add_act<ACT>(hi(s.py[0]), h2);
+        float o1 = add_act<ACT>(lo(s.py[1]), h1), o3 = add_act<ACT>(hi(s.py[1]), h3);
+        if (MASK) {
+          o0 = __fadd_rn(sel_bits(o0, kk.x, 0u), lo(s.pv[0]));
+          o2 = __fadd_rn(sel_bits(o2, kk.z, 0u), hi(s.pv[0]));
+          o1 = __fadd_rn(sel_bits(o1, kk.y, 0u), lo(s.pv[1]));
+          o3 = __fadd_rn(sel_bits(o3, kk.w, 0u), hi(s.pv[1]));
+        } else {
+          if (rk == 0 || rk == N - 1) o0 = o1 = o2 = o3 = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+          o0 = sel_bits(o0, x.keep[0], x.gval[0]);
+          o1 = sel_bits(o1, x.keep[1], x.gval[1]);
+          o2 = sel_bits(o2, x.keep[2], x.gval[2]);
+          o3 = sel_bits(o3, x.keep[3], x.gval[3]);
+        }
+        store_cols(x.pout, x.out_perm, x.st_ok, x.store, o0, o1, o2, o3);
+      }
+      if (rk >= 0) x.pout += x.out_pitch;
+      // skip / y / value rows of the next output row rk + 1
+      const int nr = rk + 1;
+      if (nr >= 0) {
+        if (nr >= 1 && nr <= N - 2 && nr < x.i1) {
+          load_row(x.pskip, x.in_perm, x.ld_ok, x.in_img, s.ps[0], s.ps[1]);
+          load_row(x.py, x.in_perm, x.ld_ok, x.in_img, s.py[0], s.py[1]);
+        } else {
+          s.ps[0] = s.ps[1] = s.py[0] = s.py[1] = zero2();
+        }
+        x.pskip += x.in_pitch;
+        x.py += x.in_pitch;
+        if (MASK) {
+          if (nr <= N - 1 && nr < x.i1) load_row(x.pvin, x.bv_perm, x.ld_ok, x.in_img, s.pv[0], s.pv[1]);
+          else s.pv[0] = s.pv[1] = zero2();
+          x.pvin += x.bv_pitch;
+        }
+      }
+    }
+  }
+  woff = (woff + 512u) & RING;
+}
+
+template <int L, int ACT, bool MASK>
+__global__ void __launch_bounds__(npde::STREAM_THREADS)
+k_tail_stream(const NPDE_GRID_CONSTANT TailStreamParams p) {
+  constexpr int RC = (L + 3) & ~3;
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  NPDE_DYN_SMEM(float4, kdl);  // [DS][32] keep masks, 16 bytes per lane and slot
+  StripItem item;
+  if (!decode_item(p.B, p.N, p.split, item)) return;
+  TailCtx x;
+  const int lane = threadIdx.x & 31, N = p.N;
+  x.lane = lane;
+  x.lane_l = (lane + 31) & 31;
+  x.lane_r = (lane + 1) & 31;
+  x.N = N;
+  x.kdelay = reinterpret_cast<char *>(kdl) + 16 * lane;
+  const int vs = item.strip * p.split.wv, ve = min(vs + p.split.wv, N);
+  const LaneCols c = make_cols(vs - RC, lane, N, vs, ve);
+  x.in_img = c.in_img;
+  x.store = c.store;
+  x.in_perm = p.in_perm != 0; x.out_perm = p.out_perm != 0; x.bv_perm = p.bv_perm != 0; x.bm_perm = p.bm_perm != 0;
+  x.ld_ok = c.c0 >= 0 && c.c0 < N;
+  x.st_ok = c.store != 0u;
+  x.i0 = item.i0; x.i1 = item.i1;
+  x.in_pitch = p.in_pitch; x.out_pitch = p.out_pitch; x.bv_pitch = p.bv_pitch; x.bm_pitch = p.bm_pitch;
+  float left = 0.f, right = 0.f;
+  x.top = x.bottom = 0.f;
+  if (!MASK) {
+    const float *bcb = p.bc4 + (size_t)item.b * 4;
+    x.top = __ldg(bcb + 0); x.bottom = __ldg(bcb + 1); left = __ldg(bcb + 2); right = __ldg(bcb + 3);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int col = c.c0 + q;
+    x.keep[q] = (c.interior >> q & 1u) ? 0xffffffffu : 0u;
+    x.gval[q] = col == 0 ? __float_as_uint(left) : (col == N - 1 ? __float_as_uint(right) : 0u);
+  }
+  TailState<L> s;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    s.pr[h] = s.ps[h] = s.py[h] = s.pv[h] = zero2();
+    s.pm[h] = bc2(1.0f);
+#pragma unroll
+    for (int k = 0; k < L; ++k) s.S[k][h][0] = s.S[k][h][1] = zero2();
+  }
+#pragma unroll
+  for (int d = 0; d < DS; ++d) *reinterpret_cast<float4 *>(x.kdelay + d * 512) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int it_first = max(x.i0 - L, 0), it_last = x.i1 - 1 + L;
+  const size_t lane_in = (size_t)item.b * p.in_bstride + c.c0;
+  // r row it_first (+ its mask row) is fetched here; every step fetches the next one
+  if (it_first >= 1 && it_first <= N - 2) {
+    load_row(p.rin + lane_in + (size_t)it_first * p.in_pitch, x.in_perm, x.ld_ok, c.in_img, s.pr[0], s.pr[1]);
+    if (MASK)
+      load_row(p.bm + (size_t)item.b * p.bm_bstride + c.c0 + (size_t)it_first * p.bm_pitch, x.bm_perm, x.ld_ok, c.in_img,
+               s.pm[0], s.pm[1]);
+  }
+  x.prin = p.rin + lane_in + (size_t)(it_first + 1) * p.in_pitch;
+  x.pmin = MASK ? p.bm + (size_t)item.b * p.bm_bstride + c.c0 + (size_t)(it_first + 1) * p.bm_pitch : nullptr;
+  // skip / y / value rows are fetched one step ahead of their output row; the first fetch is for row nr0
+  const int nr0 = max(it_first - L + 1, 0);
+  x.pskip = p.skip + lane_in + (size_t)nr0 * p.in_pitch;
+  x.py = p.y + lane_in + (size_t)nr0 * p.in_pitch;
+  x.pvin = MASK ? p.bv + (size_t)item.b * p.bv_bstride + c.c0 + (size_t)nr0 * p.bv_pitch : nullptr;
+  x.pout = p.out + (size_t)item.b * p.out_bstride + (size_t)max(it_first - L, 0) * p.out_pitch + c.c0;
+  unsigned woff = 0;
+  for (int it = it_first; it <= it_last; it += 2) {
+    tail_step<L, ACT, MASK, 0>(s, x, p, it, woff);
+    if (it + 1 <= it_last) tail_step<L, ACT, MASK, 1>(s, x, p, it + 1, woff);
   }
 }
 
@@ -1130,6 +1371,7 @@ int launch_conv(ConvStreamParams &p, cudaStream_t st) {
   return NPDE_OK;
 #else
   switch (p.act) {
+    case ACT_HEAD: return launch_conv_f<L, ACT_HEAD>(p, grid, block, smem, st);
     case NPDE_ACT_NONE: return launch_conv_f<L, NPDE_ACT_NONE>(p, grid, block, smem, st);
     case NPDE_ACT_CLAMP: return launch_conv_f<L, NPDE_ACT_CLAMP>(p, grid, block, smem, st);
     case NPDE_ACT_SIGMOID: return launch_conv_f<L, NPDE_ACT_SIGMOID>(p, grid, block, smem, st);
@@ -1165,9 +1407,11 @@ static bool perm_ok(const void *p, int pitch, long bstride, int perm, int N) {
   return ((uintptr_t)p & 15) == 0 && (pitch & 3) == 0 && (bstride & 3) == 0 && pitch >= ((N + 3) & ~3);
 }
 
-int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f,
-                const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st) {
+static int conv_stream_impl(const FieldView &in, const FieldViewMut &out, float *yout, const BcFields &bc,
+                            const FieldView &f, const float *w_host, int n_layers, int act, int B, int N,
+                            cudaStream_t st) {
   ConvStreamParams p;
+  p.yout = yout;
   p.bc4 = bc.bc4;
   p.bv = bc.values.p; p.bv_pitch = bc.values.pitch; p.bv_bstride = bc.values.bstride; p.bv_perm = bc.values.perm;
   p.bm = bc.mask.p; p.bm_pitch = bc.mask.pitch; p.bm_bstride = bc.mask.bstride; p.bm_perm = bc.mask.perm;
@@ -1194,6 +1438,74 @@ int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc
     case 3: return launch_conv<3>(p, st);
     default: return NPDE_ERR_LAYERS;
   }
+}
+
+int conv_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f,
+                const float *w_host, int n_layers, int act, int B, int N, cudaStream_t st) {
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  return conv_stream_impl(in, out, nullptr, bc, f, w_host, n_layers, act, B, N, st);
+}
+
+// Head of a U-Net step: y = Psi(x) - f and r = the n_layers pre-smoothing convs of the finest level applied
+// to the masked residual, both written as frames (rout / yout share pitch, batch stride and layout).
+int conv_head_stream(const FieldView &in, const BcFields &bc, const FieldView &f, const float *w_host, int n_layers,
+                     const FieldViewMut &rout, float *yout, int B, int N, cudaStream_t st) {
+  return conv_stream_impl(in, rout, yout, bc, f, w_host, n_layers, ACT_HEAD, B, N, st);
+}
+
+// Tail of a U-Net step: out = G(pad(act(y + (convs(rin) + skip)))); rin, skip, y share one frame layout.
+template <int L, int ACT>
+static int launch_tail(TailStreamParams &p, cudaStream_t st) {
+  constexpr int RC = (L + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
+  const size_t smem = (size_t)512 * DS;
+  static int cache[2] = {0, 0};
+  int resident = p.bm ? resident_warps_cached((const void *)k_tail_stream<L, ACT, true>, smem, &cache[1])
+                      : resident_warps_cached((const void *)k_tail_stream<L, ACT, false>, smem, &cache[0]);
+  p.split = make_split(p.B, p.N, RC, L, resident);
+  dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
+  if (p.bm) NPDE_LAUNCH((k_tail_stream<L, ACT, true>), grid, block, smem, st, p);
+  else NPDE_LAUNCH((k_tail_stream<L, ACT, false>), grid, block, smem, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+template <int L>
+static int launch_tail_act(TailStreamParams &p, int act, cudaStream_t st) {
+  switch (act) {
+    case NPDE_ACT_NONE: return launch_tail<L, NPDE_ACT_NONE>(p, st);
+    case NPDE_ACT_CLAMP: return launch_tail<L, NPDE_ACT_CLAMP>(p, st);
+    case NPDE_ACT_SIGMOID: return launch_tail<L, NPDE_ACT_SIGMOID>(p, st);
+    default: return NPDE_ERR_ACT;
+  }
+}
+
+int conv_tail_stream(const FieldView &rin, const float *skip, const float *y, const BcFields &bc, const float *w_host,
+                     int n_layers, int act, const FieldViewMut &out, int B, int N, cudaStream_t st) {
+#ifdef NPDE_DEV_ONLY_CONV3
+  (void)rin; (void)skip; (void)y; (void)bc; (void)w_host; (void)n_layers; (void)act; (void)out; (void)B; (void)N; (void)st;
+  return NPDE_ERR_ARG;
+#else
+  TailStreamParams p;
+  p.rin = rin.p; p.skip = skip; p.y = y;
+  p.in_pitch = rin.pitch; p.in_bstride = rin.bstride; p.in_perm = rin.perm;
+  p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride; p.out_perm = out.perm;
+  p.bc4 = bc.bc4;
+  p.bv = bc.values.p; p.bv_pitch = bc.values.pitch; p.bv_bstride = bc.values.bstride; p.bv_perm = bc.values.perm;
+  p.bm = bc.mask.p; p.bm_pitch = bc.mask.pitch; p.bm_bstride = bc.mask.bstride; p.bm_perm = bc.mask.perm;
+  if ((bc.bc4 == nullptr) == (bc.mask.p == nullptr)) return NPDE_ERR_BC;
+  if (!perm_ok(rin.p, rin.pitch, rin.bstride, rin.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
+      !perm_ok(p.bv, p.bv_pitch, p.bv_bstride, p.bv_perm, N) || !perm_ok(p.bm, p.bm_pitch, p.bm_bstride, p.bm_perm, N))
+    return NPDE_ERR_ARG;
+  p.B = B; p.N = N;
+  for (int l = 0; l < 4; ++l)
+    for (int t = 0; t < 9; ++t) p.w[l][t] = (l < n_layers) ? w_host[l * 9 + t] : 0.0f;
+  switch (n_layers) {
+    case 1: return launch_tail_act<1>(p, act, st);
+    case 2: return launch_tail_act<2>(p, act, st);
+    case 3: return launch_tail_act<3>(p, act, st);
+    case 4: return launch_tail_act<4>(p, act, st);
+    default: return NPDE_ERR_LAYERS;
+  }
+#endif
 }
 
 int jacobi_stream_max_depth(const float *f) { return f ? 1 : 8; }

@@ -276,7 +276,9 @@ def unet_H(r, bc, w_first, w_pool, w_second, n_layers, pre, post, is_bc_mask):
     return out
 
 
-def unet_step(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act):
+def unet_step(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act, w_host=None):
+    """w_host: optional host (numpy, float32) copy of the weights, first | pool | second concatenated: enables the
+    fused finest level (npde_unet_step_fwd_hw)."""
     x = _field(x)
     bc = _require(bc, "bc")
     f = _opt(f, "f")
@@ -285,8 +287,13 @@ def unet_step(x, bc, f, w_first, w_pool, w_second, n_layers, pre, post, act):
     kind = bc_kind(x, bc)
     y = torch.empty_like(x)
     ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_UNET_FWD, B, N, kind, n_layers, pre, post, 0), x)
-    check(lib().npde_unet_step_fwd(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wf), _ptr(wp), _ptr(wsn), n_layers, pre,
-                                   post, _act(act), _ptr(y), B, N, ws, wsb, _stream(x)), "npde_unet_step_fwd")
+    wh = None
+    if w_host is not None:
+        w_host = np.ascontiguousarray(w_host, dtype=np.float32)
+        wh = ctypes.c_void_p(w_host.ctypes.data)
+    check(lib().npde_unet_step_fwd_hw(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wf), _ptr(wp), _ptr(wsn), wh, n_layers,
+                                      pre, post, _act(act), _ptr(y), B, N, ws, wsb, _stream(x)),
+          "npde_unet_step_fwd_hw")
     return y
 
 
@@ -317,7 +324,7 @@ class UNetStepFn(torch.autograd.Function):
         ctx.cfg = (n_first, n_pool, n_layers, pre, post, act)
         wd = w.detach()
         return unet_step(x, bc, f, wd[:n_first], wd[n_first:n_first + n_pool], wd[n_first + n_pool:], n_layers, pre,
-                         post, act)
+                         post, act, w_host=wd.cpu().numpy())
 
     @staticmethod
     def backward(ctx, gout):

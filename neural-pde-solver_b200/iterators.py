@@ -212,14 +212,15 @@ class UNetIterator(Iterator):
             w = torch.stack([p.reshape(3, 3) for p in params])
             return F_.UNetStepFn.apply(x, bc, f, w, self.n_layers * self.pre_smoothing, self.n_layers - 1,
                                        self.n_layers, self.pre_smoothing, self.post_smoothing, self.act)
-        w, _ = self._cache.get(params)
+        w, w_host = self._cache.get(params)
         wf, wp, ws = self._split(w)
-        return F_.unet_step(x, bc, f, wf, wp, ws, self.n_layers, self.pre_smoothing, self.post_smoothing, self.act)
+        return F_.unet_step(x, bc, f, wf, wp, ws, self.n_layers, self.pre_smoothing, self.post_smoothing, self.act,
+                            w_host=w_host)
 
     def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
         self._check_act()
-        w, _ = self._cache.get(self._params())
-        return F_.iterate(IT_UNET, x, bc, f, k, w=w, n_layers=self.n_layers, pre=self.pre_smoothing,
+        w, w_host = self._cache.get(self._params())
+        return F_.iterate(IT_UNET, x, bc, f, k, w=w, w_host=w_host, n_layers=self.n_layers, pre=self.pre_smoothing,
                           post=self.post_smoothing, act=self.act, gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
 
     def name(self):

@@ -244,6 +244,42 @@ def test_mask_geometry_stream_vs_oracle(be, oracle, B, N, L, has_f, act):
     assert_bitwise(be.n(jac(xd, bcd, fd)), oracle.fd_step(x, bc, f), "single mask Jacobi step")
 
 
+@pytest.mark.parametrize("B,N,L,pre,post,mask,has_f,act", [(3, 129, 3, 2, 2, True, False, "clamp"),
+                                                            (2, 257, 2, 1, 3, False, True, "none"),
+                                                            (5, 65, 3, 4, 1, True, True, "clamp"),
+                                                            (2, 129, 1, 2, 2, False, False, "clamp"),
+                                                            (3, 33, 2, 3, 4, True, False, "none")])
+def test_unet_fused_level_vs_oracle(be, oracle, B, N, L, pre, post, mask, has_f, act):
+    """UNetIterator.forward with the finest level fused into the head / tail stream kernels (several strips and
+    bands, both geometries) against the CPU oracle; iterate() takes the same path."""
+    rng = np.random.RandomState(B * 31 + N + L + pre)
+    bc = _mask_geometry(rng, B, N) if mask else rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    wf = ((rng.rand(L * pre, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    wp = ((rng.rand(max(L - 1, 0), 3, 3) - 0.5) * 0.3).astype(np.float32)
+    ws = ((rng.rand(L * post, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.UNetIterator(act, L, pre, post)
+    it.is_bc_mask = mask
+    with torch.no_grad():
+        for ml, wsrc in ((it.first_layers, wf), (it.pooling_layers, wp), (it.second_layers, ws)):
+            for l, wl in zip(ml, wsrc):
+                l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    with torch.no_grad():
+        y1 = it(xd, bcd, fd)
+        y3, _, _ = it.iterate(xd, bcd, fd, 3)
+    ref = oracle.unet_step(x, bc, f, wf, wp, ws, L, pre, post, act)
+    assert_bitwise(be.n(y1), ref, "unet step, fused finest level")
+    for _ in range(2):
+        ref = oracle.unet_step(ref, bc, f, wf, wp, ws, L, pre, post, act)
+    assert_bitwise(be.n(y3), ref, "3 unet steps")
+
+
 # ------------------------------------------------------------ Multigrid / UNet --
 @pytest.mark.parametrize("name", golden_names("mg_"))
 def test_multigrid_iterator(be, name):
