@@ -94,11 +94,20 @@ def build_emulator(force=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     if force or _stale(out, srcs + HEADERS + [os.path.join(emu_dir, "cuda_emu.h")]):
         os.makedirs(os.path.dirname(out), exist_ok=True)
-        cmd = ["g++", "-O2", "-std=c++17", "-DNPDE_EMU", "-ffp-contract=off", "-fPIC", "-shared",
-               "-I" + emu_dir, "-x", "c++"] + srcs + ["-o", out]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        flags = ["g++", "-O2", "-std=c++17", "-DNPDE_EMU", "-ffp-contract=off", "-fPIC", "-I" + emu_dir]
+        objs = [os.path.join(os.path.dirname(out), os.path.basename(s_)[:-3] + ".emu.o") for s_ in srcs]
+
+        def cc(pair):
+            src, obj = pair
+            r = subprocess.run(flags + ["-x", "c++", "-c", src, "-o", obj], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("emulator build failed:\n" + r.stderr)
+
+        with ThreadPoolExecutor(max_workers=4) as ex:  # the four translation units in parallel
+            list(ex.map(cc, zip(srcs, objs)))
+        r = subprocess.run(["g++", "-shared", "-o", out] + objs, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("emulator build failed:\n" + r.stderr)
+            raise RuntimeError("emulator link failed:\n" + r.stderr)
     return out
 
 

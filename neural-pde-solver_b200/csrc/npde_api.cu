@@ -133,28 +133,31 @@ struct ConvBwdWs {
 };
 
 // ------------------------------------------------------------- V-cycle ---
-// Level fields.  Square domain: pair-permuted padded layout (the Jacobi stream kernel then moves 128 bits
-// per lane; restriction / prolongation read and write the same views).  Mask geometry: reference layout,
-// smoothing by the simple Psi+G kernel.
+// Level fields live in the pair-permuted padded layout (the Jacobi stream kernel then moves 128 bits per
+// lane; restriction / prolongation read and write the same views).  On mask geometries every level also
+// keeps permuted copies of its two bc planes for the smoother (made once per V-cycle and level).
 struct MgLevel {
   int N;
   npde::FieldViewMut p[2];  // ping-pong fields
   float *f;                 // 4^l * injected source (level >= 1), or NULL
   float *bc;                // injected [values, mask] (mask path, level >= 1)
+  float *vperm, *mperm;     // mask path: the level's bc planes in the permuted layout (smoother's 128-bit loads)
 };
 struct MgWs {
   MgLevel lv[NPDE_MAX_LEVELS];
   void carve(Bump &b, int B, int N, int bc_kind, int L, bool has_f) {
     int n = N;
-    const bool perm = bc_kind == NPDE_BC_SQUARE;
+    const bool mask = bc_kind == NPDE_BC_MASK;
     for (int l = 0; l < L; ++l) {
       size_t cells = (size_t)B * n * n;
-      int pitch = perm ? ((n + 3) & ~3) : n;
-      long bstride = perm ? (long)npde_align_up((size_t)pitch * n, 64) : (long)n * n;
+      int pitch = (n + 3) & ~3;
+      long bstride = (long)npde_align_up((size_t)pitch * n, 64);
       lv[l].N = n;
-      for (int h = 0; h < 2; ++h) lv[l].p[h] = npde::FieldViewMut{b.take<float>((size_t)B * bstride), pitch, bstride, perm ? 1 : 0};
+      for (int h = 0; h < 2; ++h) lv[l].p[h] = npde::FieldViewMut{b.take<float>((size_t)B * bstride), pitch, bstride, 1};
       lv[l].f = (l > 0 && has_f) ? b.take<float>(cells) : nullptr;
-      lv[l].bc = (l > 0 && bc_kind == NPDE_BC_MASK) ? b.take<float>(2 * cells) : nullptr;
+      lv[l].bc = (l > 0 && mask) ? b.take<float>(2 * cells) : nullptr;
+      lv[l].vperm = mask ? b.take<float>((size_t)B * bstride) : nullptr;
+      lv[l].mperm = mask ? b.take<float>((size_t)B * bstride) : nullptr;
       n = (n - 1) / 2 + 1;
     }
   }
@@ -170,6 +173,11 @@ int vcycle(MgWs &m, int l, int L, const npde::FieldView &src, const float *bc, c
   MgLevel &lv = m.lv[l];
   npde::FieldView cur = src;
   const bool coarsest = l == L - 1;
+  if (bc_kind == NPDE_BC_MASK && pre + post > 0) {
+    npde::BcFields nat = npde::bc_fields(bc, bc_kind, lv.N);
+    TRY(npde::copy_field(nat.values, npde::FieldViewMut{lv.vperm, lv.p[0].pitch, lv.p[0].bstride, 1}, B, lv.N, st));
+    TRY(npde::copy_field(nat.mask, npde::FieldViewMut{lv.mperm, lv.p[0].pitch, lv.p[0].bstride, 1}, B, lv.N, st));
+  }
   // the very last operation of the level may write the caller's tensor directly
   TRY(smooth(cur, lv, bc, bc_kind, f, pre, B, (coarsest && post == 0) ? out : nullptr, st));  // jacobi_iterator.py:41-42
   if (!coarsest) {
@@ -201,23 +209,19 @@ namespace npde {
 // n Jacobi steps src -> buf0 / buf1 (ping-pong views); *result is the view that holds the last iterate; the
 // final launch writes `last` if given.  Square domain without a source runs temporally blocked launches of
 // depth 4/2/1; otherwise one launch per step.
-int jacobi_steps_view(const FieldView &src, const FieldViewMut &buf0, const FieldViewMut &buf1, const float *bc,
-                      int bc_kind, const float *f, int n, int B, int N, const FieldViewMut *last,
-                      FieldView *result, cudaStream_t st) {
+int jacobi_steps_view(const FieldView &src, const FieldViewMut &buf0, const FieldViewMut &buf1, const BcFields &bcf,
+                      const float *f, int n, int B, int N, const FieldViewMut *last, FieldView *result,
+                      cudaStream_t st) {
   FieldView cur = src;
   int flip = 0, left = n;
+  const bool square = bcf.bc4 != nullptr;
   while (left > 0) {
     int depth = 1;
-    if (bc_kind == NPDE_BC_SQUARE && !f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+    if (square && !f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
     const bool final_launch = left - depth == 0;
     const FieldViewMut &dst = (final_launch && last) ? *last : (flip ? buf1 : buf0);
     if (!dst.p || dst.p == cur.p) return NPDE_ERR_ARG;
-    if (bc_kind == NPDE_BC_SQUARE) {
-      TRY(jacobi_stream(cur, dst, bc_fields(bc, bc_kind, N), ref_view(f, N), depth, B, N, st));
-    } else {
-      if (cur.perm || dst.perm || cur.pitch != N || dst.pitch != N) return NPDE_ERR_ARG;
-      TRY(fd_step_simple(cur.p, bc, bc_kind, f, dst.p, B, N, st));
-    }
+    TRY(jacobi_stream(cur, dst, bcf, ref_view(f, N), depth, B, N, st));
     left -= depth;
     cur = as_const(dst);
     flip ^= 1;
@@ -228,9 +232,21 @@ int jacobi_steps_view(const FieldView &src, const FieldViewMut &buf0, const Fiel
 
 int jacobi_steps(const float *src, float *buf0, float *buf1, const float *bc, int bc_kind, const float *f, int n,
                  int B, int N, const float **result, cudaStream_t st) {
+  if (bc_kind == NPDE_BC_MASK) {  // single steps on the reference layout: the coalesced thread-per-cell kernel
+    const float *cur = src;
+    float *dst = buf0;
+    for (int t = 0; t < n; ++t) {
+      if (!dst) return NPDE_ERR_ARG;
+      TRY(fd_step_simple(cur, bc, bc_kind, f, dst, B, N, st));
+      cur = dst;
+      dst = (dst == buf0) ? buf1 : buf0;
+    }
+    *result = cur;
+    return NPDE_OK;
+  }
   FieldView res;
-  TRY(jacobi_steps_view(ref_view(src, N), ref_view_mut(buf0, N), ref_view_mut(buf1, N), bc, bc_kind, f, n, B, N,
-                        nullptr, &res, st));
+  TRY(jacobi_steps_view(ref_view(src, N), ref_view_mut(buf0, N), ref_view_mut(buf1, N), bc_fields(bc, bc_kind, N), f,
+                        n, B, N, nullptr, &res, st));
   *result = res.p;
   return NPDE_OK;
 }
@@ -244,8 +260,13 @@ int smooth(npde::FieldView &cur, MgLevel &lv, const float *bc, int bc_kind, cons
   // first destination must not be `cur`
   const npde::FieldViewMut &b0 = (cur.p == lv.p[0].p) ? lv.p[1] : lv.p[0];
   const npde::FieldViewMut &b1 = (b0.p == lv.p[0].p) ? lv.p[1] : lv.p[0];
+  npde::BcFields bcf = npde::bc_fields(bc, bc_kind, lv.N);
+  if (bc_kind == NPDE_BC_MASK) {  // the permuted copies made by vcycle() for this level
+    bcf.values = npde::FieldView{lv.vperm, lv.p[0].pitch, lv.p[0].bstride, 1};
+    bcf.mask = npde::FieldView{lv.mperm, lv.p[0].pitch, lv.p[0].bstride, 1};
+  }
   npde::FieldView res;
-  TRY(npde::jacobi_steps_view(cur, b0, b1, bc, bc_kind, f, n, B, lv.N, last, &res, st));
+  TRY(npde::jacobi_steps_view(cur, b0, b1, bcf, f, n, B, lv.N, last, &res, st));
   cur = res;
   return NPDE_OK;
 }
