@@ -11,6 +11,7 @@ from . import heat_utils as utils
 from .get_iterator import get_iterator
 from .iterators import ConvIterator, Iterator, JacobiIterator, MultigridIterator, UNetIterator
 from .heat_model import HeatModel
+from . import data, generation, geometries, metrics, runtime
 
 __all__ = ["get_iterator", "Iterator", "JacobiIterator", "ConvIterator", "MultigridIterator", "UNetIterator",
-           "HeatModel", "utils", "functional"]
+           "HeatModel", "utils", "functional", "data", "generation", "geometries", "metrics", "runtime"]

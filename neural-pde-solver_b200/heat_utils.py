@@ -9,6 +9,9 @@ import torch
 
 from . import functional as F_
 from ._lib import IT_CONV, IT_JACOBI, IT_MULTIGRID, IT_UNET  # noqa: F401  (re-exported)
+# the reference's `utils` namespace also carries these (utils/__init__.py:1-5)
+from .geometries import gaussian, get_geometry  # noqa: F401
+from .metrics import Metrics  # noqa: F401
 
 
 def is_bc_mask(x, bc):
@@ -57,7 +60,8 @@ def initialize(x, bc, initialization):
         elif initialization == 'random':
             x[:, 1:-1, 1:-1] = torch.rand(batch_size, image_size - 2, image_size - 2).to(x.device)
         elif initialization == 'avg':
-            x[:, 1:-1, 1:-1] = torch.mean(bc, dim=1).view(batch_size, 1, 1)
+            # mean of the four wall temperatures on the host: same rounding as the reference's CPU path
+            x[:, 1:-1, 1:-1] = torch.mean(bc.cpu(), dim=1).view(batch_size, 1, 1).to(x.device)
         else:
             raise NotImplementedError
     return x
@@ -202,3 +206,99 @@ def solve_to_tolerance(iterator, x, bc, f, tol=1e-5, check_every=100, max_iters=
     if per_problem:
         out["first_below"] = first_below
     return out
+
+
+# ---- spectral check of a (trained) iterator: utils/heat_utils.py:216-327, utils/misc.py:99-113 ---------------
+def _probe_device(iter_func):
+    owner = getattr(iter_func, "__self__", None)
+    it = getattr(owner, "iterator", owner)
+    if isinstance(it, torch.nn.Module):
+        for p in it.parameters():
+            return p.device
+    return torch.device("cuda")
+
+
+def construct_matrix(bc, image_size, iter_func, device=None):
+    """utils/heat_utils.py:216-254: the update x' = A x + b of `iter_func` on an image_size^2 interior
+    (grid image_size + 2), and B = [[A, b], [0, 1]].
+
+    The reference calls iter_func image_size^2 + 1 times on single problems; every operator of the hot
+    path is per-problem, so here the bias probe and all unit-vector probes form ONE batch and iter_func
+    runs once.  Columns are identical to the one-at-a-time construction."""
+    import numpy as np
+    device = torch.device(device) if device is not None else _probe_device(iter_func)
+    n = image_size
+    length = n * n
+    bc_row = torch.Tensor(np.asarray(bc, dtype=np.float64)).view(1, 4)
+    probes = torch.zeros(length + 1, n + 2, n + 2)
+    idx = torch.arange(length)
+    probes[idx + 1, idx // n + 1, idx % n + 1] = 1
+    probes = probes.to(device)
+    bc_all = bc_row.repeat(length + 1, 1).contiguous().to(device)
+    probes = set_boundary(probes, bc_all)
+    y = iter_func(probes, bc_all, None).detach()[:, 1:-1, 1:-1].cpu().reshape(length + 1, length)
+    bias = y[0]
+    A = (y[1:] - bias.unsqueeze(0)).t().contiguous()  # column k = response to the k-th unit vector
+    assert A.size(0) == length
+    bias_col = torch.cat([bias, torch.Tensor([1])]).view(-1, 1)
+    B = torch.cat([torch.cat([A, torch.zeros(1, length)], dim=0), bias_col], dim=1)
+    assert B.size(0) == length + 1
+    return A, B
+
+
+def calculate_eigenvalues(model, image_size=16):
+    """utils/heat_utils.py:256-273: eigen-decomposition of the affine update matrix of model.iter_step with the
+    activation removed and square boundary handling (the convergence check of train.py:41-47)."""
+    import numpy as np
+    activation = model.get_activation()
+    is_mask = model.iterator.is_bc_mask
+    model.change_activation('none')
+    model.iterator.is_bc_mask = False
+    try:
+        _, B = construct_matrix(np.zeros((1, 4)), image_size, model.iter_step)
+        w, v = np.linalg.eig(B.numpy())
+    finally:
+        model.change_activation(activation)
+        model.iterator.is_bc_mask = is_mask
+    return w, v
+
+
+def construct_matrix_wraparound(image_size, iter_func, device=None):
+    """utils/heat_utils.py:275-302: response to unit impulses placed in the central tile of a 3x3 tiling,
+    folded back onto one tile (periodic operator, no boundary).  One batched call instead of image_size^2."""
+    device = torch.device(device) if device is not None else _probe_device(iter_func)
+    n = image_size
+    length = n * n
+    probes = torch.zeros(length, 3 * n, 3 * n)
+    idx = torch.arange(length)
+    probes[idx, idx // n + n, idx % n + n] = 1
+    probes = probes.to(device)
+    bc_all = torch.zeros(length, 4, device=device)
+    y = iter_func(probes, bc_all, None).detach().cpu()
+    folded = y.view(length, 3, n, 3, n).sum(dim=3).sum(dim=1)
+    return folded.reshape(length, length).t().contiguous().numpy()
+
+
+def calculate_eigenvalues_wraparound(model, image_size):
+    """utils/heat_utils.py:304-327: eigenvalues of A = H T + T - H for the periodic operators."""
+    import numpy as np
+    activation = model.get_activation()
+    model.change_activation('none')
+    try:
+        T = construct_matrix_wraparound(image_size, fd_step, device=_probe_device(model.iter_step))
+        H = construct_matrix_wraparound(image_size, model.H)
+        w, v = np.linalg.eig(H.dot(T) + T - H)
+    finally:
+        model.change_activation(activation)
+    return w, v
+
+
+def spectral_radius(A):
+    """utils/misc.py:107-113: largest |eigenvalue|."""
+    import numpy as np
+    return sorted(np.abs(np.linalg.eig(A)[0]))[-1]
+
+
+def dot_product(x, y):
+    """utils/misc.py:99-105: per-problem dot product."""
+    return torch.sum(x.reshape(x.size(0), -1) * y.reshape(y.size(0), -1), dim=1)

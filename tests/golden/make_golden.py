@@ -366,12 +366,138 @@ def gen_drivers():
             allow_pickle=True)
 
 
+def gen_pipeline():
+    """generation.py (solve-to-tolerance dataset pipeline), data/heat_data.py readers, runtime.get_data,
+    utils.Metrics and the spectral check, run as the reference runs them."""
+    import random
+    import shutil
+    import tempfile
+    import generation  # reference script: defines its parser at import, parses only under __main__
+    from data.heat_data import HeatDataset, HeatGeometryDataset
+    import runtime as ref_runtime
+
+    def gen_opt(root, **kw):
+        d = dict(save_dir=root, batch_size=4, save_every=1, n_frames=1, n_runs=2, image_size=17, max_temp=100,
+                 poisson=0, geometry="square", use_model=1)
+        d.update(kw)
+        return argparse.Namespace(**d)
+
+    cases = {
+        "square17": dict(image_size=17, batch_size=4, n_runs=2),
+        "square17_cold": dict(image_size=17, batch_size=4, n_runs=2, use_model=0),
+        "poisson17_cold": dict(image_size=17, batch_size=3, n_runs=1, poisson=1, use_model=0),
+        "poisson33": dict(image_size=33, batch_size=3, n_runs=2, poisson=1),
+        "Lshape33": dict(image_size=33, batch_size=3, n_runs=2, geometry="Lshape"),
+        "cylinders33_cold": dict(image_size=33, batch_size=2, n_runs=1, geometry="cylinders", use_model=0),
+        "cylinders65_cold": dict(image_size=65, batch_size=2, n_runs=1, geometry="cylinders", use_model=0),
+    }
+    for tag, kw in cases.items():
+        root = tempfile.mkdtemp()
+        try:
+            np.random.seed(666)  # generation.py:31
+            opt = gen_opt(root, **kw)
+            if opt.geometry == "square":
+                generation.generate_square(opt)
+            else:
+                generation.generate_geometry(opt)
+            arrs = {"args": np.array([kw.get(k, d) for k, d in (("image_size", 17), ("batch_size", 4), ("n_runs", 2),
+                                                                   ("poisson", 0), ("use_model", 1))]),
+                    "geometry": np.array(kw.get("geometry", "square"))}
+            for run in range(opt.n_runs):
+                arrs["frames_%04d" % run] = np.load(os.path.join(opt.save_dir, "frames", "%04d.npy" % run))
+            if opt.geometry == "square":
+                arrs["bc"] = np.load(os.path.join(opt.save_dir, "bc.npy"))
+            # what the reference's readers make of these files
+            random.seed(5)
+            if opt.geometry == "square":
+                dset = HeatDataset(opt.save_dir, True, 100, 0, opt.poisson) if opt.poisson else \
+                    HeatDataset(opt.save_dir, False, 100, 0, 0)
+            else:
+                dset = HeatGeometryDataset(opt.save_dir, True, 100, 0)
+            arrs["dset_len"] = np.array(len(dset))
+            for idx in range(min(len(dset), 3)):
+                for k, v in dset[idx].items():
+                    arrs["sample%d_%s" % (idx, k)] = npy(v)
+            data = ref_runtime.get_data(opt.geometry, 5, opt.save_dir, 100)
+            for k, v in data.items():
+                arrs["runtime_" + k] = npy(v)
+            path = os.path.join(HERE, "pipeline_" + tag + ".npz")
+            np.savez_compressed(path, **arrs)
+            print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
+
+    # ---- Metrics (utils/metrics.py) on error matrices with never-converging rows
+    rng = np.random.RandomState(7)
+    model_err = np.cumprod(rng.uniform(0.7, 1.0, (12, 40)), axis=1)
+    jac_err = np.cumprod(rng.uniform(0.85, 1.0, (12, 40)), axis=1)
+    model_err[3] = 1.0
+    jac_err[5] = 1.0
+    m = utils.Metrics(scale=2.5, error_threshold=0.05)
+    m.update({"model errors": torch.Tensor(model_err), "Jacobi errors": torch.Tensor(jac_err)})
+    m.update({"model errors": torch.Tensor(model_err[:4] * 0.5)})
+    invalid = m.invalid
+    res = m.get_results()
+    save("metrics_case", model_err=model_err.astype(np.float32), jac_err=jac_err.astype(np.float32),
+         results=np.array([res["Jacobi"], res["model"], res["ratio"], invalid], np.float64))
+
+    # ---- spectral check (utils/heat_utils.py:216-327): update matrices of a conv model, probe by probe.
+    # utils.construct_matrix / construct_matrix_wraparound call .view(-1) on a non-contiguous slice, which
+    # torch 2.x rejects; the probes below are the same single-problem calls of the reference's own
+    # iter_step / fd_step / H, one at a time, flattened with reshape instead.
+    # ATen's conv2d sums in a different order for a batch of ONE (see test_oracle_golden.py), so each matrix is
+    # stored twice: probes applied alone (rep=1, the literal reference loop; compared at 1e-5) and probes
+    # applied as a batch of two identical problems (rep=2, ATen's batched order; compared bit for bit).
+    def probe_matrix(bc, n, iter_func, rep):
+        bc = torch.Tensor(bc).view(1, 4).repeat(rep, 1)
+        x = utils.set_boundary(torch.zeros(rep, n + 2, n + 2), bc)
+        bias = iter_func(x, bc, None).detach()[0, 1:-1, 1:-1].reshape(-1)
+        cols = []
+        for i in range(n):
+            for j in range(n):
+                y = x.clone()
+                y[:, i + 1, j + 1] = 1
+                cols.append(iter_func(y, bc, None).detach()[0, 1:-1, 1:-1].reshape(-1) - bias)
+        A = torch.stack(cols, dim=1)
+        Bm = torch.cat([torch.cat([A, torch.zeros(1, n * n)], dim=0),
+                        torch.cat([bias, torch.Tensor([1])]).view(-1, 1)], dim=1)
+        return A, Bm
+
+    def probe_matrix_wrap(n, iter_func, rep):
+        bc = torch.zeros(rep, 4)
+        cols = []
+        for i in range(n):
+            for j in range(n):
+                y = torch.zeros(rep, 3 * n, 3 * n)
+                y[:, i + n, j + n] = 1
+                y = iter_func(y, bc, None).detach()[0:1]
+                cols.append(y.view(1, 3, n, 3, n).sum(dim=3).sum(dim=1).reshape(-1))
+        return torch.stack(cols, dim=1).numpy()
+
+    seed()
+    model = HeatModel(make_opt(is_train=False, conv_n_layers=2))
+    rand_conv_weights(model.iterator, 0.1)
+    w = np.stack([npy(l.weight)[0, 0] for l in model.iterator.layers])
+    A, Bm = probe_matrix(np.array([[0.3, 0.1, 0.7, 0.5]]), 7, model.iter_step, 2)
+    A1, Bm1 = probe_matrix(np.array([[0.3, 0.1, 0.7, 0.5]]), 7, model.iter_step, 1)
+    model.change_activation("none")
+    _, B0 = probe_matrix(np.zeros((1, 4)), 6, model.iter_step, 1)
+    ev = np.linalg.eig(B0.numpy())[0]
+    Tw, Tw1 = probe_matrix_wrap(5, utils.fd_step, 2), probe_matrix_wrap(5, utils.fd_step, 1)
+    Hw, Hw1 = probe_matrix_wrap(5, model.H, 2), probe_matrix_wrap(5, model.H, 1)
+    model.change_activation("clamp")
+    Aw = Hw1.dot(Tw1) + Tw1 - Hw1
+    save("spectral_conv2", w=w, A=npy(A), B=npy(Bm), A_single=npy(A1), B_single=npy(Bm1),
+         eig_abs_sorted=np.sort(np.abs(ev)),
+         T_wrap=Tw.astype(np.float32), H_wrap=Hw.astype(np.float32),
+         T_wrap_single=Tw1.astype(np.float32), H_wrap_single=Hw1.astype(np.float32),
+         eigw_abs_sorted=np.sort(np.abs(np.linalg.eig(Aw)[0])), rho=np.array(utils.spectral_radius(Aw)))
+
+
+GENERATORS = {"ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
+              "backward": gen_backward, "bptt": gen_bptt, "drivers": gen_drivers, "pipeline": gen_pipeline}
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_ops()
-    gen_conv()
-    gen_multigrid()
-    gen_unet()
-    gen_backward()
-    gen_bptt()
-    gen_drivers()
+    for name in (sys.argv[1:] or list(GENERATORS)):
+        GENERATORS[name]()
