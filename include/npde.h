@@ -68,6 +68,7 @@ extern "C" {
 #define NPDE_WS_MG 3         /* npde_mg_step */
 #define NPDE_WS_UNET_FWD 4   /* npde_unet_H, npde_unet_step_fwd */
 #define NPDE_WS_UNET_BWD 5   /* npde_unet_step_bwd */
+#define NPDE_WS_CG 6         /* npde_cg_step */
 #define NPDE_WS_ITERATE 16   /* npde_iterate: pass NPDE_WS_ITERATE + NPDE_IT_* of the iterator */
 
 int npde_version(void);
@@ -98,6 +99,12 @@ int npde_fd_error(const float *x, const float *bc, int bc_kind, const float *f, 
 /* utils/heat_utils.py:134-144 l2_error -> err (B). */
 int npde_l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
                   void *stream);
+
+/* models/iterators/conjugate_gradient.py:15-47 ConjugateGradient.forward: n_iters conjugate-gradient iterations
+ * on the 5-point operator, boundary ring of x kept; x (B,N,N) -> y (B,N,N), y != x.  The reference takes no
+ * boundary description here (bc is unused, :15) and no source (f must be None: `f + r` does not broadcast, :24-25).
+ * Per-problem alpha / beta stay on the device (deterministic two-level fp32 sums). */
+int npde_cg_step(const float *x, int n_iters, float *y, int B, int N, void *ws, size_t ws_bytes, void *stream);
 
 /* models/iterators/conv_iterator.py:19-31 ConvIterator.H on r (B,N-2,N-2).
  * bc_kind == NPDE_BC_MASK <=> iterator.is_bc_mask (bc may be NULL otherwise). */

@@ -9,9 +9,10 @@ hand-written sm_100a CUDA kernels behind the reference's own Python API.
 from . import _lib, functional
 from . import heat_utils as utils
 from .get_iterator import get_iterator
-from .iterators import ConvIterator, Iterator, JacobiIterator, MultigridIterator, UNetIterator
+from .iterators import (ConjugateGradient, ConvIterator, Iterator, JacobiIterator, MultigridIterator,
+                        MultigridResidualIterator, UNetIterator)
 from .heat_model import HeatModel
 from . import data, generation, geometries, metrics, runtime
 
-__all__ = ["get_iterator", "Iterator", "JacobiIterator", "ConvIterator", "MultigridIterator", "UNetIterator",
+__all__ = ["get_iterator", "Iterator", "JacobiIterator", "ConvIterator", "MultigridIterator", "UNetIterator", "ConjugateGradient", "MultigridResidualIterator",
            "HeatModel", "utils", "functional", "data", "generation", "geometries", "metrics", "runtime"]

@@ -18,7 +18,7 @@ BC_SQUARE, BC_MASK = 0, 1
 ACT = {"none": 0, "clamp": 1, "sigmoid": 2}
 AGG = {"max": 0, "mean": 1}
 IT_JACOBI, IT_CONV, IT_MULTIGRID, IT_UNET = 0, 1, 2, 3
-WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_ITERATE = 0, 1, 2, 3, 4, 5, 16
+WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_CG, WS_ITERATE = 0, 1, 2, 3, 4, 5, 6, 16
 MAX_CONV_LAYERS = 8
 
 _c_float_p = ctypes.c_void_p  # raw device pointers
@@ -48,6 +48,7 @@ PROTOTYPES = {
     "npde_fd_step": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp]),
     "npde_fd_error": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_l2_error": (_int, [_vp, _vp, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_cg_step": (_int, [_vp, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_conv_H": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_conv_step_fwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_conv_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _vp, _size, _vp]),

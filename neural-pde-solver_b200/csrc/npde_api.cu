@@ -500,6 +500,14 @@ int npde_fd_error(const float *x, const float *bc, int bc_kind, const float *f, 
   return npde::fd_error(x, bc, bc_kind, f, aggregate, err, B, N, ws, ws_bytes, S(stream));
 }
 
+int npde_cg_step(const float *x, int n_iters, float *y, int B, int N, void *ws, size_t ws_bytes, void *stream) {
+  TRY(npde::check_common(x, y, B, N));
+  if (n_iters < 0) return NPDE_ERR_ARG;
+  if (x == y) return NPDE_ERR_ARG;  // the first kernel reads neighbours of x while writing y
+  TRY(ws_ok(ws, ws_bytes, npde::cg_ws_bytes(B, N)));
+  return npde::cg_step(x, n_iters, y, B, N, ws, S(stream));
+}
+
 int npde_l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
                   void *stream) {
   TRY(npde::check_common(x, gt, B, N));
@@ -846,6 +854,8 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
       u.carve(b, B, N, n_layers, pre, post, bc_kind == NPDE_BC_MASK);
       return b.off;
     }
+    case NPDE_WS_CG:
+      return npde::cg_ws_bytes(B, N);
     case NPDE_WS_ITERATE + NPDE_IT_JACOBI:
     case NPDE_WS_ITERATE + NPDE_IT_CONV:
     case NPDE_WS_ITERATE + NPDE_IT_MULTIGRID:

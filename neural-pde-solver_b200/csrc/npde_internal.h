@@ -34,6 +34,9 @@ inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch
 
 // square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
 bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
+// npde_cg.cu
+size_t cg_ws_bytes(int B, int N);
+int cg_step(const float *x, int n_iters, float *y, int B, int N, void *ws, cudaStream_t st);
 // npde_grid_ops.cu
 int reduce_chunks(int N);
 size_t reduce_ws_bytes(int B, int N);

@@ -249,6 +249,16 @@ class ConvStepFn(torch.autograd.Function):
 
 
 # -------------------------------------------------------- Multigrid / UNet --
+def cg_step(x, n_iters):
+    """ConjugateGradient.forward (conjugate_gradient.py:15-47): n_iters CG iterations, boundary ring kept."""
+    x = _field(x)
+    B, N, _ = x.shape
+    y = torch.empty_like(x)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CG, B, N, 0, 0, 0, 0, 0), x)
+    check(lib().npde_cg_step(_ptr(x), int(n_iters), _ptr(y), B, N, ws, wsb, _stream(x)), "npde_cg_step")
+    return y
+
+
 def mg_step(x, bc, f, n_layers, pre, post):
     x = _field(x)
     bc = _require(bc, "bc")

@@ -1,7 +1,7 @@
 """models/get_iterator.py:3-48 -- the drop-in boundary of the reference."""
 import torch
 
-from .iterators import ConvIterator, JacobiIterator, MultigridIterator, UNetIterator
+from .iterators import ConjugateGradient, ConvIterator, JacobiIterator, MultigridIterator, UNetIterator
 
 
 def get_iterator(opt):
@@ -13,12 +13,14 @@ def get_iterator(opt):
     elif opt.iterator == 'multigrid':
         iterator = MultigridIterator(opt.mg_n_layers, opt.mg_pre_smoothing, opt.mg_post_smoothing)
         is_train = False
+    elif opt.iterator == 'cg':
+        iterator = ConjugateGradient(opt.cg_n_iters)
+        is_train = False
     elif opt.iterator == 'conv':
         iterator = ConvIterator(opt.activation, opt.conv_n_layers)
     elif opt.iterator == 'unet':
         iterator = UNetIterator(opt.activation, opt.mg_n_layers, opt.mg_pre_smoothing, opt.mg_post_smoothing)
     else:
-        # 'cg' (models/iterators/conjugate_gradient.py) is outside this build's hot path
         raise NotImplementedError
 
     if torch.cuda.is_available():
@@ -27,7 +29,7 @@ def get_iterator(opt):
     # Compare to Jacobi methods
     if opt.iterator == 'conv' or opt.iterator == 'multigrid':
         compare_model = JacobiIterator()
-    elif opt.iterator == 'unet':
+    elif opt.iterator == 'unet' or opt.iterator == 'cg':
         compare_model = MultigridIterator(opt.mg_n_layers, opt.mg_pre_smoothing, opt.mg_post_smoothing)
     else:
         compare_model = None

@@ -92,6 +92,85 @@ class MultigridIterator(Iterator):
         return 'Multigrid'
 
 
+def _iterate_stepwise(it, x, bc, f, k, gt, want_l2, want_fd, out):
+    """iterate() contract for iterators without a fused k-step kernel (comparison solvers outside the hot
+    path): k forward calls; the error rows still come from the device reductions, no host sync."""
+    x = x.detach()
+    rows_fd = [utils.fd_error(x, bc, f)] if want_fd else None
+    rows_l2 = [] if (want_l2 and gt is not None) else None
+    for _ in range(k):
+        x = it.forward(x, bc, f)
+        if rows_fd is not None:
+            rows_fd.append(utils.fd_error(x, bc, f))
+        if rows_l2 is not None:
+            rows_l2.append(utils.l2_error(x, gt))
+    if out is not None:
+        out.copy_(x)
+        x = out
+    return (x, torch.stack(rows_l2) if rows_l2 else None, torch.stack(rows_fd) if rows_fd is not None else None)
+
+
+class MultigridResidualIterator(Iterator):
+    """models/iterators/jacobi_iterator.py:81-143: V-cycle on the residual equation (the reference notes it
+    "doesn't work well" near boundaries; kept for API completeness).  Composition of the grid operators of
+    this package; the two field additions are element-wise torch ops (exact IEEE, same as the reference)."""
+
+    def __init__(self, n_layers, pre_smoothing, post_smoothing):
+        super(MultigridResidualIterator, self).__init__()
+        self.n_layers = n_layers
+        self.pre_smoothing = pre_smoothing
+        self.post_smoothing = post_smoothing
+        self.n_operations = (pre_smoothing + post_smoothing + 2) * 4 / 3
+
+    def multigrid_step(self, x, bc, f, step):
+        if step == 0:
+            return None
+        x = utils.set_boundary(x.clone(), bc)
+        if self.pre_smoothing > 0:
+            x = JacobiIterator().iterate(x, bc, f, self.pre_smoothing)[0]
+        r = utils.fd_step(x, bc, f) - x
+        zeros_bc = torch.zeros(x.shape[0], 4, device=x.device)
+        r_sub = utils.restriction(r, zeros_bc)
+        ek_sub = self.multigrid_step(r_sub, zeros_bc, -r_sub, step - 1)
+        if ek_sub is not None:
+            x = x + utils.interpolation(ek_sub, zeros_bc)
+        x = utils.set_boundary(x, bc)
+        if self.post_smoothing > 0:
+            x = JacobiIterator().iterate(x, bc, f, self.post_smoothing)[0]
+        return x
+
+    def forward(self, x, bc, f):
+        return self.multigrid_step(x.detach(), bc, f, self.n_layers)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        return _iterate_stepwise(self, x, bc, f, k, gt, want_l2, want_fd, out)
+
+    def name(self):
+        return 'Multigrid residual'
+
+
+class ConjugateGradient(Iterator):
+    """models/iterators/conjugate_gradient.py:8-49: n_iters CG iterations per forward (one npde_cg_step call;
+    alpha / beta stay on the device)."""
+
+    def __init__(self, n_iters):
+        super(ConjugateGradient, self).__init__()
+        self.n_iters = n_iters
+        self.n_operations = n_iters
+
+    def forward(self, x, bc, f):
+        if f is not None:
+            # the reference adds f (B,N,N) to a (B,1,N-2,N-2) residual, which does not broadcast (:24-25)
+            raise RuntimeError("ConjugateGradient supports f=None only (as in the reference)")
+        return F_.cg_step(x, self.n_iters)
+
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+        return _iterate_stepwise(self, x, bc, f, k, gt, want_l2, want_fd, out)
+
+    def name(self):
+        return 'Conjugate Gradient'
+
+
 class _WeightCache(object):
     """Device (n,3,3) stack + host numpy copy of a list of (1,1,3,3) conv weights.  The host
     copy lets the fused kernel take the weights as launch parameters; it is refreshed only

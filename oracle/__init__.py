@@ -231,6 +231,36 @@ def conv_step_bwd(x, bc, f, w, act, gout, want_gx=True):
     return gw, gx
 
 
+def cg_step(x, n_iters):
+    """ConjugateGradient.forward (conjugate_gradient.py:15-47), f = None."""
+    x_, px = _f(x)
+    B, N, _ = x_.shape
+    y = np.empty_like(x_)
+    lib().orc_cg_step(px, int(n_iters), y.ctypes.data_as(ctypes.c_void_p), B, N)
+    return y
+
+
+def multigrid_residual_step(x, bc, f, n_layers, pre, post):
+    """MultigridResidualIterator.forward (jacobi_iterator.py:81-143) composed from the operators above."""
+    def level(x, bc, f, step):
+        if step == 0:
+            return None
+        x = set_boundary(x, bc)
+        for _ in range(pre):
+            x = fd_step(x, bc, f)
+        r = fd_step(x, bc, f) - x
+        zeros = np.zeros((x.shape[0], 4), np.float32)
+        r_sub = restriction(r, zeros)
+        ek = level(r_sub, zeros, -r_sub, step - 1)
+        if ek is not None:
+            x = x + interpolation(ek, zeros)
+        x = set_boundary(x, bc)
+        for _ in range(post):
+            x = fd_step(x, bc, f)
+        return x
+    return level(np.ascontiguousarray(x, np.float32), bc, f, n_layers)
+
+
 def iterate(iterator, x, bc, f, w, act, k, gt=None, want_fd=False):
     """iterator: 'jacobi' | 'conv'.  Returns (x_k, err_l2 (k,B) | None, err_fd (k+1,B) | None)."""
     x_, px = _f(x)

@@ -494,7 +494,36 @@ def gen_pipeline():
          eigw_abs_sorted=np.sort(np.abs(np.linalg.eig(Aw)[0])), rho=np.array(utils.spectral_radius(Aw)))
 
 
-GENERATORS = {"ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
+def gen_solvers():
+    """The comparison solvers of get_iterator: ConjugateGradient (conjugate_gradient.py:8-49) and
+    MultigridResidualIterator (jacobi_iterator.py:81-143), run by the reference."""
+    from models.iterators import ConjugateGradient
+    from models.iterators.jacobi_iterator import MultigridResidualIterator
+    for tag, B, N, n_iters in (("square17_4", 3, 17, 4), ("square33_10", 2, 33, 10), ("square65_25", 2, 65, 25)):
+        seed()
+        x, bc, _ = square_problem(B, N, False)
+        it = ConjugateGradient(n_iters)
+        y = it(x.clone(), bc, None)
+        y2 = it(y.clone(), bc, None)
+        save("cg_" + tag, x=npy(x), bc=npy(bc), y=npy(y), y2=npy(y2), meta=np.array([n_iters]))
+    for tag, geom, B, N, L, pre, post, poisson in (("square33_2_2_2", "square", 2, 33, 2, 2, 2, False),
+                                                  ("square65_3_1_2_f", "square", 2, 65, 3, 1, 2, True),
+                                                  ("lshape33_2_2_1", "Lshape", 2, 33, 2, 2, 1, False)):
+        seed()
+        x, bc, f = square_problem(B, N, poisson) if geom == "square" else mask_problem(B, N, geom)
+        it = MultigridResidualIterator(L, pre, post)
+        it.is_bc_mask = geom != "square"
+        y = it(x.clone(), bc, f)
+        save("mgres_" + tag, x=npy(x), bc=npy(bc), f=None if f is None else npy(f), y=npy(y),
+             meta=np.array([L, pre, post]))
+    rows = []
+    it, cmp_, ratio, is_train = get_iterator(make_opt(iterator="cg", geometry="square"))
+    rows.append(("cg", "square", it.name(), cmp_.name(), float(ratio), bool(is_train), bool(it.is_bc_mask),
+                 float(it.n_operations)))
+    np.save(os.path.join(HERE, "get_iterator_contract_cg.npy"), np.array(rows, dtype=object), allow_pickle=True)
+
+
+GENERATORS = {"solvers": gen_solvers, "ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
               "backward": gen_backward, "bptt": gen_bptt, "drivers": gen_drivers, "pipeline": gen_pipeline}
 
 if __name__ == "__main__":

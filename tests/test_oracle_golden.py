@@ -95,3 +95,23 @@ def test_conv_backward(oracle, name):
     # autograd's reduction order is unspecified: tolerance, relative to the largest entry
     assert rel_err(gw, g["gw"]) <= 2e-5, (gw, g["gw"])
     assert rel_err(gx, g["gx"]) <= 2e-5
+
+
+@pytest.mark.parametrize("name", golden_names("cg_"))
+def test_conjugate_gradient(oracle, name):
+    """ConjugateGradient.forward: the dot products are torch.sum trees of unspecified order, so the oracle
+    (fp64-accumulated sums) matches the reference to rounding: 1e-5 relative."""
+    g = load_golden(name)
+    n_iters = int(g["meta"][0])
+    y = oracle.cg_step(g["x"], n_iters)
+    assert rel_err(y, g["y"]) <= 1e-5
+    assert rel_err(oracle.cg_step(y, n_iters), g["y2"]) <= 1e-5
+    assert_bitwise(y[:, 0, :], g["x"][:, 0, :], "boundary ring kept")
+
+
+@pytest.mark.parametrize("name", golden_names("mgres_"))
+def test_multigrid_residual(oracle, name):
+    g = load_golden(name)
+    L, pre, post = (int(v) for v in g["meta"])
+    assert_bitwise(oracle.multigrid_residual_step(g["x"], g["bc"], g.get("f"), L, pre, post), g["y"],
+                   "MultigridResidualIterator.forward")

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_bitwise, load_golden, rel_err
+from conftest import assert_bitwise, golden_names, load_golden, rel_err
 from test_parity import Backend, BACKENDS
 
 
@@ -240,3 +240,51 @@ def test_spectral_matrices_vs_reference(be):
     np.testing.assert_allclose(u.spectral_radius(H.dot(T) + T - H), float(g["rho"]), rtol=1e-5)
     assert np.sort(np.abs(w))[-1] == pytest.approx(1.0, abs=1e-5)  # the affine row; all others must be < 1
     assert np.sort(np.abs(w))[-2] < 1.0
+
+
+# ------------------------------------------------------- comparison solvers of get_iterator (8f.4) --
+@pytest.mark.parametrize("name", golden_names("cg_"))
+def test_conjugate_gradient_vs_reference_and_oracle(be, oracle, name):
+    """npde_cg_step: n CG iterations with device-resident alpha / beta.  fp32 dot products are summed in a
+    different (deterministic) association than torch.sum: 1e-5 relative against reference and oracle."""
+    g = load_golden(name)
+    n_iters = int(g["meta"][0])
+    it = be.npde.ConjugateGradient(n_iters)
+    x, bc = be.t(g["x"]), be.t(g["bc"])
+    y = it(x, bc, None)
+    assert rel_err(be.n(y), g["y"]) <= 1e-5
+    assert rel_err(be.n(y), oracle.cg_step(g["x"], n_iters)) <= 1e-5
+    y2 = it(y, bc, None)
+    assert rel_err(be.n(y2), g["y2"]) <= 1e-5
+    assert_bitwise(be.n(it(x, bc, None)), be.n(y), "deterministic")
+    assert_bitwise(be.n(x), g["x"], "input untouched")
+    assert_bitwise(be.n(y)[:, :, 0], g["x"][:, :, 0], "ring kept")
+    with pytest.raises(RuntimeError):
+        it(x, bc, torch.zeros_like(x))
+    # iterate() contract used by calculate_errors: fd rows from the device reductions
+    yk, _, rows = it.iterate(x, bc, None, 2, want_fd=True)
+    assert_bitwise(be.n(yk), be.n(y2), "iterate(2) = two forwards")
+    assert rows.shape == (3, x.shape[0])
+
+
+@pytest.mark.parametrize("name", golden_names("mgres_"))
+def test_multigrid_residual_vs_reference(be, name):
+    g = load_golden(name)
+    L, pre, post = (int(v) for v in g["meta"])
+    it = be.npde.MultigridResidualIterator(L, pre, post)
+    it.is_bc_mask = g["bc"].ndim == 4
+    x = be.t(g["x"])
+    assert_bitwise(be.n(it(x, be.t(g["bc"]), be.t(g.get("f")))), g["y"], "MultigridResidualIterator.forward")
+    assert_bitwise(be.n(x), g["x"], "input untouched")
+
+
+def test_get_iterator_cg_contract(be):
+    rows = np.load(os.path.join(os.path.dirname(__file__), "golden", "get_iterator_contract_cg.npy"),
+                   allow_pickle=True)
+    for itname, geom, name, cmp_name, ratio, is_train, is_mask, n_ops in rows:
+        opt = argparse.Namespace(iterator=itname, activation="clamp", conv_n_layers=3, mg_n_layers=3,
+                                 mg_pre_smoothing=2, mg_post_smoothing=2, cg_n_iters=4, geometry=geom, is_train=True)
+        it, cmp_, r, tr = be.npde.get_iterator(opt)
+        assert it.name() == name and cmp_.name() == cmp_name
+        assert float(r) == float(ratio) and bool(tr) == bool(is_train)
+        assert bool(it.is_bc_mask) == bool(is_mask) and float(it.n_operations) == float(n_ops)

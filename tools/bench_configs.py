@@ -196,6 +196,18 @@ def main():
     dt = time.perf_counter() - t0
     print(json.dumps({"name": "train_step_conv3_257_b64_K20 (N~U{1..20} fused no-grad steps + 1 differentiable step, Adam)",
                       "ms_per_train_step": dt / n * 1e3}), flush=True)
+    # BASELINE config 4 proper: gradient through ALL N unrolled iterations (N ~ U{1..20}, mean 10.5)
+    modelf = npde.HeatModel(opt, full_bptt=True)
+    modelf.iterator.to(DEV)
+    modelf.train(x, gt, bc, None)
+    torch.cuda.synchronize()
+    np.random.seed(1)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        modelf.train(x, gt, bc, None)
+    torch.cuda.synchronize()
+    print(json.dumps({"name": "train_step_conv3_257_b64_K20_full_bptt (gradient through all N~U{1..20} iterations, Adam)",
+                      "ms_per_train_step": (time.perf_counter() - t0) / n * 1e3}), flush=True)
     opt.iterator = "unet"
     modelu = npde.HeatModel(opt)
     modelu.iterator.to(DEV)
