@@ -69,6 +69,7 @@ extern "C" {
 #define NPDE_WS_UNET_FWD 4   /* npde_unet_H, npde_unet_step_fwd */
 #define NPDE_WS_UNET_BWD 5   /* npde_unet_step_bwd */
 #define NPDE_WS_CG 6         /* npde_cg_step */
+#define NPDE_WS_CONV_BPTT 7  /* npde_conv_iterate_bwd (npde_conv_iterate_tape uses NPDE_WS_CONV_FWD) */
 #define NPDE_WS_ITERATE 16   /* npde_iterate: pass NPDE_WS_ITERATE + NPDE_IT_* of the iterator */
 
 int npde_version(void);
@@ -130,6 +131,18 @@ int npde_conv_step_fwd(const float *x, const float *bc, int bc_kind, const float
 int npde_conv_step_bwd(const float *x, const float *bc, int bc_kind, const float *f, const float *w,
                        int n_layers, int act, const float *gout, float *gw, float *gx, int B, int N, void *ws,
                        size_t ws_bytes, void *stream);
+
+/* Backprop through k unrolled ConvIterator steps (BASELINE config 4; the reference gets it from autograd over a
+ * Python loop of forward calls, models/heat_model.py:48-53 without the detach).
+ * npde_conv_iterate_tape: tape (k,B,N,N) receives x_0 = x, x_1, ..., x_{k-1} and y = x_k  (k >= 1).
+ * npde_conv_iterate_bwd:  gout = dL/dx_k; gw (n_layers,3,3) is OVERWRITTEN with the weight gradient summed over the
+ *   k steps in fp32, last step first (the order autograd accumulates in); gx = dL/dx_0 may be NULL. */
+int npde_conv_iterate_tape(const float *x, const float *bc, int bc_kind, const float *f, const float *w,
+                           const float *w_host, int n_layers, int act, int k, float *tape, float *y, int B, int N,
+                           void *ws, size_t ws_bytes, void *stream);
+int npde_conv_iterate_bwd(const float *tape, const float *bc, int bc_kind, const float *f, const float *w,
+                          int n_layers, int act, int k, const float *gout, float *gw, float *gx, int B, int N,
+                          void *ws, size_t ws_bytes, void *stream);
 
 /* utils/heat_utils.py:352-360 subsample: x (B,N,N) -> y (B,M,M), M=(N-1)/2+1 (exact injection). */
 int npde_subsample(const float *x, float *y, int B, int N, void *stream);

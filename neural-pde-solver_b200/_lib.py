@@ -18,7 +18,7 @@ BC_SQUARE, BC_MASK = 0, 1
 ACT = {"none": 0, "clamp": 1, "sigmoid": 2}
 AGG = {"max": 0, "mean": 1}
 IT_JACOBI, IT_CONV, IT_MULTIGRID, IT_UNET = 0, 1, 2, 3
-WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_CG, WS_ITERATE = 0, 1, 2, 3, 4, 5, 6, 16
+WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_CG, WS_CONV_BPTT, WS_ITERATE = 0, 1, 2, 3, 4, 5, 6, 7, 16
 MAX_CONV_LAYERS = 8
 
 _c_float_p = ctypes.c_void_p  # raw device pointers
@@ -52,6 +52,10 @@ PROTOTYPES = {
     "npde_conv_H": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_conv_step_fwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _vp, _int, _int, _vp, _size, _vp]),
     "npde_conv_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp, _vp, _vp, _int, _int, _vp, _size, _vp]),
+    "npde_conv_iterate_tape": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _int, _int, _vp,
+                                      _size, _vp]),
+    "npde_conv_iterate_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _int, _int, _vp,
+                                     _size, _vp]),
     "npde_subsample": (_int, [_vp, _vp, _int, _int, _vp]),
     "npde_restrict": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),
     "npde_prolong": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),

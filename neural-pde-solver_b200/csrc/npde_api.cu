@@ -448,6 +448,35 @@ struct IterWs {
   }
 };
 
+// Backward of one Conv step given its input x (recomputes the layer tape), SURVEY.md Appendix B.
+// gw is overwritten, or accumulated into in fp32 when `accumulate`.
+int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kind, const float *f, const float *w,
+                       int L, int act, const float *gout, float *gw, bool accumulate, float *gx, int B, int N,
+                       cudaStream_t st) {
+  int Sz = N - 2;
+  size_t bytes = sizeof(float) * (size_t)B * Sz * Sz;
+  const float *mask = mask0(bc, bc_kind, N);
+  size_t mbs = 2 * (size_t)N * N;
+  // forward with tape
+  TRY(npde::psi_residual(x, f, mask, mbs, c.y_int, c.rs[0], B, N, st));
+  for (int l = 0; l < L; ++l) TRY(npde::conv3x3(c.rs[l], Sz, w + 9 * l, 1, 1, mask, mbs, c.rs[l + 1], Sz, B, st));
+  // backward
+  TRY(npde::bwd_gz(gout, c.y_int, c.rs[L], mask, mbs, act, c.gz, B, N, st));
+  TRY(d2d(c.g, c.gz, bytes, st));
+  float *g = c.g, *t = c.t;
+  for (int l = L - 1; l >= 0; --l) {
+    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
+    TRY(npde::weight_grad(g, Sz, c.rs[l], Sz, 1, 1, gw + 9 * l, B, c.wg, c.wg_bytes, st, accumulate));
+    TRY(npde::conv3x3_transpose(g, Sz, w + 9 * l, 1, 1, t, Sz, B, st));
+    float *sw = g; g = t; t = sw;
+  }
+  if (gx) {
+    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
+    TRY(npde::bwd_gx(c.gz, g, gx, B, N, st));
+  }
+  return NPDE_OK;
+}
+
 }  // namespace
 
 // ======================================================================= C ABI
@@ -551,30 +580,51 @@ int npde_conv_step_bwd(const float *x, const float *bc, int bc_kind, const float
   if (n_layers < 1 || n_layers > NPDE_MAX_CONV_LAYERS) return NPDE_ERR_LAYERS;
   if (!w || !gw) return NPDE_ERR_NULL;
   TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_CONV_BWD, B, N, bc_kind, n_layers, 0, 0, 0)));
-  cudaStream_t st = S(stream);
   Bump b(ws);
   ConvBwdWs c;
   c.carve(b, B, N, n_layers);
-  int Sz = N - 2, L = n_layers;
-  size_t bytes = sizeof(float) * (size_t)B * Sz * Sz;
-  const float *mask = mask0(bc, bc_kind, N);
-  size_t mbs = 2 * (size_t)N * N;
-  // forward with tape
-  TRY(npde::psi_residual(x, f, mask, mbs, c.y_int, c.rs[0], B, N, st));
-  for (int l = 0; l < L; ++l) TRY(npde::conv3x3(c.rs[l], Sz, w + 9 * l, 1, 1, mask, mbs, c.rs[l + 1], Sz, B, st));
-  // backward (SURVEY.md Appendix B)
-  TRY(npde::bwd_gz(gout, c.y_int, c.rs[L], mask, mbs, act, c.gz, B, N, st));
-  TRY(d2d(c.g, c.gz, bytes, st));
-  float *g = c.g, *t = c.t;
-  for (int l = L - 1; l >= 0; --l) {
-    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
-    TRY(npde::weight_grad(g, Sz, c.rs[l], Sz, 1, 1, gw + 9 * l, B, c.wg, c.wg_bytes, st));
-    TRY(npde::conv3x3_transpose(g, Sz, w + 9 * l, 1, 1, t, Sz, B, st));
-    float *sw = g; g = t; t = sw;
+  return conv_step_bwd_impl(c, x, bc, bc_kind, f, w, n_layers, act, gout, gw, false, gx, B, N, S(stream));
+}
+
+int npde_conv_iterate_tape(const float *x, const float *bc, int bc_kind, const float *f, const float *w,
+                           const float *w_host, int n_layers, int act, int k, float *tape, float *y, int B, int N,
+                           void *ws, size_t ws_bytes, void *stream) {
+  TRY(npde::check_common(x, y, B, N));
+  TRY(npde::check_bc(bc, bc_kind));
+  if (!tape) return NPDE_ERR_NULL;
+  if (k < 1) return NPDE_ERR_ARG;
+  const size_t n = (size_t)B * N * N;
+  TRY(d2d(tape, x, sizeof(float) * n, S(stream)));
+  for (int t = 0; t < k; ++t) {
+    float *dst = (t + 1 < k) ? tape + (size_t)(t + 1) * n : y;
+    TRY(npde_conv_step_fwd(tape + (size_t)t * n, bc, bc_kind, f, w, w_host, n_layers, act, dst, B, N, ws, ws_bytes,
+                           stream));
   }
-  if (gx) {
-    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
-    TRY(npde::bwd_gx(c.gz, g, gx, B, N, st));
+  return NPDE_OK;
+}
+
+int npde_conv_iterate_bwd(const float *tape, const float *bc, int bc_kind, const float *f, const float *w,
+                          int n_layers, int act, int k, const float *gout, float *gw, float *gx, int B, int N,
+                          void *ws, size_t ws_bytes, void *stream) {
+  TRY(npde::check_common(tape, gout, B, N));
+  TRY(npde::check_bc(bc, bc_kind));
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  if (n_layers < 1 || n_layers > NPDE_MAX_CONV_LAYERS) return NPDE_ERR_LAYERS;
+  if (!w || !gw) return NPDE_ERR_NULL;
+  if (k < 1) return NPDE_ERR_ARG;
+  TRY(ws_ok(ws, ws_bytes, npde_workspace_bytes(NPDE_WS_CONV_BPTT, B, N, bc_kind, n_layers, 0, 0, 0)));
+  Bump b(ws);
+  ConvBwdWs c;
+  c.carve(b, B, N, n_layers);
+  const size_t n = (size_t)B * N * N;
+  float *g[2] = {b.take<float>(n), b.take<float>(n)};
+  const float *gin = gout;
+  // last step first: the order in which autograd adds the per-step weight gradients (fp32)
+  for (int t = k - 1; t >= 0; --t) {
+    float *gnext = (t > 0) ? g[t & 1] : gx;
+    TRY(conv_step_bwd_impl(c, tape + (size_t)t * n, bc, bc_kind, f, w, n_layers, act, gin, gw, t != k - 1, gnext, B, N,
+                           S(stream)));
+    gin = gnext;
   }
   return NPDE_OK;
 }
@@ -856,6 +906,14 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
     }
     case NPDE_WS_CG:
       return npde::cg_ws_bytes(B, N);
+    case NPDE_WS_CONV_BPTT: {
+      ConvBwdWs c;
+      int L = n_layers < 0 ? 0 : (n_layers > NPDE_MAX_CONV_LAYERS ? NPDE_MAX_CONV_LAYERS : n_layers);
+      c.carve(b, B, N, L);
+      b.take<float>((size_t)B * N * N);
+      b.take<float>((size_t)B * N * N);
+      return b.off;
+    }
     case NPDE_WS_ITERATE + NPDE_IT_JACOBI:
     case NPDE_WS_ITERATE + NPDE_IT_CONV:
     case NPDE_WS_ITERATE + NPDE_IT_MULTIGRID:

@@ -49,8 +49,10 @@ __global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int s
 }
 
 // adjoint of k_conv3x3 w.r.t. its input: out[p,q] = sum_{a,c} w[a,c] * g[(p+pad-a)/s, (q+pad-c)/s]
+// (stride is a template parameter: the divisibility tests below would otherwise be integer divisions per tap)
+template <int stride>
 __global__ void k_conv3x3_transpose(const float *__restrict__ g, int Hg, const float *__restrict__ w,
-                                    int stride, int pad, float *__restrict__ out, int Ho) {
+                                    int pad, float *__restrict__ out, int Ho) {
   int q = blockIdx.x * TX + threadIdx.x, p = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (p >= Ho || q >= Ho) return;
   const float *gb = g + (size_t)b * Hg * Hg;
@@ -200,22 +202,23 @@ __global__ void k_bwd_gx(const float *__restrict__ gz, const float *__restrict__
 constexpr int WG_THREADS = 256;
 __global__ void __launch_bounds__(WG_THREADS)
 k_weight_grad(const float *__restrict__ g, int Hg, const float *__restrict__ r, int Hr, int stride, int pad,
-              float *gw9, double *part, unsigned *counter, int rows_per_block, int blocks_per_img) {
+              float *gw9, double *part, unsigned *counter, int rows_per_block, int blocks_per_img, int accumulate) {
   int b = blockIdx.x / blocks_per_img, chunk = blockIdx.x % blocks_per_img;
   const float *gb = g + (size_t)b * Hg * Hg, *rb = r + (size_t)b * Hr * Hr;
   int i0 = chunk * rows_per_block, i1 = min(i0 + rows_per_block, Hg);
   double acc[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) acc[t] = 0.0;
-  for (int idx = threadIdx.x; idx < (i1 - i0) * Hg; idx += WG_THREADS) {
-    int i = i0 + idx / Hg, j = idx % Hg;
-    float gv = __ldg(gb + (size_t)i * Hg + j);
+  // a warp per row, lanes along the row: coalesced, no index arithmetic beyond adds
+  for (int i = i0 + (int)(threadIdx.x >> 5); i < i1; i += WG_THREADS / 32)
+    for (int j = threadIdx.x & 31; j < Hg; j += 32) {
+      float gv = __ldg(gb + (size_t)i * Hg + j);
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+      for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        acc[a * 3 + c] += (double)gv * (double)ldz(rb, Hr, i * stride + a - pad, j * stride + c - pad);
-  }
+        for (int c = 0; c < 3; ++c)
+          acc[a * 3 + c] += (double)gv * (double)ldz(rb, Hr, i * stride + a - pad, j * stride + c - pad);
+    }
   __shared__ double sh[WG_THREADS / 32][9];
   __shared__ bool last;
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -237,18 +240,21 @@ k_weight_grad(const float *__restrict__ g, int Hg, const float *__restrict__ r, 
     last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (last && threadIdx.x < 9) {
+  if (last) {  // the block that finishes last adds the per-block partials: a warp per tap, fixed order
     __threadfence();
     volatile double *p = part;
-    double v = 0.0;
-    for (unsigned k = 0; k < gridDim.x; ++k) v += p[(size_t)k * 9 + threadIdx.x];
-    gw9[threadIdx.x] = (float)v;
+    for (int t = warp; t < 9; t += WG_THREADS / 32) {
+      double v = 0.0;
+      for (unsigned k = lane; k < gridDim.x; k += 32) v += p[(size_t)k * 9 + t];
+      v = npde_warp_sum(v);
+      if (lane == 0) gw9[t] = accumulate ? __fadd_rn(gw9[t], (float)v) : (float)v;
+    }
   }
 }
 
 inline int wg_rows_per_block(int Hg) {
-  int rows = 32768 / (Hg > 0 ? Hg : 1);
-  return rows < 1 ? 1 : rows;
+  int rows = 8192 / (Hg > 0 ? Hg : 1);
+  return rows < WG_THREADS / 32 ? WG_THREADS / 32 : rows;
 }
 
 }  // namespace
@@ -270,7 +276,9 @@ int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad
 
 int conv3x3_transpose(const float *g, int Hg, const float *w9, int stride, int pad, float *out, int Ho, int B,
                       cudaStream_t st) {
-  NPDE_LAUNCH(k_conv3x3_transpose, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, g, Hg, w9, stride, pad, out, Ho);
+  if (stride == 1) NPDE_LAUNCH(k_conv3x3_transpose<1>, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, g, Hg, w9, pad, out, Ho);
+  else if (stride == 2) NPDE_LAUNCH(k_conv3x3_transpose<2>, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, g, Hg, w9, pad, out, Ho);
+  else return NPDE_ERR_ARG;
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
@@ -339,7 +347,7 @@ size_t weight_grad_ws_bytes(int B, int Hg) {
 }
 
 int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int pad, float *gw9, int B,
-                void *ws, size_t ws_bytes, cudaStream_t st) {
+                void *ws, size_t ws_bytes, cudaStream_t st, bool accumulate) {
   if (!ws || ((uintptr_t)ws & 255) || ws_bytes < weight_grad_ws_bytes(B, Hg)) return NPDE_ERR_WORKSPACE;
   int rpb = wg_rows_per_block(Hg);
   int bpi = (Hg + rpb - 1) / rpb;
@@ -349,7 +357,7 @@ int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int 
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return (int)e;
   NPDE_LAUNCH(k_weight_grad, dim3(B * bpi), dim3(WG_THREADS), 0, st, g, Hg, r, Hr, stride, pad, gw9, part,
-              counter, rpb, bpi);
+              counter, rpb, bpi, accumulate ? 1 : 0);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

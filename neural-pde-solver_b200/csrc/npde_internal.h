@@ -87,8 +87,9 @@ int pad_up_crop_transpose(const float *g, int s, float *out, int B, cudaStream_t
 int bwd_gz(const float *gout, const float *y_int, const float *rL, const float *mask, size_t mask_bstride,
            int act, float *gz, int B, int N, cudaStream_t st);
 // gw9 (9 floats) <- sum_{b,i,j} g[b,i,j] * r[b, i*stride + a - pad, j*stride + c - pad]
+// accumulate: gw9 += (fp32) instead of gw9 = (backprop through several steps sums in fp32, like autograd)
 int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int pad, float *gw9, int B,
-                void *ws, size_t ws_bytes, cudaStream_t st);
+                void *ws, size_t ws_bytes, cudaStream_t st, bool accumulate = false);
 size_t weight_grad_ws_bytes(int B, int Hg);
 int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream_t st);
 

@@ -248,6 +248,47 @@ class ConvStepFn(torch.autograd.Function):
         return gx, None, None, gw.reshape(w.shape), None, None
 
 
+class ConvUnrollFn(torch.autograd.Function):
+    """k differentiable ConvIterator steps as ONE autograd node: forward keeps the k iterates
+    (npde_conv_iterate_tape), backward walks them back in a single library call (npde_conv_iterate_bwd).
+    Same gradients as k chained ConvStepFn nodes, without k round trips through the autograd engine."""
+
+    @staticmethod
+    def forward(ctx, x, bc, f, w, act, w_host, k):
+        x = _field(x)
+        bc = _require(bc, "bc")
+        f = _opt(f, "f")
+        wd = _weights(w)
+        B, N, _ = x.shape
+        L = int(wd.shape[0])
+        kind = bc_kind(x, bc)
+        tape = torch.empty((k, B, N, N), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_FWD, B, N, kind, L, 0, 0, 0), x)
+        wh = None if w_host is None else ctypes.c_void_p(np.ascontiguousarray(w_host, np.float32).ctypes.data)
+        check(lib().npde_conv_iterate_tape(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wd), wh, L, _act(act), int(k),
+                                           _ptr(tape), _ptr(y), B, N, ws, wsb, _stream(x)), "npde_conv_iterate_tape")
+        ctx.save_for_backward(tape, bc, f if f is not None else x.new_empty(0), wd)
+        ctx.has_f, ctx.act, ctx.k, ctx.w_shape = f is not None, act, int(k), w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, gout):
+        tape, bc, f, w = ctx.saved_tensors
+        f = f if ctx.has_f else None
+        gout = _field(gout, "gout")
+        _, B, N, _ = tape.shape
+        L = int(w.shape[0])
+        kind = bc_kind(tape[0], bc)
+        gw = torch.empty((L, 3, 3), dtype=torch.float32, device=tape.device)
+        gx = torch.empty_like(gout) if ctx.needs_input_grad[0] else None
+        ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_BPTT, B, N, kind, L, 0, 0, 0), tape)
+        check(lib().npde_conv_iterate_bwd(_ptr(tape), _ptr(bc), kind, _ptr(f), _ptr(w), L, _act(ctx.act), ctx.k,
+                                          _ptr(gout), _ptr(gw), _ptr(gx), B, N, ws, wsb, _stream(tape)),
+              "npde_conv_iterate_bwd")
+        return gx, None, None, gw.reshape(ctx.w_shape), None, None, None
+
+
 # -------------------------------------------------------- Multigrid / UNet --
 def cg_step(x, n_iters):
     """ConjugateGradient.forward (conjugate_gradient.py:15-47): n_iters CG iterations, boundary ring kept."""

@@ -85,6 +85,8 @@ class HeatModel(object):
         iteration is a differentiable step (the autograd tape keeps one field per step)."""
         y = start.detach()
         if self.full_bptt:
+            if hasattr(self.iterator, 'unrolled'):
+                return self.iterator.unrolled(y, bc, f, n_steps)  # one autograd node, one backward call
             for _ in range(n_steps):
                 y = self.iter_step(y, bc, f)
             return y

@@ -230,6 +230,19 @@ class ConvIterator(Iterator):
             return F_.ConvStepFn.apply(x, bc, f, w, self.act, w_host)
         return F_.conv_step(x, bc, f, w_dev, self.act, w_host)
 
+    def unrolled(self, x, bc, f, k):
+        """k chained forward calls as one differentiable node (backprop through all k iterations)."""
+        self._check_act()
+        self._consistent(x, bc)
+        params = self._params()
+        if k < 1 or not params:
+            for _ in range(k):
+                x = self.forward(x, bc, f)
+            return x
+        _, w_host = self._cache.get(params)
+        w = torch.stack([p.reshape(3, 3) for p in params])
+        return F_.ConvUnrollFn.apply(x, bc, f, w, self.act, w_host, k)
+
     def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
         self._check_act()
         self._consistent(x, bc)

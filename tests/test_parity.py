@@ -383,6 +383,20 @@ def test_backprop_through_k_steps(be, name):
         gw = np.stack([be.n(l.weight.grad)[0, 0] for l in it.layers])
         assert rel_err(gw, g["gw"]) <= 5e-5, (gw, g["gw"])
     assert rel_err(be.n(xg.grad), g["gx"]) <= 5e-5
+    if "w_first" not in g:
+        # the same k steps as ONE autograd node (npde_conv_iterate_tape / npde_conv_iterate_bwd): identical
+        # forward, and gradients summed over the steps in the order autograd uses -> bit-identical
+        chained = [be.n(l.weight.grad).copy() for l in it.layers], be.n(xg.grad).copy()
+        for l in it.layers:
+            l.weight.grad = None
+        xg2 = x.clone().requires_grad_(True)
+        y2 = it.unrolled(xg2, bc, f, int(g["k"]))
+        torch.nn.MSELoss()(y2, gt).backward()
+        assert_bitwise(be.n(y2), be.n(y), "fused unrolled forward")
+        for l, ref in zip(it.layers, chained[0]):
+            assert_bitwise(be.n(l.weight.grad), ref, "fused BPTT weight gradient")
+        assert_bitwise(be.n(xg2.grad), chained[1], "fused BPTT input gradient")
+        assert_bitwise(be.n(x), g["x"], "input untouched")
 
 
 def test_full_bptt_training_option(be):
