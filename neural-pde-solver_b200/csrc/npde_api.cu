@@ -448,6 +448,66 @@ struct IterWs {
   }
 };
 
+// ------------------------------------------------------------ CUDA graphs ---
+// Small problems are launch bound (a 32 x 65^2 Conv3 step is one 3 us kernel; a U-Net step at 1 x 1025^2 is ~25
+// kernels of a few us each), so the k-step loop replays a short captured segment instead of issuing every launch
+// from the host: the segment (an even number of steps, ping-pong buffers back where they started) is captured
+// once on a private stream, instantiated, and launched into the caller's stream as often as it fits.  The
+// caller's stream may be the legacy default stream, which cannot capture -- hence the private stream.
+struct StepGraph {
+#ifndef NPDE_EMU
+  cudaStream_t cs = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool capturing = false;
+  // false: graphs are not usable here (caller is capturing itself, or stream creation failed) -> plain launches
+  bool begin(cudaStream_t caller) {
+    cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(caller, &status) != cudaSuccess || status != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return false;
+    }
+    if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return false; }
+    capturing = true;
+    return true;
+  }
+  int abort_capture() {
+    if (capturing) { cudaStreamEndCapture(cs, &graph); capturing = false; cudaGetLastError(); }
+    return NPDE_OK;
+  }
+  int finish_and_launch(int times, cudaStream_t caller) {
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    capturing = false;
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < times; ++i) {
+      e = cudaGraphLaunch(exec, caller);
+      if (e != cudaSuccess) return (int)e;
+    }
+    return NPDE_OK;
+  }
+  ~StepGraph() {
+    abort_capture();
+    if (exec) cudaGraphExecDestroy(exec);  // in-flight launches complete; resources are released afterwards
+    if (graph) cudaGraphDestroy(graph);
+    if (cs) cudaStreamDestroy(cs);
+  }
+#endif
+};
+
+// replaying pays once the host cannot keep the device busy: few cells per launch and enough steps to amortise
+// the capture + instantiation
+inline bool graph_worthwhile(size_t cells, int k) {
+#ifdef NPDE_EMU
+  (void)cells; (void)k;
+  return false;
+#else
+  return cells <= ((size_t)8 << 20) && k >= 16;
+#endif
+}
+
 // Backward of one Conv step given its input x (recomputes the layer tape), SURVEY.md Appendix B.
 // gw is overwritten, or accumulated into in fp32 when `accumulate`.
 int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kind, const float *f, const float *w,
@@ -985,20 +1045,41 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       bcf.mask = npde::as_const(mp);
     }
     int left = d->k, flip = 0, done = 0;
-    while (left > 0) {
-      int adv = 1;
-      if (jac_fast && !d->f && !want_err && d->bc_kind == NPDE_BC_SQUARE) {
-        adv = depth;
-        while (adv > left) adv >>= 1;
+    const int full_adv = (jac_fast && !d->f && !want_err && d->bc_kind == NPDE_BC_SQUARE) ? depth : 1;
+    auto launch = [&](const npde::FieldView &src, const npde::FieldViewMut &dst, int adv, cudaStream_t s) -> int {
+      if (conv_fast) return npde::conv_stream(src, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, s);
+      return npde::jacobi_stream(src, dst, bcf, fv, adv, B, N, s);
+    };
+#ifndef NPDE_EMU
+    // launch-bound sizes: x_in -> pad[0] once, then replay a captured segment of SEG launches pad[0] -> pad[1] -> ...
+    // -> pad[0]; the plain loop below finishes the remainder and writes the caller's tensor
+    constexpr int SEG = 32;
+    if (!want_err && graph_worthwhile(cells, d->k) && left > full_adv * (SEG + 1)) {
+      StepGraph sg;
+      if (sg.begin(st)) {
+        int rc = NPDE_OK;
+        for (int i = 0; i < SEG && rc == NPDE_OK; ++i) rc = launch(npde::as_const(pad[i & 1]), pad[(i + 1) & 1], full_adv, sg.cs);
+        if (rc != NPDE_OK) { sg.abort_capture(); return rc; }
+        TRY(launch(cur, pad[0], full_adv, st));
+        left -= full_adv;
+        done += full_adv;
+        int times = (left - 1) / (full_adv * SEG);
+        TRY(sg.finish_and_launch(times, st));
+        left -= times * full_adv * SEG;
+        done += times * full_adv * SEG;
+        cur = npde::as_const(pad[0]);
+        flip = 1;
       }
+    }
+#endif
+    while (left > 0) {
+      int adv = full_adv;
+      while (adv > left) adv >>= 1;
       // the final launch writes the caller's tensor directly (reference layout)
       bool final_launch = (left - adv == 0);
       bool alias = final_launch && (const void *)d->x_out == (const void *)cur.p;  // k == 1 in place
       npde::FieldViewMut dst = (final_launch && !alias) ? last : pad[flip];
-      if (conv_fast)
-        TRY(npde::conv_stream(cur, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, st));
-      else
-        TRY(npde::jacobi_stream(cur, dst, bcf, fv, adv, B, N, st));
+      TRY(launch(cur, dst, adv, st));
       left -= adv;
       done += adv;
       if (final_launch && alias) {
@@ -1024,30 +1105,46 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     wp = wf + 9 * (size_t)d->n_layers * d->pre;
     wsnd = wp + 9 * (size_t)(d->n_layers - 1);
   }
-  for (int t = 0; t < d->k; ++t) {
+  auto step = [&](const float *src, float *dst, void *s) -> int {
+    switch (it) {
+      case NPDE_IT_JACOBI: {
+        const float *res = nullptr;
+        return npde::jacobi_steps(src, dst, nullptr, d->bc, d->bc_kind, d->f, 1, B, N, &res, S(s));
+      }
+      case NPDE_IT_CONV:
+        return npde_conv_step_fwd(src, d->bc, d->bc_kind, d->f, d->w, d->w_host, d->n_layers, d->act, dst, B, N,
+                                  w.step, w.step_bytes, s);
+      case NPDE_IT_MULTIGRID:
+        return npde_mg_step(src, d->bc, d->bc_kind, d->f, d->n_layers, d->pre, d->post, dst, B, N, w.step,
+                            w.step_bytes, s);
+      default:
+        return npde_unet_step_fwd_hw(src, d->bc, d->bc_kind, d->f, wf, wp, wsnd, d->w_host, d->n_layers, d->pre,
+                                     d->post, d->act, dst, B, N, w.step, w.step_bytes, s);
+    }
+  };
+  int t = 0;
+#ifndef NPDE_EMU
+  // launch-bound sizes: x_in -> A once, then replay the captured pair of steps A -> B -> A
+  if (!want_err && graph_worthwhile(cells, d->k)) {
+    StepGraph sg;
+    if (sg.begin(st)) {
+      int rc = step(bufA, bufB, sg.cs);
+      if (rc == NPDE_OK) rc = step(bufB, bufA, sg.cs);
+      if (rc != NPDE_OK) { sg.abort_capture(); return rc; }
+      TRY(step(cur, bufA, stream));
+      int times = (d->k - 1) / 2;
+      TRY(sg.finish_and_launch(times, st));
+      cur = bufA;
+      t = 1 + 2 * times;
+    }
+  }
+#endif
+  for (; t < d->k; ++t) {
     if (d->err_fd)
       TRY(npde::fd_error(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd + (size_t)t * B, B, N, w.red,
                          w.red_bytes, st));
     float *nxt = (cur == bufA) ? bufB : bufA;
-    switch (it) {
-      case NPDE_IT_JACOBI: {
-        const float *res = nullptr;
-        TRY(npde::jacobi_steps(cur, nxt, nullptr, d->bc, d->bc_kind, d->f, 1, B, N, &res, st));
-        break;
-      }
-      case NPDE_IT_CONV:
-        TRY(npde_conv_step_fwd(cur, d->bc, d->bc_kind, d->f, d->w, d->w_host, d->n_layers, d->act, nxt, B, N,
-                               w.step, w.step_bytes, stream));
-        break;
-      case NPDE_IT_MULTIGRID:
-        TRY(npde_mg_step(cur, d->bc, d->bc_kind, d->f, d->n_layers, d->pre, d->post, nxt, B, N, w.step,
-                         w.step_bytes, stream));
-        break;
-      default:
-        TRY(npde_unet_step_fwd_hw(cur, d->bc, d->bc_kind, d->f, wf, wp, wsnd, d->w_host, d->n_layers, d->pre, d->post,
-                                  d->act, nxt, B, N, w.step, w.step_bytes, stream));
-        break;
-    }
+    TRY(step(cur, nxt, stream));
     cur = nxt;
     if (d->err_l2) TRY(npde::l2_error(cur, d->gt, d->err_l2 + (size_t)t * B, B, N, w.red, w.red_bytes, st));
   }
