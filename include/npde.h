@@ -18,8 +18,10 @@
  *      H inputs/outputs   : (B, N-2, N-2)
  *      conv weights       : (L, 3, 3), cross-correlation, no bias (conv_iterator.py:12-15)
  *  - enqueue-only on `stream` (a cudaStream_t passed as void*); never
- *    synchronises, never allocates: scratch comes from the caller
- *    (npde_workspace_bytes), must be 256-byte aligned.
+ *    synchronises, never allocates device memory: scratch comes from the
+ *    caller (npde_workspace_bytes), must be 256-byte aligned.  (npde_iterate may
+ *    create and destroy a private capture stream and an executable CUDA graph
+ *    per call on launch-bound sizes; no state survives the call.)
  *  - returns NPDE_OK (0), a negative NPDE_ERR_* argument error, or a positive
  *    cudaError_t.  No global mutable state; thread-safe per stream.
  *  - arithmetic order is fixed (explicit fmaf chains) so results

@@ -120,6 +120,7 @@ struct ConvBwdWs {
   float *rs[NPDE_MAX_CONV_LAYERS + 1];
   void *wg;
   size_t wg_bytes;
+  unsigned *counters;
   void carve(Bump &b, int B, int N, int L) {
     size_t n = (size_t)B * (N - 2) * (N - 2);
     y_int = b.take<float>(n);
@@ -127,8 +128,10 @@ struct ConvBwdWs {
     g = b.take<float>(n);
     t = b.take<float>(n);
     for (int l = 0; l <= L; ++l) rs[l] = b.take<float>(n);
-    wg_bytes = npde::weight_grad_ws_bytes(B, N - 2);
+    size_t a = npde::weight_grad_ws_bytes(B, N - 2), c = npde::bwd_layer_ws_bytes(B, N - 2);
+    wg_bytes = a > c ? a : c;
     wg = b.take_bytes(wg_bytes);
+    counters = b.take<unsigned>(NPDE_MAX_CONV_LAYERS);
   }
 };
 
@@ -522,16 +525,29 @@ int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kin
   for (int l = 0; l < L; ++l) TRY(npde::conv3x3(c.rs[l], Sz, w + 9 * l, 1, 1, mask, mbs, c.rs[l + 1], Sz, B, st));
   // backward
   TRY(npde::bwd_gz(gout, c.y_int, c.rs[L], mask, mbs, act, c.gz, B, N, st));
-  TRY(d2d(c.g, c.gz, bytes, st));
-  float *g = c.g, *t = c.t;
+  {
+    cudaError_t e = cudaMemsetAsync(c.counters, 0, sizeof(unsigned) * NPDE_MAX_CONV_LAYERS, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  // layer by layer: one fused pass per layer gives both the weight gradient and the gradient of the layer input.
+  // gz itself must survive for the last kernel, so on mask geometries (in-place fg multiply) work on a copy.
+  const float *g = c.gz;
+  float *outs[2] = {c.g, c.t};
+  int o = 0;
+  if (mask) {
+    TRY(d2d(c.g, c.gz, bytes, st));
+    g = c.g;
+    o = 1;
+  }
   for (int l = L - 1; l >= 0; --l) {
-    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
-    TRY(npde::weight_grad(g, Sz, c.rs[l], Sz, 1, 1, gw + 9 * l, B, c.wg, c.wg_bytes, st, accumulate));
-    TRY(npde::conv3x3_transpose(g, Sz, w + 9 * l, 1, 1, t, Sz, B, st));
-    float *sw = g; g = t; t = sw;
+    if (mask) TRY(npde::mul_fg(const_cast<float *>(g), mask, mbs, Sz, B, st));
+    TRY(npde::bwd_layer(g, c.rs[l], w + 9 * l, outs[o], Sz, gw + 9 * l, B, c.wg, c.wg_bytes, c.counters + l, accumulate,
+                        st));
+    g = outs[o];
+    o ^= 1;
   }
   if (gx) {
-    if (mask) TRY(npde::mul_fg(g, mask, mbs, Sz, B, st));
+    if (mask) TRY(npde::mul_fg(const_cast<float *>(g), mask, mbs, Sz, B, st));
     TRY(npde::bwd_gx(c.gz, g, gx, B, N, st));
   }
   return NPDE_OK;

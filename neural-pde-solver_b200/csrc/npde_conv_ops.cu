@@ -252,6 +252,72 @@ k_weight_grad(const float *__restrict__ g, int Hg, const float *__restrict__ r, 
   }
 }
 
+// One backward layer of a same-size 3x3 stack (stride 1, pad 1) in a single pass over g:
+//   t  = conv^T(g; w)           (same tap order as k_conv3x3_transpose<1>)
+//   gw = sum_cells g (x) r      (same fp64 two-stage scheme as k_weight_grad)
+// A block covers 32 columns x BL_ROWS rows (each thread walks BL_ROWS / 8 rows), so the block reduction of the
+// nine fp64 sums is amortised over 2048 cells.
+constexpr int BL_ROWS = 64;
+__global__ void __launch_bounds__(TX * TY)
+k_bwd_layer(const float *__restrict__ g, const float *__restrict__ r, const float *__restrict__ w, float *__restrict__ t,
+            int S, float *gw9, double *part, unsigned *counter, int accumulate) {
+  const int j = blockIdx.x * TX + threadIdx.x, b = blockIdx.z;
+  const float *gb = g + (size_t)b * S * S, *rb = r + (size_t)b * S * S;
+  float *tb = t + (size_t)b * S * S;
+  float wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = __ldg(w + k);
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+  if (j < S) {
+    for (int i = blockIdx.y * BL_ROWS + threadIdx.y; i < min((int)(blockIdx.y + 1) * BL_ROWS, S); i += TY) {
+      float out = 0.0f;
+      const float gv = __ldg(gb + (size_t)i * S + j);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          int ii = i + 1 - a, jj = j + 1 - c;
+          if (ii >= 0 && jj >= 0 && ii < S && jj < S) out = __fmaf_rn(wk[a * 3 + c], __ldg(gb + (size_t)ii * S + jj), out);
+          acc[a * 3 + c] += (double)gv * (double)ldz(rb, S, i + a - 1, j + c - 1);
+        }
+      tb[(size_t)i * S + j] = out;
+    }
+  }
+  __shared__ double sh[TY][9];
+  __shared__ bool last;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    double v = npde_warp_sum(acc[k]);
+    if (lane == 0) sh[warp][k] = v;
+  }
+  __syncthreads();
+  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+  const unsigned me = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int tid = threadIdx.y * TX + threadIdx.x;
+  if (tid < 9) {
+    double v = 0.0;
+    for (int q = 0; q < TY; ++q) v += sh[q][tid];
+    part[(size_t)me * 9 + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = (atomicAdd(counter, 1u) == nblocks - 1);
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    volatile double *p = part;
+    for (int k = warp; k < 9; k += TY) {
+      double v = 0.0;
+      for (unsigned q = lane; q < nblocks; q += 32) v += p[(size_t)q * 9 + k];
+      v = npde_warp_sum(v);
+      if (lane == 0) gw9[k] = accumulate ? __fadd_rn(gw9[k], (float)v) : (float)v;
+    }
+  }
+}
+
 inline int wg_rows_per_block(int Hg) {
   int rows = 8192 / (Hg > 0 ? Hg : 1);
   return rows < WG_THREADS / 32 ? WG_THREADS / 32 : rows;
@@ -358,6 +424,23 @@ int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int 
   if (e != cudaSuccess) return (int)e;
   NPDE_LAUNCH(k_weight_grad, dim3(B * bpi), dim3(WG_THREADS), 0, st, g, Hg, r, Hr, stride, pad, gw9, part,
               counter, rpb, bpi, accumulate ? 1 : 0);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+static inline dim3 bwd_layer_grid(int S, int B) { return dim3((S + TX - 1) / TX, (S + BL_ROWS - 1) / BL_ROWS, B); }
+
+size_t bwd_layer_ws_bytes(int B, int S) {
+  dim3 gd = bwd_layer_grid(S, B);
+  return npde_align_up(sizeof(double) * 9 * (size_t)gd.x * gd.y * gd.z, 256) + 256;
+}
+
+// counter: a zeroed unsigned owned by this launch (the caller clears all of a step's counters with one memset)
+int bwd_layer(const float *g, const float *r, const float *w9, float *t, int S, float *gw9, int B, void *ws,
+              size_t ws_bytes, unsigned *counter, bool accumulate, cudaStream_t st) {
+  if (!ws || ((uintptr_t)ws & 255) || ws_bytes < bwd_layer_ws_bytes(B, S) || !counter) return NPDE_ERR_WORKSPACE;
+  NPDE_LAUNCH(k_bwd_layer, bwd_layer_grid(S, B), dim3(TX, TY), 0, st, g, r, w9, t, S, gw9,
+              reinterpret_cast<double *>(ws), counter, accumulate ? 1 : 0);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

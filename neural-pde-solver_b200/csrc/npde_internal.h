@@ -91,6 +91,10 @@ int bwd_gz(const float *gout, const float *y_int, const float *rL, const float *
 int weight_grad(const float *g, int Hg, const float *r, int Hr, int stride, int pad, float *gw9, int B,
                 void *ws, size_t ws_bytes, cudaStream_t st, bool accumulate = false);
 size_t weight_grad_ws_bytes(int B, int Hg);
+// fused backward layer of a same-size stack: t = conv^T(g; w9), gw9 (+)= g (x) r; *counter must be 0
+size_t bwd_layer_ws_bytes(int B, int S);
+int bwd_layer(const float *g, const float *r, const float *w9, float *t, int S, float *gw9, int B, void *ws,
+              size_t ws_bytes, unsigned *counter, bool accumulate, cudaStream_t st);
 int bwd_gx(const float *gz, const float *g0, float *gx, int B, int N, cudaStream_t st);
 
 // npde_stream.cu -- fused register-streaming kernels (Conv L-layer Phi_H, Jacobi T-step)

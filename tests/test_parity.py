@@ -624,3 +624,28 @@ def test_error_behaviour(be):
     with pytest.raises(be.npde._lib.NpdeError):  # even multigrid level size
         be.npde.MultigridIterator(3, 1, 1)(torch.zeros(2, 19, 19, device=be.device),
                                            torch.zeros(2, 4, device=be.device), None)
+
+
+def test_c_abi_argument_errors(be):
+    """The C entry points reject bad arguments with the NPDE_ERR_* codes of include/npde.h instead of launching."""
+    import ctypes
+    L = be.npde._lib
+    lib = L.lib()
+    x = torch.zeros(2, 17, 17, device=be.device)
+    y = torch.zeros_like(x)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.npde_cg_step(p(x), 3, p(x), 2, 17, None, 0, None) == -7          # in place: NPDE_ERR_ARG
+    assert lib.npde_cg_step(p(x), 3, p(y), 2, 17, None, 0, None) == -6          # no workspace: NPDE_ERR_WORKSPACE
+    assert lib.npde_cg_step(None, 3, p(y), 2, 17, None, 0, None) == -1          # NPDE_ERR_NULL
+    assert lib.npde_cg_step(p(x), 3, p(y), 0, 17, None, 0, None) == -2          # NPDE_ERR_SIZE
+    bc = torch.zeros(2, 4, device=be.device)
+    w = torch.zeros(3, 3, 3, device=be.device)
+    assert lib.npde_conv_iterate_tape(p(x), p(bc), 0, None, p(w), None, 3, 1, 0, p(y), p(y), 2, 17, None, 0, None) == -7
+    assert lib.npde_conv_iterate_tape(p(x), p(bc), 0, None, p(w), None, 3, 1, 2, None, p(y), 2, 17, None, 0, None) == -1
+    assert lib.npde_conv_iterate_bwd(p(x), p(bc), 0, None, p(w), 3, 7, 2, p(y), p(w), None, 2, 17, None, 0, None) == -4
+    assert lib.npde_conv_iterate_bwd(p(x), p(bc), 0, None, p(w), 9, 1, 2, p(y), p(w), None, 2, 17, None, 0, None) == -5
+    assert lib.npde_conv_iterate_bwd(p(x), p(bc), 5, None, p(w), 3, 1, 2, p(y), p(w), None, 2, 17, None, 0, None) == -3
+    assert lib.npde_strerror(-6).decode().startswith("workspace")
+    assert lib.npde_workspace_bytes(L.WS_CG, 2, 17, 0, 0, 0, 0, 0) > 4 * 2 * 17 * 17 * 4
+    assert lib.npde_workspace_bytes(L.WS_CONV_BPTT, 2, 17, 0, 3, 0, 0, 0) > \
+        lib.npde_workspace_bytes(L.WS_CONV_BWD, 2, 17, 0, 3, 0, 0, 0)
