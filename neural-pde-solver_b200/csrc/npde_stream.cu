@@ -1080,11 +1080,18 @@ struct JacobiStreamParams {
   Split split;
 };
 
-// MASK (T == 1 only): G = y*(1-m)+v at every cell, Psi zero-padded on the whole grid (heat_utils.py:51-53,96-106)
+// MASK: G = y*(1-m)+v at every cell, Psi zero-padded on the whole grid (heat_utils.py:51-53,96-106).
+// With T > 1 stage s needs the bc rows of grid row it - s: every arriving mask / value row is turned into
+// "keep bits" (m == 0 and the cell exists) plus values and parked in a lane-private shared-memory ring of
+// JAC_RING rows (32 bytes per lane and row), from which the T stages read their row; rows and columns outside
+// the grid come out as exact zeros, which is the zero padding the next stage expects.
+constexpr int JAC_RING = 8;  // rows, power of two, > largest T on a mask geometry
+constexpr size_t jacobi_mask_smem(int T) { return T > 1 ? (size_t)JAC_RING * 2 * 32 * 16 : 0; }
 template <int T, bool MASK = false>
 __global__ void __launch_bounds__(npde::STREAM_THREADS)
 k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
-  static_assert(!MASK || T == 1, "mask geometries run one Jacobi step per launch");
+  static_assert(!MASK || T < JAC_RING, "mask ring too short");
+  constexpr bool MRING = MASK && T > 1;
   constexpr int RC = (T + 3) & ~3;  // column halo: whole lanes
   StripItem item;
   if (!decode_item(p.B, p.N, p.split, item)) return;
@@ -1130,9 +1137,25 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   f2 pf[2], pff[2], pm[2], pv[2];
   pf[0] = pf[1] = pff[0] = pff[1] = pv[0] = pv[1] = zero2();
   pm[0] = pm[1] = bc2(1.0f);
+  NPDE_DYN_SMEM(uint4, mring);  // MRING: slot (row & 7): [keep bits of 32 lanes][values of 32 lanes]
+  if (MRING) {
+#pragma unroll
+    for (int r = 0; r < JAC_RING; ++r) {
+      mring[r * 64 + lane] = make_uint4(0u, 0u, 0u, 0u);
+      mring[r * 64 + 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  // mask geometries: the ring need not be Dirichlet, so columns beyond the grid (pad columns of the permuted
+  // layout, whatever they hold) must read as the zero padding of the stencil
+  const unsigned img0 = (c.in_img & 1u) ? 0xffffffffu : 0u, img1 = (c.in_img & 2u) ? 0xffffffffu : 0u;
+  const unsigned img2 = (c.in_img & 4u) ? 0xffffffffu : 0u, img3 = (c.in_img & 8u) ? 0xffffffffu : 0u;
   load_row(xin + (size_t)it_first * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
+  if (MASK) {
+    pf[0] = and2(pf[0], img0, img2);
+    pf[1] = and2(pf[1], img1, img3);
+  }
   if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
-  if (MASK && it_first >= 1) {  // mask / value rows of the first output row it_first - 1
+  if (MASK && !MRING && it_first >= 1) {  // mask / value rows of the first output row it_first - 1
     load_row(min_ + (size_t)(it_first - 1) * p.bm_pitch, p.bm_perm != 0, ld_ok, c.in_img, pm[0], pm[1]);
     load_row(vin + (size_t)(it_first - 1) * p.bv_pitch, p.bv_perm != 0, ld_ok, c.in_img, pv[0], pv[1]);
   }
@@ -1154,11 +1177,24 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
           o0 = sub2(o0, pff[0]);
           o1 = sub2(o1, pff[1]);
         }
-        if (MASK) {  // m is 0 or 1: x*(1-m) is a select, then + v
-          o0 = and2(o0, lo(pm[0]) == 0.0f ? 0xffffffffu : 0u, hi(pm[0]) == 0.0f ? 0xffffffffu : 0u);
-          o1 = and2(o1, lo(pm[1]) == 0.0f ? 0xffffffffu : 0u, hi(pm[1]) == 0.0f ? 0xffffffffu : 0u);
-          o0 = mk2(__fadd_rn(lo(o0), lo(pv[0])), __fadd_rn(hi(o0), hi(pv[0])));
-          o1 = mk2(__fadd_rn(lo(o1), lo(pv[1])), __fadd_rn(hi(o1), hi(pv[1])));
+        if (MRING) {  // keep bits / values of grid row `row`, parked s steps ago
+          if (row >= 0 && row <= N - 1) {
+            const uint4 k = mring[(row & (JAC_RING - 1)) * 64 + lane];
+            const uint4 v = mring[(row & (JAC_RING - 1)) * 64 + 32 + lane];
+            o0 = and2(o0, k.x, k.z);
+            o1 = and2(o1, k.y, k.w);
+            o0 = mk2(__fadd_rn(lo(o0), __uint_as_float(v.x)), __fadd_rn(hi(o0), __uint_as_float(v.z)));
+            o1 = mk2(__fadd_rn(lo(o1), __uint_as_float(v.y)), __fadd_rn(hi(o1), __uint_as_float(v.w)));
+          } else {
+            o0 = o1 = zero2();
+          }
+        } else if (MASK) {  // m is 0 or 1: x*(1-m) is a select, then + v; columns beyond the grid stay exact zeros
+          o0 = and2(o0, ((c.in_img & 1u) && lo(pm[0]) == 0.0f) ? 0xffffffffu : 0u,
+                    ((c.in_img & 4u) && hi(pm[0]) == 0.0f) ? 0xffffffffu : 0u);
+          o1 = and2(o1, ((c.in_img & 2u) && lo(pm[1]) == 0.0f) ? 0xffffffffu : 0u,
+                    ((c.in_img & 8u) && hi(pm[1]) == 0.0f) ? 0xffffffffu : 0u);
+          o0 = mk2(__fadd_rn(lo(o0), (c.in_img & 1u) ? lo(pv[0]) : 0.0f), __fadd_rn(hi(o0), (c.in_img & 4u) ? hi(pv[0]) : 0.0f));
+          o1 = mk2(__fadd_rn(lo(o1), (c.in_img & 2u) ? lo(pv[1]) : 0.0f), __fadd_rn(hi(o1), (c.in_img & 8u) ? hi(pv[1]) : 0.0f));
         } else {
           apply_G_square(o0, o1, row, N, c, top, bottom, left, right);
         }
@@ -1178,6 +1214,10 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
       const int nx = it + 1;
       if (nx <= x_last) {
         load_row(xin + (size_t)nx * p.in_pitch, in_perm, ld_ok, c.in_img, pf[0], pf[1]);
+        if (MASK) {
+          pf[0] = and2(pf[0], img0, img2);
+          pf[1] = and2(pf[1], img1, img3);
+        }
       } else {
         pf[0] = pf[1] = zero2();
       }
@@ -1186,9 +1226,22 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
         if (L2_AHEAD > 0 && it + L2_AHEAD <= x_last)
           prefetch_row(fin + (size_t)(it + L2_AHEAD) * p.f_pitch, lane, c.in_img);
       }
-      if (MASK && it <= N - 1 && it < i1) {
+      if (MASK && it <= N - 1 && it < (MRING ? it_last : i1)) {
         load_row(min_ + (size_t)it * p.bm_pitch, p.bm_perm != 0, ld_ok, c.in_img, pm[0], pm[1]);
         load_row(vin + (size_t)it * p.bv_pitch, p.bv_perm != 0, ld_ok, c.in_img, pv[0], pv[1]);
+        if (MRING) {  // row `it` is first used by stage 1 of the next step
+          uint4 k, v;
+          k.x = ((c.in_img & 1u) && lo(pm[0]) == 0.0f) ? 0xffffffffu : 0u;
+          k.y = ((c.in_img & 2u) && lo(pm[1]) == 0.0f) ? 0xffffffffu : 0u;
+          k.z = ((c.in_img & 4u) && hi(pm[0]) == 0.0f) ? 0xffffffffu : 0u;
+          k.w = ((c.in_img & 8u) && hi(pm[1]) == 0.0f) ? 0xffffffffu : 0u;
+          v.x = (c.in_img & 1u) ? __float_as_uint(lo(pv[0])) : 0u;
+          v.y = (c.in_img & 2u) ? __float_as_uint(lo(pv[1])) : 0u;
+          v.z = (c.in_img & 4u) ? __float_as_uint(hi(pv[0])) : 0u;
+          v.w = (c.in_img & 8u) ? __float_as_uint(hi(pv[1])) : 0u;
+          mring[(it & (JAC_RING - 1)) * 64 + lane] = k;
+          mring[(it & (JAC_RING - 1)) * 64 + 32 + lane] = v;
+        }
         if (L2_AHEAD > 0 && it + L2_AHEAD < i1) {
           prefetch_row(min_ + (size_t)(it + L2_AHEAD) * p.bm_pitch, lane, c.in_img);
           prefetch_row(vin + (size_t)(it + L2_AHEAD) * p.bv_pitch, lane, c.in_img);
@@ -1384,10 +1437,11 @@ template <int T, bool MASK = false>
 int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 3) & ~3;
   static int cache = 0;
-  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>, 0, &cache);
+  const size_t smem = MASK ? jacobi_mask_smem(T) : 0;
+  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>, smem, &cache);
   p.split = make_split(p.B, p.N, RC, T, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
-  NPDE_LAUNCH((k_jacobi_stream<T, MASK>), grid, block, 0, st, p);
+  NPDE_LAUNCH((k_jacobi_stream<T, MASK>), grid, block, smem, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
@@ -1537,7 +1591,7 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
     return NPDE_ERR_BC;
   if (!perm_ok(p.bv, p.bv_pitch, p.bv_bstride, p.bv_perm, N) || !perm_ok(p.bm, p.bm_pitch, p.bm_bstride, p.bm_perm, N))
     return NPDE_ERR_ARG;
-  if (p.bm && depth != 1) return NPDE_ERR_ARG;
+  if (p.bm && depth > 4) return NPDE_ERR_ARG;
   p.in = in.p; p.in_pitch = in.pitch; p.in_bstride = in.bstride;
   p.out = out.p; p.out_pitch = out.pitch; p.out_bstride = out.bstride;
   p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride;
@@ -1550,8 +1604,8 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
   switch (depth) {
     case 1: return p.bm ? launch_jacobi<1, true>(p, st) : launch_jacobi<1>(p, st);
 #ifndef NPDE_DEV_ONLY_CONV3
-    case 2: return launch_jacobi<2>(p, st);
-    case 4: return launch_jacobi<4>(p, st);
+    case 2: return p.bm ? launch_jacobi<2, true>(p, st) : launch_jacobi<2>(p, st);
+    case 4: return p.bm ? launch_jacobi<4, true>(p, st) : launch_jacobi<4>(p, st);
     case 8: return launch_jacobi<8>(p, st);
 #endif
     default: return NPDE_ERR_ARG;

@@ -40,6 +40,7 @@ struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;

@@ -649,3 +649,38 @@ def test_c_abi_argument_errors(be):
     assert lib.npde_workspace_bytes(L.WS_CG, 2, 17, 0, 0, 0, 0, 0) > 4 * 2 * 17 * 17 * 4
     assert lib.npde_workspace_bytes(L.WS_CONV_BPTT, 2, 17, 0, 3, 0, 0, 0) > \
         lib.npde_workspace_bytes(L.WS_CONV_BWD, 2, 17, 0, 3, 0, 0, 0)
+
+
+@pytest.mark.parametrize("B,N,k", [(3, 65, 9), (2, 129, 12), (5, 33, 7)])
+def test_mask_jacobi_temporal_blocking_open_border(be, oracle, B, N, k):
+    """Temporally blocked Jacobi on a mask geometry whose outer ring is NOT Dirichlet (m = 0 there): the
+    zero padding beyond the grid then matters at every stage.  Depths 1, 2, 4 and the default vs the oracle."""
+    rng = np.random.RandomState(N + k)
+    m = (rng.rand(B, N, N) < 0.08).astype(np.float32)
+    v = rng.rand(B, N, N).astype(np.float32) * m
+    bc = np.stack([v, m], 1)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    ref, _, ref_fd = oracle.iterate("jacobi", x, bc, None, None, "none", k, want_fd=True)
+    jac = be.npde.JacobiIterator()
+    jac.is_bc_mask = True
+    xd, bcd = be.t(x), be.t(bc)
+    for depth in (0, 1, 2, 4):
+        y, _, _ = jac.iterate(xd, bcd, None, k, temporal_depth=depth)
+        assert_bitwise(be.n(y), ref, "mask Jacobi, %d steps, depth %d" % (k, depth))
+    y, _, fd = jac.iterate(xd, bcd, None, k, want_fd=True)
+    assert_bitwise(be.n(y), ref, "with residual rows")
+    assert_bitwise(be.n(fd), ref_fd, "residual rows")
+    # the fused Conv kernel and the V-cycle on the same open-border geometry
+    w = ((rng.rand(3, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", 3)
+    it.is_bc_mask = True
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    yc, _, _ = it.iterate(xd, bcd, None, 5)
+    assert_bitwise(be.n(yc), oracle.iterate("conv", x, bc, None, w, "clamp", 5)[0], "5 Conv3 steps, open border")
+    if N >= 65:
+        mg = be.npde.MultigridIterator(3, 3, 5)
+        mg.is_bc_mask = True
+        assert_bitwise(be.n(mg(xd, bcd, None)), oracle.multigrid_step(x, bc, None, 3, 3, 5), "V-cycle (3,3,5), open border")
