@@ -3,9 +3,10 @@
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/dp_train_check.py
 
-Every rank trains on its slice of a 64 x 257^2 batch with HeatModel(opt, world=True) (weight-gradient
-all-reduce over NVLink); rank 0 also trains a single-process model on the full batch.  Checks: replicas stay
-bit-identical, and equal the full-batch run to 1e-6; prints the time per training step."""
+Every rank trains on its slice of a (64 x world) x 257^2 batch -- BASELINE config 4 at world = 8: batch 512,
+K = 20 -- with HeatModel(opt, world=True) (weight-gradient all-reduce over NVLink); rank 0 also trains a
+single-process model on the full batch.  Checks: replicas stay bit-identical, and equal the full-batch run to
+1e-6; prints the time per training step.  NPDE_FULL_BPTT=1: gradient through all unrolled iterations."""
 import argparse
 import importlib
 import os
@@ -29,7 +30,8 @@ def main():
     opt = argparse.Namespace(iterator="conv", activation="clamp", conv_n_layers=3, mg_n_layers=3, mg_pre_smoothing=2,
                              mg_post_smoothing=2, cg_n_iters=4, geometry="square", is_train=True, optimizer="adam",
                              lr_init=1e-3, max_iter_steps=20, max_iter_steps_from_gt=20, lambda_gt=0.0)
-    B, N = 64, 257
+    full_bptt = os.environ.get("NPDE_FULL_BPTT", "0") == "1"
+    B, N = 64 * world, 257
     rng = np.random.RandomState(0)
     bc = rng.rand(B, 4).astype(np.float32)
     x = rng.rand(B, N, N).astype(np.float32)
@@ -37,7 +39,7 @@ def main():
     w0 = ((rng.rand(3, 1, 1, 3, 3) - 0.5) * 0.2).astype(np.float32)
 
     def make(world_flag):
-        m = npde.HeatModel(opt, world=world_flag)
+        m = npde.HeatModel(opt, world=world_flag, full_bptt=full_bptt)
         m.iterator.to(dev)
         with torch.no_grad():
             for l, w in zip(m.iterator.layers, w0):
@@ -68,8 +70,9 @@ def main():
         for _ in range(steps + 1):
             ref.train(torch.from_numpy(x).to(dev), torch.from_numpy(gt).to(dev), torch.from_numpy(bc).to(dev), None)
         wr = torch.stack([l.weight.detach().reshape(9) for l in ref.iterator.layers])
-        print("world %d: replicas identical: %s; max |w_dp - w_single| = %.3g; %.2f ms per DP train step; loss %.6g"
-              % (world, same, float((w - wr).abs().max()), dt * 1e3, out["loss"]["loss_x"]))
+        print("world %d, global batch %d, full_bptt %s: replicas identical: %s; max |w_dp - w_single| = %.3g; "
+              "%.2f ms per DP train step; loss %.6g"
+              % (world, B, full_bptt, same, float((w - wr).abs().max()), dt * 1e3, out["loss"]["loss_x"]))
         assert same and float((w - wr).abs().max()) < 1e-6
     dist.destroy_process_group()
 
