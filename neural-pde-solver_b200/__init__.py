@@ -12,7 +12,7 @@ from .get_iterator import get_iterator
 from .iterators import (ConjugateGradient, ConvIterator, Iterator, JacobiIterator, MultigridIterator,
                         MultigridResidualIterator, UNetIterator)
 from .heat_model import HeatModel
-from . import data, generation, geometries, metrics, runtime
+from . import data, evaluation, generation, geometries, metrics, runtime
 
 __all__ = ["get_iterator", "Iterator", "JacobiIterator", "ConvIterator", "MultigridIterator", "UNetIterator", "ConjugateGradient", "MultigridResidualIterator",
-           "HeatModel", "utils", "functional", "data", "generation", "geometries", "metrics", "runtime"]
+           "HeatModel", "utils", "functional", "data", "evaluation", "generation", "geometries", "metrics", "runtime"]

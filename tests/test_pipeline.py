@@ -288,3 +288,49 @@ def test_get_iterator_cg_contract(be):
         assert it.name() == name and cmp_.name() == cmp_name
         assert float(r) == float(ratio) and bool(tr) == bool(is_train)
         assert bool(it.is_bc_mask) == bool(is_mask) and float(it.n_operations) == float(n_ops)
+
+
+# ---------------------------------------------------------------------------- test.py evaluation driver --
+def test_evaluation_driver_vs_oracle(be, oracle, tmp_path, capsys):
+    """evaluation.test (test.py:96-123) on a generated set: iterations-to-1 % of a Conv3 model and of Jacobi per
+    problem, averaged by Metrics, equal the same quantities computed with the oracle; the eigenvalue check runs
+    through the batched probes and finds a contraction."""
+    g = load_golden("pipeline_square17_cold")
+    gen, data = be.npde.generation, be.npde.data
+    gopt = _gen_opt(str(tmp_path), g, be.device)
+    np.random.seed(666)
+    gen.generate_square(gopt)
+    opt, model = _conv_model(be)
+    for k, v in dict(dset_path=gopt.save_dir, max_temp=100, data_limit=0, poisson=0, batch_size=4, n_workers=0,
+                     log_every=10, n_evaluation_steps=120).items():
+        setattr(opt, k, v)
+    loader = data.get_data_loader(opt)           # is_train False: the test split (run 1), no shuffling
+    results, spectra = be.npde.evaluation.test(opt, model, loader)
+    capsys.readouterr()
+
+    w = np.stack([l.weight.detach().cpu().numpy()[0, 0] for l in model.iterator.layers])
+    dset = data.HeatDataset(gopt.save_dir, False, 100, 0, 0)
+    jac_steps, model_steps = [], []
+    for idx in range(len(dset)):
+        s = dset[idx]
+        x, bc, gt = (s[k].numpy()[None].copy() for k in ("x", "bc", "final"))
+        x[:, 1:-1, 1:-1] = torch.mean(torch.from_numpy(bc), dim=1).view(1, 1, 1).numpy()
+        start = oracle.l2_error(x, gt)           # evaluate() normalises by the error of the initialised field
+
+        def first(stepper):
+            y = x
+            for k in range(1, opt.n_evaluation_steps + 1):
+                y = stepper(y)
+                if np.float32(oracle.l2_error(y, gt)[0]) / np.float32(start[0]) < 0.01:
+                    return k
+            return None
+        jac_steps.append(first(lambda y: oracle.fd_step(y, bc, None)))
+        model_steps.append(first(lambda y: oracle.conv_step(y, bc, None, w, "clamp")))
+    ok = [i for i in range(len(dset)) if jac_steps[i] is not None and model_steps[i] is not None]
+    assert ok, "no problem reaches 1 % within the evaluation steps"
+    assert results["Jacobi"] == pytest.approx(np.mean([jac_steps[i] for i in ok]))
+    assert results["model"] == pytest.approx(np.mean([model_steps[i] for i in ok]))
+    assert results["ratio"] == pytest.approx(np.mean([model_steps[i] / jac_steps[i] for i in ok]))
+    w_model, w_h, w_fd = spectra
+    assert w_model[-1] == pytest.approx(1.0, abs=1e-5) and w_model[-2] < 1.0 and w_fd[-2] < 1.0
+    assert opt.initialization == "avg"
