@@ -422,8 +422,10 @@ int level_sizes_ok(int N, int L) {
 
 // npde_iterate: two ping-pong fields (padded pitch: 16-byte aligned rows), the
 // reduction scratch and the largest per-step workspace any iterator may need.
+constexpr int ITER_SEG = 32;  // fused launches per captured segment of the Jacobi / Conv loop (even)
 struct IterWs {
   float *buf[2];
+  float *stage_l2, *stage_fd;  // (ITER_SEG, B) error rows of one replayed segment
   float *fpad;  // the source in the padded layout (Jacobi / Conv fast path)
   float *vpad, *mpad;  // mask geometry: the two bc planes in the padded layout (Conv fast path)
   int pitch;
@@ -444,6 +446,8 @@ struct IterWs {
     mpad = mask_fast ? b.take<float>(cells) : nullptr;
     red_bytes = npde::reduce_ws_bytes(B, N);
     red = b.take_bytes(red_bytes);
+    stage_l2 = b.take<float>((size_t)ITER_SEG * B);
+    stage_fd = b.take<float>((size_t)ITER_SEG * B);
     step_bytes = 0;
     if (iterator == NPDE_IT_CONV) step_bytes = npde_workspace_bytes(NPDE_WS_CONV_FWD, B, N, bc_kind, L, 0, 0, 0);
     if (iterator == NPDE_IT_MULTIGRID) step_bytes = npde_workspace_bytes(NPDE_WS_MG, B, N, bc_kind, L, pre, post, 0);
@@ -480,17 +484,21 @@ struct StepGraph {
     if (capturing) { cudaStreamEndCapture(cs, &graph); capturing = false; cudaGetLastError(); }
     return NPDE_OK;
   }
-  int finish_and_launch(int times, cudaStream_t caller) {
+  int finish() {
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
     capturing = false;
     if (e != cudaSuccess) return (int)e;
     e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) return (int)e;
-    for (int i = 0; i < times; ++i) {
-      e = cudaGraphLaunch(exec, caller);
-      if (e != cudaSuccess) return (int)e;
-    }
-    return NPDE_OK;
+    return e == cudaSuccess ? NPDE_OK : (int)e;
+  }
+  int launch_once(cudaStream_t caller) {
+    cudaError_t e = cudaGraphLaunch(exec, caller);
+    return e == cudaSuccess ? NPDE_OK : (int)e;
+  }
+  int finish_and_launch(int times, cudaStream_t caller) {
+    int rc = finish();
+    for (int i = 0; i < times && rc == NPDE_OK; ++i) rc = launch_once(caller);
+    return rc;
   }
   ~StepGraph() {
     abort_capture();
@@ -1070,20 +1078,43 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
 #ifndef NPDE_EMU
     // launch-bound sizes: x_in -> pad[0] once, then replay a captured segment of SEG launches pad[0] -> pad[1] -> ...
     // -> pad[0]; the plain loop below finishes the remainder and writes the caller's tensor
-    constexpr int SEG = 32;
-    if (!want_err && graph_worthwhile(cells, d->k) && left > full_adv * (SEG + 1)) {
+    constexpr int SEG = ITER_SEG;
+    if (graph_worthwhile(cells, d->k) && left > full_adv * (SEG + 1)) {
       StepGraph sg;
       if (sg.begin(st)) {
+        // error rows of a replayed segment land in staging rows (fixed addresses) and are copied to their place
+        // in the caller's (k, B) / (k+1, B) arrays after every replay
+        auto rows = [&](const npde::FieldView &v, float *l2_row, float *fd_row, cudaStream_t s) -> int {
+          if (d->err_l2) TRY(npde::l2_error_view(v, d->gt, l2_row, B, N, w.red, w.red_bytes, s, true));
+          if (d->err_fd)
+            TRY(npde::fd_error_view(v, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, fd_row, B, N, w.red, w.red_bytes, s, true));
+          return NPDE_OK;
+        };
+        if (want_err) TRY(npde::reduce_ws_clear(w.red, w.red_bytes, B, N, st));  // once; reductions keep them clean
         int rc = NPDE_OK;
-        for (int i = 0; i < SEG && rc == NPDE_OK; ++i) rc = launch(npde::as_const(pad[i & 1]), pad[(i + 1) & 1], full_adv, sg.cs);
+        for (int i = 0; i < SEG && rc == NPDE_OK; ++i) {
+          rc = launch(npde::as_const(pad[i & 1]), pad[(i + 1) & 1], full_adv, sg.cs);
+          if (rc == NPDE_OK && want_err)
+            rc = rows(npde::as_const(pad[(i + 1) & 1]), w.stage_l2 + (size_t)i * B, w.stage_fd + (size_t)i * B, sg.cs);
+        }
         if (rc != NPDE_OK) { sg.abort_capture(); return rc; }
         TRY(launch(cur, pad[0], full_adv, st));
         left -= full_adv;
         done += full_adv;
-        int times = (left - 1) / (full_adv * SEG);
-        TRY(sg.finish_and_launch(times, st));
-        left -= times * full_adv * SEG;
-        done += times * full_adv * SEG;
+        if (want_err)
+          TRY(rows(npde::as_const(pad[0]), d->err_l2 ? d->err_l2 + (size_t)(done - 1) * B : nullptr,
+                   d->err_fd ? d->err_fd + (size_t)done * B : nullptr, st));
+        const int times = (left - 1) / (full_adv * SEG);
+        TRY(sg.finish());
+        for (int r = 0; r < times; ++r) {
+          TRY(sg.launch_once(st));
+          if (d->err_l2)
+            TRY(d2d(d->err_l2 + (size_t)done * B, w.stage_l2, sizeof(float) * (size_t)SEG * B, st));
+          if (d->err_fd)
+            TRY(d2d(d->err_fd + (size_t)(done + 1) * B, w.stage_fd, sizeof(float) * (size_t)SEG * B, st));
+          left -= full_adv * SEG;
+          done += full_adv * SEG;
+        }
         cur = npde::as_const(pad[0]);
         flip = 1;
       }

@@ -105,6 +105,7 @@ __device__ __forceinline__ void block_reduce_finish(double v, ReduceWs ws, int c
     for (int c = 1; c < chunks; ++c) t = IS_MAX ? fmax(t, p[c]) : t + p[c];
     if (IS_MAX) err[b] = (float)t;
     else err[b] = take_sqrt ? sqrtf((float)(t / denom)) : (float)(t / denom);
+    ws.counter[b] = 0u;  // leave the counters clean: back-to-back reductions on one workspace need no memset
   }
 }
 
@@ -148,22 +149,20 @@ k_fd_error(const float *__restrict__ x, int xp, long xbs, int xperm, BcView bc, 
 
 __global__ void __launch_bounds__(RED_THREADS)
 k_l2_error(const float *__restrict__ x, int xp, long xbs, int xperm, const float *__restrict__ gt, float *err,
-           ReduceWs ws, int N, int cells_per_chunk) {
+           ReduceWs ws, int N, int rows_per_chunk) {
   int b = blockIdx.y, chunks = gridDim.x;
   size_t n = (size_t)N * N;
-  size_t c0 = (size_t)blockIdx.x * cells_per_chunk;
-  size_t c1 = c0 + cells_per_chunk < n ? c0 + cells_per_chunk : n;
+  const int r0 = blockIdx.x * rows_per_chunk, r1 = min(r0 + rows_per_chunk, N);
   const float *xb = x + (size_t)b * xbs, *gb = gt + (size_t)b * n;
-  const bool plain = xp == N && !xperm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc = 0.0;
-  for (size_t o = c0 + threadIdx.x; o < c1; o += RED_THREADS) {
-    size_t xo = o;  // same cell -> thread mapping (and hence summation order) for every layout
-    if (!plain) {
-      const int i = (int)(o / N), j = (int)(o - (size_t)i * N);
-      xo = (size_t)i * xp + view_col(j, xperm);
+  // a warp per row, lanes along it: the same cell -> thread mapping (and hence summation order) for every layout
+  for (int i = r0 + warp; i < r1; i += RED_THREADS / 32) {
+    const float *xr = xb + (size_t)i * xp, *gr = gb + (size_t)i * N;
+    for (int j = lane; j < N; j += 32) {
+      float d = __fsub_rn(__ldg(xr + view_col(j, xperm)), __ldg(gr + j));
+      acc += (double)__fmul_rn(d, d);
     }
-    float d = __fsub_rn(__ldg(xb + xo), __ldg(gb + o));
-    acc += (double)__fmul_rn(d, d);
   }
   block_reduce_finish<false>(acc, ws, chunks, err, b, (double)n, true);
 }
@@ -261,14 +260,21 @@ size_t reduce_ws_bytes(int B, int N) {
          npde_align_up(sizeof(unsigned) * (size_t)B, 256);
 }
 
-static int reduce_ws_carve(void *ws, size_t ws_bytes, int B, int N, ReduceWs *out, cudaStream_t st) {
+static int reduce_ws_carve(void *ws, size_t ws_bytes, int B, int N, ReduceWs *out, cudaStream_t st,
+                           bool counters_clean = false) {
   if (!ws || ((uintptr_t)ws & 255)) return NPDE_ERR_WORKSPACE;
   if (ws_bytes < reduce_ws_bytes(B, N)) return NPDE_ERR_WORKSPACE;
   size_t part_bytes = npde_align_up(sizeof(double) * (size_t)B * reduce_chunks(N), 256);
   out->part = reinterpret_cast<double *>(ws);
   out->counter = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(ws) + part_bytes);
+  if (counters_clean) return NPDE_OK;
   cudaError_t e = cudaMemsetAsync(out->counter, 0, sizeof(unsigned) * (size_t)B, st);
   return e == cudaSuccess ? NPDE_OK : (int)e;
+}
+
+int reduce_ws_clear(void *ws, size_t ws_bytes, int B, int N, cudaStream_t st) {
+  ReduceWs r;
+  return reduce_ws_carve(ws, ws_bytes, B, N, &r, st, false);
 }
 
 int set_boundary(float *x, const float *bc, int bc_kind, int B, int N, cudaStream_t st) {
@@ -303,11 +309,11 @@ int fd_error(const float *x, const float *bc, int bc_kind, const float *f, int a
 }
 
 int fd_error_view(const FieldView &xv, const float *bc, int bc_kind, const float *f, int aggregate, float *err,
-                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st) {
+                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st, bool counters_clean) {
   if (bc_kind == NPDE_BC_SQUARE && aggregate == NPDE_AGG_MAX && N >= 3)  // the streaming kernel (npde_stream.cu)
     return fd_error_max_stream(xv, ref_view(f, N), err, B, N, st);
   ReduceWs r;
-  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
+  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st, counters_clean);
   if (rc) return rc;
   BcView v{bc, bc_kind};
   int chunks = reduce_chunks(N);
@@ -331,16 +337,15 @@ int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws
 }
 
 int l2_error_view(const FieldView &xv, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool counters_clean) {
   ReduceWs r;
-  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st);
+  int rc = reduce_ws_carve(ws, ws_bytes, B, N, &r, st, counters_clean);
   if (rc) return rc;
   int chunks = reduce_chunks(N);
-  long n = (long)N * N;
-  int cpc = (int)((n + chunks - 1) / chunks);
-  chunks = (int)((n + cpc - 1) / cpc);
+  int rpc = (N + chunks - 1) / chunks;
+  chunks = (N + rpc - 1) / rpc;
   NPDE_LAUNCH(k_l2_error, dim3(chunks, B), dim3(RED_THREADS), 0, st, xv.p, xv.pitch, xv.bstride, xv.perm, gt, err, r,
-              N, cpc);
+              N, rpc);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

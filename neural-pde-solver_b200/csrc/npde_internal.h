@@ -50,9 +50,11 @@ int l2_error(const float *x, const float *gt, float *err, int B, int N, void *ws
              cudaStream_t st);
 // same on any field view (the internal buffers of the k-step loop); bc, f and gt stay in the reference layout
 int fd_error_view(const FieldView &x, const float *bc, int bc_kind, const float *f, int aggregate, float *err,
-                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st);
+                  int B, int N, void *ws, size_t ws_bytes, cudaStream_t st, bool counters_clean = false);
+// counters_clean: the reduction counters of `ws` are known to be zero (every reduction leaves them so)
+int reduce_ws_clear(void *ws, size_t ws_bytes, int B, int N, cudaStream_t st);
 int l2_error_view(const FieldView &x, const float *gt, float *err, int B, int N, void *ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  cudaStream_t st, bool counters_clean = false);
 int subsample(const float *x, float *y, int B, int N, float scale, cudaStream_t st);
 // same, input images `x_bstride` floats apart (the mask plane of a (B,2,N,N) bc tensor)
 int subsample_strided(const float *x, size_t x_bstride, float *y, int B, int N, float scale, cudaStream_t st);
