@@ -61,6 +61,7 @@ extern "C" {
 
 #define NPDE_MAX_CONV_LAYERS 8
 #define NPDE_MAX_LEVELS 12
+#define NPDE_SMALL_MAX_N 65 /* npde_iterate: up to this grid size the whole Jacobi / Conv k-step loop is one kernel */
 #define NPDE_MAX_UNET_SMOOTH 8 /* npde_unet_step_bwd: pre / post smoothing convs per level (the reference uses <= 4) */
 
 /* operations for npde_workspace_bytes */
@@ -199,7 +200,9 @@ typedef struct npde_iterate_desc {
   int pre, post;       /* multigrid / unet smoothing counts */
   int act;             /* NPDE_ACT_* (conv, unet) */
   int k;               /* number of applications, >= 0 */
-  int temporal_depth;  /* Jacobi steps fused per HBM round trip (1,2,4,8); 0 = library default (4) */
+  int temporal_depth;  /* 0 = library default: grids up to NPDE_SMALL_MAX_N run the whole Jacobi / Conv loop in one
+                        * on-chip kernel, larger ones stream with 4 Jacobi steps per HBM round trip; 1,2,4,8 = streaming
+                        * kernels with that many Jacobi steps per round trip (Conv: one step per launch) */
   const float *x_in;   /* (B,N,N) */
   float *x_out;        /* (B,N,N); may alias x_in */
   const float *bc;

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libnpde_b200.so")
-SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_cg.cu", "npde_api.cu"]
+SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_cg.cu", "npde_small.cu", "npde_api.cu"]
 HEADERS = [os.path.join(CSRC, "npde_common.cuh"), os.path.join(CSRC, "npde_internal.h"),
            os.path.join(ROOT, "include", "npde.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=6) as ex:
         list(ex.map(run, jobs))
     objs = [os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
@@ -103,7 +103,7 @@ def build_emulator(force=False):
             if r.returncode != 0:
                 raise RuntimeError("emulator build failed:\n" + r.stderr)
 
-        with ThreadPoolExecutor(max_workers=5) as ex:  # the translation units in parallel
+        with ThreadPoolExecutor(max_workers=6) as ex:  # the translation units in parallel
             list(ex.map(cc, zip(srcs, objs)))
         r = subprocess.run(["g++", "-shared", "-o", out] + objs, capture_output=True, text=True)
         if r.returncode != 0:

@@ -1032,6 +1032,11 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   }
   int depth = d->temporal_depth == 0 ? 4 : d->temporal_depth;  // 4 measured fastest at 1025^2 (halo 4 = one lane)
   if (depth != 1 && depth != 2 && depth != 4 && depth != 8) return NPDE_ERR_ARG;
+  // grids that fit in shared memory: all k steps (and their error rows) in one kernel, x read and written once.
+  // An explicit temporal_depth selects the streaming kernels below instead.
+  if (d->temporal_depth == 0 && d->k >= 1 && npde::small_iterate_supported(it, N, d->n_layers, d->w_host))
+    return npde::small_iterate(it, d->x_in, d->x_out, d->bc, d->bc_kind, d->f, d->w_host, d->n_layers, d->act, d->k,
+                               d->gt, d->err_l2, d->err_fd, B, N, S(stream));
   size_t need = npde_workspace_bytes(NPDE_WS_ITERATE + it, B, N, d->bc_kind, d->n_layers, d->pre, d->post, d->k);
   TRY(ws_ok(d->workspace, d->workspace_bytes, need));
   cudaStream_t st = S(stream);

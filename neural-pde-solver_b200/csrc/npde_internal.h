@@ -34,6 +34,11 @@ inline FieldView as_const(const FieldViewMut &v) { return FieldView{v.p, v.pitch
 
 // square domain, 1 <= n_layers <= 4 and a HOST copy of the weights (they travel as kernel parameters)
 bool conv_stream_supported(int bc_kind, int n_layers, const float *w_host);
+// npde_small.cu: the whole k-step loop of a grid that fits in shared memory (N <= NPDE_SMALL_MAX_N) in one kernel
+bool small_iterate_supported(int iterator, int N, int n_layers, const float *w_host);
+int small_iterate(int iterator, const float *x_in, float *x_out, const float *bc, int bc_kind, const float *f,
+                  const float *w_host, int n_layers, int act, int k, const float *gt, float *err_l2, float *err_fd,
+                  int B, int N, cudaStream_t st);
 // npde_cg.cu
 size_t cg_ws_bytes(int B, int N);
 int cg_step(const float *x, int n_iters, float *y, int B, int N, void *ws, cudaStream_t st);

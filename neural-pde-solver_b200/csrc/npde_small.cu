@@ -1,0 +1,238 @@
+// npde_small.cu -- the whole k-step loop of a small problem in ONE kernel.
+//
+// Up to 65^2 (BASELINE configs[0]: 32 x 65^2, 800 evaluation steps, test.py) a grid fits in shared memory, so
+// the ultimate temporal blocking applies: one CTA per problem loads x once, applies Phi k times entirely on chip
+// (five zero-bordered (N+2)^2 planes: two iterates, y, two residual planes; phases separated by __syncthreads)
+// and writes x_k once.  The per-step error rows the loop drivers ask for (utils/heat_utils.py:163-181,
+// generation.py:82-93) are block reductions in the same kernel.  Every cell is computed with exactly the
+// operations of the layered kernels (npde_psi / npde_residual / row-major fmaf chains / npde_apply_G), so the
+// iterates are bit-identical to the stream kernels and the oracle.
+#include "npde_internal.h"
+
+namespace npde {
+namespace {
+
+constexpr int SMALL_THREADS = 1024;
+
+struct SmallParams {
+  const float *x_in;
+  float *x_out;
+  BcView bc;
+  const float *f, *gt;
+  float *err_l2, *err_fd;
+  ConvW w;
+  int L, act, jacobi, k, B, N;
+};
+
+// Cells are dealt to threads once: cell q of thread t is linear index t + q * SMALL_THREADS (at most MAXC per
+// thread at 65^2).  Everything that does not change from step to step -- the cell's offset in the padded planes,
+// whether it is interior, its Dirichlet data (ring value or 1-m and v), its source and ground-truth values --
+// is read once into registers, and every phase is a fully unrolled loop over the thread's cells (independent
+// fmaf chains interleave).
+constexpr int MAXC = (NPDE_SMALL_MAX_N * NPDE_SMALL_MAX_N + SMALL_THREADS - 1) / SMALL_THREADS;
+
+__device__ __forceinline__ float block_max(float v, float *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(NPDE_FULL_MASK, v, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = red[0];
+  for (int w = 1; w < SMALL_THREADS / 32; ++w) t = fmaxf(t, red[w]);
+  return t;
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  v = npde_warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < SMALL_THREADS / 32; ++w) t += red[w];  // fixed order
+  return t;
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_small_iterate(const SmallParams p) {
+  NPDE_DYN_SMEM(float, smem);
+  __shared__ double red[SMALL_THREADS / 32];
+  const int N = p.N, P = N + 2, PP = P * P, b = blockIdx.x;
+  float *X0 = smem, *X1 = X0 + PP, *Y = X1 + PP, *R0 = Y + PP, *R1 = R0 + PP;
+  const size_t img = (size_t)b * N * N;
+  const bool mask = p.bc.kind == NPDE_BC_MASK, has_f = p.f != nullptr;
+
+  for (int q = threadIdx.x; q < 5 * PP; q += SMALL_THREADS) smem[q] = 0.0f;
+  __syncthreads();
+
+  // per-cell constants
+  int off[MAXC];        // offset in a padded plane, -1: the thread has no such cell
+  bool inner[MAXC];     // 1 <= i,j <= N-2
+  bool ring[MAXC];      // square domain: G overwrites the cell with gv
+  float om[MAXC];       // mask geometry: 1 - m
+  float gv[MAXC];       // square: ring value; mask: bc value
+  float fq[MAXC], gq[MAXC];
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q) {
+    const int idx = (int)threadIdx.x + q * SMALL_THREADS;
+    off[q] = -1; inner[q] = false; ring[q] = false; om[q] = 1.0f; gv[q] = 0.0f; fq[q] = 0.0f; gq[q] = 0.0f;
+    if (idx < N * N) {
+      const int i = idx / N, j = idx - i * N;
+      off[q] = (i + 1) * P + j + 1;
+      inner[q] = i >= 1 && i <= N - 2 && j >= 1 && j <= N - 2;
+      if (mask) {
+        const float *val = p.bc.bc + (size_t)b * 2 * N * N;
+        om[q] = __fsub_rn(1.0f, __ldg(val + (size_t)N * N + idx));
+        gv[q] = __ldg(val + idx);
+      } else if (!inner[q]) {  // heat_utils.py:55-58: rows first, then columns (columns win the corners)
+        const float *c4 = p.bc.bc + (size_t)b * 4;
+        ring[q] = true;
+        gv[q] = j == 0 ? __ldg(c4 + 2) : (j == N - 1 ? __ldg(c4 + 3) : (i == 0 ? __ldg(c4 + 0) : __ldg(c4 + 1)));
+      }
+      if (has_f) fq[q] = __ldg(p.f + img + idx);
+      if (p.gt) gq[q] = __ldg(p.gt + img + idx);
+      X0[off[q]] = __ldg(p.x_in + img + idx);
+    }
+  }
+  __syncthreads();
+  float *cur = X0, *nxt = X1;
+
+  // G at one cell (npde_apply_G with the per-cell constants)
+  auto G = [&](float v, int q) -> float {
+    if (mask) return __fadd_rn(__fmul_rn(v, om[q]), gv[q]);
+    return ring[q] ? gv[q] : v;
+  };
+  // utils/heat_utils.py:108-132 fd_error('max') of the iterate in `cur` -> err_fd[row]
+  auto fd_row = [&](int row) {
+    float vmax = 0.0f;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      if (off[q] < 0 || !(mask || inner[q])) continue;
+      const float *c = cur + off[q];
+      float v = npde_residual(c[-P], c[-1], c[0], c[1], c[P]);
+      if (has_f) v = __fsub_rn(v, fq[q]);
+      if (mask) v = __fmul_rn(v, om[q]);
+      vmax = fmaxf(vmax, fabsf(v));
+    }
+    float t = block_max(vmax, reinterpret_cast<float *>(red));
+    if (threadIdx.x == 0) p.err_fd[(size_t)row * p.B + b] = t;
+  };
+  // utils/heat_utils.py:134-144 l2_error against gt -> err_l2[row]
+  auto l2_row = [&](int row) {
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < MAXC; ++q) {
+      if (off[q] < 0) continue;
+      float dlt = __fsub_rn(cur[off[q]], gq[q]);
+      acc += (double)__fmul_rn(dlt, dlt);
+    }
+    double t = block_sum(acc, red);
+    if (threadIdx.x == 0) p.err_l2[(size_t)row * p.B + b] = sqrtf((float)(t / ((double)N * (double)N)));
+  };
+
+  if (p.err_fd) fd_row(0);
+  for (int t = 0; t < p.k; ++t) {
+    if (p.jacobi) {
+      // utils/heat_utils.py:96-106: Psi zero padded, minus f, G
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        if (off[q] < 0) continue;
+        const float *c = cur + off[q];
+        float v = npde_psi(c[-P], c[-1], c[1], c[P]);
+        if (has_f) v = __fsub_rn(v, fq[q]);
+        nxt[off[q]] = G(v, q);
+      }
+    } else {
+      // conv_iterator.py:38-43: y = Psi_int(x) - f, r0 = (y - x_int) [* fg]
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        if (!inner[q]) continue;
+        const float *c = cur + off[q];
+        float y = npde_psi(c[-P], c[-1], c[1], c[P]);
+        if (has_f) y = __fsub_rn(y, fq[q]);
+        float r = __fsub_rn(y, c[0]);
+        if (mask) r = __fmul_rn(r, om[q]);
+        Y[off[q]] = y;
+        R0[off[q]] = r;
+      }
+      __syncthreads();
+      // conv_iterator.py:19-31: L x (3x3 cross-correlation, zero padded, [* fg]).  The residual planes hold the
+      // (N-2)^2 interior; their zero padding is the grid ring, which is never written.
+      float *src = R0, *dst = R1;
+      for (int l = 0; l < p.L; ++l) {
+        float w[9];
+#pragma unroll
+        for (int k9 = 0; k9 < 9; ++k9) w[k9] = p.w.w[l][k9];
+#pragma unroll
+        for (int q = 0; q < MAXC; ++q) {
+          if (!inner[q]) continue;
+          const float *c = src + off[q];
+          float acc = __fmul_rn(w[0], c[-P - 1]);
+          acc = __fmaf_rn(w[1], c[-P], acc);
+          acc = __fmaf_rn(w[2], c[-P + 1], acc);
+          acc = __fmaf_rn(w[3], c[-1], acc);
+          acc = __fmaf_rn(w[4], c[0], acc);
+          acc = __fmaf_rn(w[5], c[1], acc);
+          acc = __fmaf_rn(w[6], c[P - 1], acc);
+          acc = __fmaf_rn(w[7], c[P], acc);
+          acc = __fmaf_rn(w[8], c[P + 1], acc);
+          if (mask) acc = __fmul_rn(acc, om[q]);
+          dst[off[q]] = acc;
+        }
+        __syncthreads();
+        float *sw = src; src = dst; dst = sw;
+      }
+      // conv_iterator.py:46-50: G(pad(act(y + h)))
+#pragma unroll
+      for (int q = 0; q < MAXC; ++q) {
+        if (off[q] < 0) continue;
+        float v = inner[q] ? npde_act(__fadd_rn(Y[off[q]], src[off[q]]), p.act) : 0.0f;
+        nxt[off[q]] = G(v, q);
+      }
+    }
+    __syncthreads();
+    float *sw = cur; cur = nxt; nxt = sw;
+    if (p.err_l2) l2_row(t);
+    if (p.err_fd) fd_row(t + 1);
+  }
+#pragma unroll
+  for (int q = 0; q < MAXC; ++q)
+    if (off[q] >= 0) p.x_out[img + (int)threadIdx.x + q * SMALL_THREADS] = cur[off[q]];
+}
+
+}  // namespace
+
+bool small_iterate_supported(int iterator, int N, int n_layers, const float *w_host) {
+  if (N > NPDE_SMALL_MAX_N) return false;
+  if (iterator == NPDE_IT_JACOBI) return true;
+  return iterator == NPDE_IT_CONV && n_layers >= 1 && n_layers <= NPDE_MAX_CONV_LAYERS && w_host != nullptr;
+}
+
+int small_iterate(int iterator, const float *x_in, float *x_out, const float *bc, int bc_kind, const float *f,
+                  const float *w_host, int n_layers, int act, int k, const float *gt, float *err_l2, float *err_fd,
+                  int B, int N, cudaStream_t st) {
+  SmallParams p;
+  p.x_in = x_in; p.x_out = x_out;
+  p.bc = BcView{bc, bc_kind};
+  p.f = f; p.gt = gt; p.err_l2 = err_l2; p.err_fd = err_fd;
+  p.jacobi = iterator == NPDE_IT_JACOBI ? 1 : 0;
+  p.L = p.jacobi ? 0 : n_layers;
+  p.act = act; p.k = k; p.B = B; p.N = N;
+  for (int l = 0; l < NPDE_MAX_CONV_LAYERS; ++l)
+    for (int t = 0; t < 9; ++t) p.w.w[l][t] = (!p.jacobi && l < n_layers) ? w_host[l * 9 + t] : 0.0f;
+  const size_t smem = sizeof(float) * 5 * (size_t)(N + 2) * (N + 2);
+#ifndef NPDE_EMU
+  static bool configured = false;
+  if (!configured) {
+    const size_t most = sizeof(float) * 5 * (size_t)(NPDE_SMALL_MAX_N + 2) * (NPDE_SMALL_MAX_N + 2);
+    cudaError_t e = cudaFuncSetAttribute((const void *)k_small_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+#endif
+  NPDE_LAUNCH(k_small_iterate, dim3(B), dim3(SMALL_THREADS), smem, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+}  // namespace npde

@@ -243,12 +243,14 @@ class ConvIterator(Iterator):
         w = torch.stack([p.reshape(3, 3) for p in params])
         return F_.ConvUnrollFn.apply(x, bc, f, w, self.act, w_host, k)
 
-    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
+    def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None, temporal_depth=0):
+        """temporal_depth: 0 = library default (grids up to 65^2 run the whole loop in one on-chip kernel);
+        1 forces the streaming kernel (one launch per step)."""
         self._check_act()
         self._consistent(x, bc)
         w_dev, w_host = self._cache.get(self._params())
         return F_.iterate(IT_CONV, x, bc, f, k, w=w_dev, w_host=w_host, n_layers=self.n_layers, act=self.act,
-                          gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+                          gt=gt, want_l2=want_l2, want_fd=want_fd, out=out, temporal_depth=temporal_depth)
 
     def name(self):
         return 'Conv{}'.format(self.n_layers)

@@ -117,11 +117,13 @@ def test_conv_iterator(be, name):
     with torch.no_grad():
         y1 = it(x, bc, f)
         h = it.H(be.t(g["r"]).unsqueeze(1), bc)[:, 0]
-        y10, _, _ = it.iterate(x, bc, f, 10)
+        y10, _, _ = it.iterate(x, bc, f, 10)                       # <= 65^2: the one-kernel on-chip loop
+        y10s, _, _ = it.iterate(x, bc, f, 10, temporal_depth=1)    # the streaming kernel, one launch per step
         z = x
         for _ in range(10):
             z = it.iter_step(z, bc, f)
     assert_bitwise(be.n(z), be.n(y10), "iterate(10) == 10 x forward")
+    assert_bitwise(be.n(y10s), be.n(y10), "streaming loop == on-chip loop")
     if g["x"].shape[0] >= 2 and it.act != "sigmoid":
         assert_bitwise(be.n(h), g["H"], "H")
         assert_bitwise(be.n(y1), g["step1"], "conv step")
@@ -684,3 +686,47 @@ def test_mask_jacobi_temporal_blocking_open_border(be, oracle, B, N, k):
         mg = be.npde.MultigridIterator(3, 3, 5)
         mg.is_bc_mask = True
         assert_bitwise(be.n(mg(xd, bcd, None)), oracle.multigrid_step(x, bc, None, 3, 3, 5), "V-cycle (3,3,5), open border")
+
+
+@pytest.mark.parametrize("B,N,L,mask,has_f,act,k", [(3, 65, 3, False, False, "clamp", 7), (2, 33, 2, True, True, "none", 5),
+                                                    (5, 17, 1, False, True, "sigmoid", 4), (2, 65, 4, True, False, "clamp", 6),
+                                                    (1, 5, 3, False, False, "clamp", 3)])
+def test_small_grid_on_chip_loop(be, oracle, B, N, L, mask, has_f, act, k):
+    """k_small_iterate (grids up to 65^2: the whole loop in one kernel, one CTA per problem): iterates and both
+    kinds of error rows against the oracle, Conv and Jacobi, square and mask geometries, with and without source."""
+    rng = np.random.RandomState(B * 131 + N + L)
+    bc = _mask_geometry(rng, B, N) if mask else rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    gt = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator(act, L)
+    it.is_bc_mask = mask
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd, gtd = be.t(x), be.t(bc), be.t(f), be.t(gt)
+    y, e2, ef = it.iterate(xd, bcd, fd, k, gt=gtd, want_l2=True, want_fd=True)
+    ref, r2, rf = oracle.iterate("conv", x, bc, f, w, act, k, gt=gt, want_fd=True)
+    if act == "sigmoid":
+        assert rel_err(be.n(y), ref) <= 1e-5
+    else:
+        assert_bitwise(be.n(y), ref, "on-chip Conv loop")
+        assert_bitwise(be.n(ef), rf, "fd_error rows")
+        assert rel_err(be.n(e2), r2) <= 1e-6
+    jac = be.npde.JacobiIterator()
+    jac.is_bc_mask = mask
+    yj, j2, jf = jac.iterate(xd, bcd, fd, k + 3, gt=gtd, want_l2=True, want_fd=True)
+    refj, rj2, rjf = oracle.iterate("jacobi", x, bc, f, None, "none", k + 3, gt=gt, want_fd=True)
+    assert_bitwise(be.n(yj), refj, "on-chip Jacobi loop")
+    assert_bitwise(be.n(jf), rjf, "Jacobi fd_error rows")
+    assert rel_err(be.n(j2), rj2) <= 1e-6
+    assert_bitwise(be.n(xd), x, "input untouched")
+    # in place
+    xc = xd.clone()
+    jac.iterate(xc, bcd, fd, k + 3, out=xc)
+    assert_bitwise(be.n(xc), refj, "in place")
