@@ -48,6 +48,53 @@ __global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int s
   out[((size_t)b * Ho + i) * Ho + j] = acc;
 }
 
+// Same-size variant (stride 1, pad 1, natural column order): a thread owns one column of a CONV_ROWS-row chunk and
+// slides a 3x3 register window down it -- 3 loads per output instead of 9, no per-tap index arithmetic.  The
+// taps are combined in the same row-major fmaf chain as k_conv3x3, so results are bit-identical.
+constexpr int CONV_ROWS = 8;
+__global__ void __launch_bounds__(TX * TY)
+k_conv3x3_same(ArrView in, int H, const float *__restrict__ w, const float *__restrict__ mask, size_t mask_bstride,
+               float *__restrict__ out) {
+  const int j = blockIdx.x * TX + threadIdx.x, b = blockIdx.z;
+  const int i0 = (blockIdx.y * TY + threadIdx.y) * CONV_ROWS;
+  if (j >= H || i0 >= H) return;
+  const float *p = in.p + (size_t)b * in.bstride + (size_t)in.off * in.pitch + in.off;  // element (0,0)
+  float wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = __ldg(w + k);
+  const bool has_l = j > 0, has_r = j < H - 1;
+  auto row3 = [&](int i, float &a, float &c, float &e) {
+    if (i < 0 || i >= H) { a = c = e = 0.0f; return; }
+    const float *r = p + (size_t)i * in.pitch + j;
+    a = has_l ? __ldg(r - 1) : 0.0f;
+    c = __ldg(r);
+    e = has_r ? __ldg(r + 1) : 0.0f;
+  };
+  float u0, u1, u2, m0, m1, m2, d0, d1, d2;
+  row3(i0 - 1, u0, u1, u2);
+  row3(i0, m0, m1, m2);
+  const float *mk = mask ? mask + (size_t)b * mask_bstride : nullptr;
+#pragma unroll
+  for (int r = 0; r < CONV_ROWS; ++r) {
+    const int i = i0 + r;
+    if (i >= H) break;
+    row3(i + 1, d0, d1, d2);
+    float acc = __fmul_rn(wk[0], u0);
+    acc = __fmaf_rn(wk[1], u1, acc);
+    acc = __fmaf_rn(wk[2], u2, acc);
+    acc = __fmaf_rn(wk[3], m0, acc);
+    acc = __fmaf_rn(wk[4], m1, acc);
+    acc = __fmaf_rn(wk[5], m2, acc);
+    acc = __fmaf_rn(wk[6], d0, acc);
+    acc = __fmaf_rn(wk[7], d1, acc);
+    acc = __fmaf_rn(wk[8], d2, acc);
+    if (mk) acc = __fmul_rn(acc, fg_at(mk, H, i, j));
+    out[((size_t)b * H + i) * H + j] = acc;
+    u0 = m0; u1 = m1; u2 = m2;
+    m0 = d0; m1 = d1; m2 = d2;
+  }
+}
+
 // adjoint of k_conv3x3 w.r.t. its input: out[p,q] = sum_{a,c} w[a,c] * g[(p+pad-a)/s, (q+pad-c)/s]
 // (stride is a template parameter: the divisibility tests below would otherwise be integer divisions per tap)
 template <int stride>
@@ -271,18 +318,55 @@ k_bwd_layer(const float *__restrict__ g, const float *__restrict__ r, const floa
 #pragma unroll
   for (int k = 0; k < 9; ++k) acc[k] = 0.0;
   if (j < S) {
-    for (int i = blockIdx.y * BL_ROWS + threadIdx.y; i < min((int)(blockIdx.y + 1) * BL_ROWS, S); i += TY) {
+    // a thread walks BL_ROWS / TY consecutive rows of its column with two sliding 3x3 register windows (g and r):
+    // 6 loads per cell instead of 18
+    constexpr int RPT = BL_ROWS / TY;
+    const int i0 = blockIdx.y * BL_ROWS + threadIdx.y * RPT;
+    const bool has_l = j > 0, has_r = j < S - 1;
+    auto row3 = [&](const float *base, int i, float &a, float &c, float &e) {
+      if (i < 0 || i >= S) { a = c = e = 0.0f; return; }
+      const float *q = base + (size_t)i * S + j;
+      a = has_l ? __ldg(q - 1) : 0.0f;
+      c = __ldg(q);
+      e = has_r ? __ldg(q + 1) : 0.0f;
+    };
+    float gu[3], gm[3], gd[3], ru[3], rm[3], rd[3];
+    row3(gb, i0 - 1, gu[0], gu[1], gu[2]);
+    row3(gb, i0, gm[0], gm[1], gm[2]);
+    row3(rb, i0 - 1, ru[0], ru[1], ru[2]);
+    row3(rb, i0, rm[0], rm[1], rm[2]);
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) {
+      const int i = i0 + rr;
+      if (i >= S) break;
+      row3(gb, i + 1, gd[0], gd[1], gd[2]);
+      row3(rb, i + 1, rd[0], rd[1], rd[2]);
+      // conv^T: out[i,j] = sum_{a,c} w[a,c] * g[i+1-a, j+1-c], taps in (a,c) row-major order, out-of-range skipped
+      // (adding w * 0 to a finite sum leaves it unchanged, so reading zeros instead of skipping is the same chain)
       float out = 0.0f;
-      const float gv = __ldg(gb + (size_t)i * S + j);
-#pragma unroll
-      for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          int ii = i + 1 - a, jj = j + 1 - c;
-          if (ii >= 0 && jj >= 0 && ii < S && jj < S) out = __fmaf_rn(wk[a * 3 + c], __ldg(gb + (size_t)ii * S + jj), out);
-          acc[a * 3 + c] += (double)gv * (double)ldz(rb, S, i + a - 1, j + c - 1);
-        }
+      out = __fmaf_rn(wk[0], gd[2], out);
+      out = __fmaf_rn(wk[1], gd[1], out);
+      out = __fmaf_rn(wk[2], gd[0], out);
+      out = __fmaf_rn(wk[3], gm[2], out);
+      out = __fmaf_rn(wk[4], gm[1], out);
+      out = __fmaf_rn(wk[5], gm[0], out);
+      out = __fmaf_rn(wk[6], gu[2], out);
+      out = __fmaf_rn(wk[7], gu[1], out);
+      out = __fmaf_rn(wk[8], gu[0], out);
       tb[(size_t)i * S + j] = out;
+      // weight gradient: gw[a,c] += g[i,j] * r[i+a-1, j+c-1]
+      const double gv = (double)gm[1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        acc[0 + c] += gv * (double)ru[c];
+        acc[3 + c] += gv * (double)rm[c];
+        acc[6 + c] += gv * (double)rd[c];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        gu[c] = gm[c]; gm[c] = gd[c];
+        ru[c] = rm[c]; rm[c] = rd[c];
+      }
     }
   }
   __shared__ double sh[TY][9];
@@ -334,6 +418,12 @@ int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const
 
 int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
                  size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
+  if (stride == 1 && pad == 1 && Hi == Ho && !in.perm) {
+    dim3 grid((Ho + TX - 1) / TX, (Ho + TY * CONV_ROWS - 1) / (TY * CONV_ROWS), B);
+    NPDE_LAUNCH(k_conv3x3_same, grid, dim3(TX, TY), 0, st, in, Ho, w9, mask, mask_bstride, out);
+    NPDE_CHECK_LAUNCH();
+    return NPDE_OK;
+  }
   NPDE_LAUNCH(k_conv3x3, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, in, Hi, w9, stride, pad, mask, mask_bstride,
               out, Ho);
   NPDE_CHECK_LAUNCH();
