@@ -52,6 +52,11 @@ __global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int s
 // slides a 3x3 register window down it -- 3 loads per output instead of 9, no per-tap index arithmetic.  The
 // taps are combined in the same row-major fmaf chain as k_conv3x3, so results are bit-identical.
 constexpr int CONV_ROWS = 8;
+#ifdef NPDE_EMU
+constexpr size_t CONV_SAME_MIN_CELLS = (size_t)1 << 11;  // the emulated suite's small cases must reach both kernels
+#else
+constexpr size_t CONV_SAME_MIN_CELLS = (size_t)1 << 20;
+#endif
 __global__ void __launch_bounds__(TX * TY)
 k_conv3x3_same(ArrView in, int H, const float *__restrict__ w, const float *__restrict__ mask, size_t mask_bstride,
                float *__restrict__ out) {
@@ -418,7 +423,8 @@ int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const
 
 int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
                  size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
-  if (stride == 1 && pad == 1 && Hi == Ho && !in.perm) {
+  // (8 rows per thread: only once there are enough cells to fill the machine with an eighth of the threads)
+  if (stride == 1 && pad == 1 && Hi == Ho && !in.perm && (size_t)B * Ho * Ho >= CONV_SAME_MIN_CELLS) {
     dim3 grid((Ho + TX - 1) / TX, (Ho + TY * CONV_ROWS - 1) / (TY * CONV_ROWS), B);
     NPDE_LAUNCH(k_conv3x3_same, grid, dim3(TX, TY), 0, st, in, Ho, w9, mask, mask_bstride, out);
     NPDE_CHECK_LAUNCH();

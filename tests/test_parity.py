@@ -730,3 +730,36 @@ def test_small_grid_on_chip_loop(be, oracle, B, N, L, mask, has_f, act, k):
     xc = xd.clone()
     jac.iterate(xc, bcd, fd, k + 3, out=xc)
     assert_bitwise(be.n(xc), refj, "in place")
+
+
+@pytest.mark.gpu
+def test_large_batch_layered_kernels_vs_oracle(oracle):
+    """Sizes at which the coarse U-Net levels and the backward run on the row-sliding kernels (k_conv3x3_same,
+    k_bwd_layer; >= 2^20 cells per launch): U-Net step on a mask geometry bit for bit, Conv3 backward to 1e-5."""
+    be = Backend("cuda")
+    rng = np.random.RandomState(77)
+    B, N = 20, 513
+    bc = _mask_geometry(rng, B, N)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    wf = ((rng.rand(6, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    wp = ((rng.rand(2, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    ws = ((rng.rand(3, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.UNetIterator("clamp", 3, 2, 1)
+    it.is_bc_mask = True
+    with torch.no_grad():
+        for ml, wsrc in ((it.first_layers, wf), (it.pooling_layers, wp), (it.second_layers, ws)):
+            for l, wl in zip(ml, wsrc):
+                l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    with torch.no_grad():
+        y = it(be.t(x), be.t(bc), None)
+    assert_bitwise(be.n(y), oracle.unet_step(x, bc, None, wf, wp, ws, 3, 2, 1, "clamp"), "U-Net step, 20 x 513^2 masks")
+    # Conv3 one-step backward on the square domain
+    bc4 = rng.rand(B, 4).astype(np.float32)
+    xs = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc4)
+    w = ((rng.rand(3, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    gout = (rng.rand(B, N, N).astype(np.float32) - 0.5)
+    gw, gx = be.F.conv_step_bwd(be.t(xs), be.t(bc4), None, be.t(w), "clamp", be.t(gout), True)
+    rw, rx = oracle.conv_step_bwd(xs, bc4, None, w, "clamp", gout)
+    assert rel_err(be.n(gw), rw) <= 1e-5
+    assert rel_err(be.n(gx), rx) <= 1e-5
