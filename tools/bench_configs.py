@@ -173,6 +173,22 @@ def main():
         print(json.dumps({"name": "jacobi_257_b64_time_to_1e-6_residual", "seconds": dt, "iterations": res["iterations"],
                           "converged": res["converged"], "final_residual": res["history"][-1][1]}), flush=True)
 
+    if not args.quick:
+        # BASELINE's second metric at the headline size: Jacobi to a 1e-6 residual on 64 x 1025^2 (temporally blocked,
+        # one scalar read back per 2000 iterations).  The CPU reference needs ~0.77 s per iteration.
+        B, N = 64, 1025
+        x, bc, _ = square_problem(B, N)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x = npde.utils.initialize(x, bc, "avg")
+        res = npde.utils.solve_to_tolerance(npde.JacobiIterator(), x, bc, None, tol=1e-6, check_every=2000,
+                                            max_iters=2000000)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print(json.dumps({"name": "jacobi_1025_b64_time_to_1e-6_residual", "seconds": dt, "iterations": res["iterations"],
+                          "converged": res["converged"], "final_residual": res["history"][-1][1],
+                          "G_cell_updates_per_s": B * N * N * res["iterations"] / dt / 1e9}), flush=True)
+
     # ---- config 4: training step, 257^2, batch 64 per GPU, K = 20 --------------------------------
     import argparse as _ap
     opt = _ap.Namespace(iterator="conv", activation="clamp", conv_n_layers=3, mg_n_layers=3, mg_pre_smoothing=2,
