@@ -67,7 +67,7 @@ def main():
         get = lambda k: (r[hdr.index(k)], units[hdr.index(k)]) if k in hdr else ("n/a", "")
         lines = ["# ncu --set full: %s" % get("Kernel Name")[0].strip(), "",
                  "Capture: `ncu --set full -k regex:k_conv_stream -s 150 -c 1 --clock-control none --import-source on "
-                 "python bench.py --steps 1 --warmup 3 --no-cpu` on one B200 (workload conv3_jacobi_square_1025_b64: "
+                 "python bench.py --steps 1 --warmup 3 --no-cpu --no-ttr` on one B200 (workload conv3_jacobi_square_1025_b64: "
                  "64 x 1025^2, clamp, one Phi_H application per launch).", "", "| metric | value |", "|---|---|"]
         for k, label in KEYS:
             v, u = get(k)
@@ -116,7 +116,7 @@ def main():
             tot[name][1] += t
         total = sum(v[1] for v in tot.values())
         lines = ["# launch list: `ncu --metrics gpu__time_duration.sum --clock-control none -c 320 python bench.py "
-                 "--steps 1 --warmup 3 --no-cpu`", "",
+                 "--steps 1 --warmup 3 --no-cpu --no-ttr`", "",
                  "Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.", "",
                  "| kernel | launches | total us | avg us | share |", "|---|---|---|---|---|"]
         for name, (n, t) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
