@@ -763,3 +763,52 @@ def test_large_batch_layered_kernels_vs_oracle(oracle):
     rw, rx = oracle.conv_step_bwd(xs, bc4, None, w, "clamp", gout)
     assert rel_err(be.n(gw), rw) <= 1e-5
     assert rel_err(be.n(gx), rx) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask,has_f", [(False, False), (True, True), (False, True), (True, False)])
+def test_graph_replay_paths_vs_oracle(oracle, mask, has_f):
+    """npde_iterate on a launch-bound size that takes the CUDA-graph replay (129^2, k >= 16): captured segments of 32
+    fused launches with and without staged error rows, Conv and temporally blocked Jacobi, U-Net / multigrid pairs of
+    steps -- all against the oracle."""
+    be = Backend("cuda")
+    rng = np.random.RandomState(5 + 2 * mask + has_f)
+    B, N, k = 3, 129, 75
+    bc = _mask_geometry(rng, B, N) if mask else rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    gt = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(3, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", 3)
+    it.is_bc_mask = mask
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd, gtd = be.t(x), be.t(bc), be.t(f), be.t(gt)
+    ref, r2, rf = oracle.iterate("conv", x, bc, f, w, "clamp", k, gt=gt, want_fd=True)
+    y, _, _ = it.iterate(xd, bcd, fd, k)
+    assert_bitwise(be.n(y), ref, "Conv3, %d steps, replayed segments" % k)
+    y, e2, ef = it.iterate(xd, bcd, fd, k, gt=gtd, want_l2=True, want_fd=True)
+    assert_bitwise(be.n(y), ref, "Conv3 with staged error rows")
+    assert_bitwise(be.n(ef), rf, "fd_error rows")
+    assert rel_err(be.n(e2), r2) <= 1e-6
+    jac = be.npde.JacobiIterator()
+    jac.is_bc_mask = mask
+    kj = 2 * k + 1
+    refj, _, rjf = oracle.iterate("jacobi", x, bc, f, None, "none", kj, want_fd=True)
+    yj, _, _ = jac.iterate(xd, bcd, fd, kj)
+    assert_bitwise(be.n(yj), refj, "Jacobi, %d steps, replayed segments of blocked launches" % kj)
+    yj, _, jf = jac.iterate(xd, bcd, fd, kj, want_fd=True)
+    assert_bitwise(be.n(yj), refj, "Jacobi with staged residual rows")
+    assert_bitwise(be.n(jf), rjf, "Jacobi fd_error rows")
+    mg = be.npde.MultigridIterator(3, 2, 2)
+    mg.is_bc_mask = mask
+    ym, _, _ = mg.iterate(xd, bcd, fd, 17)
+    refm = x
+    for _ in range(17):
+        refm = oracle.multigrid_step(refm, bc, f, 3, 2, 2)
+    assert_bitwise(be.n(ym), refm, "17 V-cycles, replayed pairs")
