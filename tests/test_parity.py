@@ -812,3 +812,18 @@ def test_graph_replay_paths_vs_oracle(oracle, mask, has_f):
     for _ in range(17):
         refm = oracle.multigrid_step(refm, bc, f, 3, 2, 2)
     assert_bitwise(be.n(ym), refm, "17 V-cycles, replayed pairs")
+    wf = ((rng.rand(4, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    wp = ((rng.rand(1, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    ws = ((rng.rand(2, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    un = be.npde.UNetIterator("clamp", 2, 2, 1)
+    un.is_bc_mask = mask
+    with torch.no_grad():
+        for ml, wsrc in ((un.first_layers, wf), (un.pooling_layers, wp), (un.second_layers, ws)):
+            for l, wl in zip(ml, wsrc):
+                l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    un = un.to(be.device)
+    yu, _, _ = un.iterate(xd, bcd, fd, 18)
+    refu = x
+    for _ in range(18):
+        refu = oracle.unet_step(refu, bc, f, wf, wp, ws, 2, 2, 1, "clamp")
+    assert_bitwise(be.n(yu), refu, "18 U-Net steps, replayed pairs")
