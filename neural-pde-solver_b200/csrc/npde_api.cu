@@ -308,6 +308,7 @@ struct UnetBwdWs {
   float *gz, *g[2];
   void *wg;
   size_t wg_bytes;
+  unsigned *counter;  // block counter of the fused backward-layer kernel
   void carve(Bump &b, int B, int N, int L, int pre, int post, bool is_mask) {
     base.carve(b, B, N, L, is_mask);
     for (int l = 0; l < L; ++l) {
@@ -321,8 +322,10 @@ struct UnetBwdWs {
     gz = b.take<float>(n0);
     g[0] = b.take<float>(n0);
     g[1] = b.take<float>(n0);
-    wg_bytes = npde::weight_grad_ws_bytes(B, N - 2);
+    size_t wa = npde::weight_grad_ws_bytes(B, N - 2), wb = npde::bwd_layer_ws_bytes(B, N - 2);
+    wg_bytes = wa > wb ? wa : wb;
     wg = b.take_bytes(wg_bytes);
+    counter = b.take<unsigned>(1);
   }
 };
 
@@ -905,6 +908,12 @@ int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float
   TRY(npde::bwd_gz(gout, u.base.y_int, h, mask[0], mbs[0], act, u.gz, B, N, st));
   float *g = u.g[0], *other = u.g[1];
   auto swap = [&]() { float *t = g; g = other; other = t; };
+  // backward of one same-size conv layer: weight gradient and input gradient in one fused pass over g
+  auto layer_bwd = [&](const float *gin, const float *r, const float *w9, float *gout_, int S, float *gw9) -> int {
+    cudaError_t e = cudaMemsetAsync(u.counter, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return (int)e;
+    return npde::bwd_layer(gin, r, w9, gout_, S, gw9, B, u.wg, u.wg_bytes, u.counter, false, st);
+  };
   TRY(d2d(g, u.gz, sizeof(float) * cells(0), st));
   for (int i = L - 1; i >= 0; --i) {
     const int l = L - 1 - i;
@@ -916,9 +925,7 @@ int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float
     TRY(d2d(u.gskip[l], g, sizeof(float) * cells(l), st));
     for (int j = post - 1; j >= 0; --j) {
       if (mask[l]) TRY(npde::mul_fg(g, mask[l], mbs[l], sz[l], B, st));
-      TRY(npde::weight_grad(g, sz[l], u.Sx[l][j], sz[l], 1, 1, gw_second + 9 * (i * post + j), B, u.wg, u.wg_bytes,
-                            st));
-      TRY(npde::conv3x3_transpose(g, sz[l], w_second + 9 * (i * post + j), 1, 1, other, sz[l], B, st));
+      TRY(layer_bwd(g, u.Sx[l][j], w_second + 9 * (i * post + j), other, sz[l], gw_second + 9 * (i * post + j)));
       swap();
     }
   }
@@ -927,8 +934,7 @@ int npde_unet_step_bwd(const float *x, const float *bc, int bc_kind, const float
   for (int l = L - 1; l >= 0; --l) {
     for (int j = pre - 1; j >= 0; --j) {
       if (mask[l]) TRY(npde::mul_fg(g, mask[l], mbs[l], sz[l], B, st));
-      TRY(npde::weight_grad(g, sz[l], u.F[l][j], sz[l], 1, 1, gw_first + 9 * (l * pre + j), B, u.wg, u.wg_bytes, st));
-      TRY(npde::conv3x3_transpose(g, sz[l], w_first + 9 * (l * pre + j), 1, 1, other, sz[l], B, st));
+      TRY(layer_bwd(g, u.F[l][j], w_first + 9 * (l * pre + j), other, sz[l], gw_first + 9 * (l * pre + j)));
       swap();
     }
     if (l > 0) {  // the stride-2 pooling conv that produced this level's input (:63-66)
