@@ -357,11 +357,12 @@ int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const floa
   for (int l = l0; l < L; ++l) {
     int s = u.s[l];
     for (int j = 0; j < pre; ++j) {
-      float *dst = other(cur);
+      // the last pre-smoothing conv writes the skip tensor in place (:61), no copy
+      float *dst = (j == pre - 1) ? u.skip[l] : other(cur);
       TRY(npde::conv3x3(cur, s, wf + 9 * (l * pre + j), 1, 1, u.mask[l], u.mbs[l], dst, s, B, st));
       cur = dst;
     }
-    TRY(d2d(u.skip[l], cur, sizeof(float) * (size_t)B * s * s, st));  // :61
+    if (pre == 0) TRY(d2d(u.skip[l], cur, sizeof(float) * (size_t)B * s * s, st));
     if (l < L - 1) {
       float *dst = other(cur);
       TRY(npde::conv3x3(cur, s, wp + 9 * l, 2, 0, u.mask[l + 1], u.mbs[l + 1], dst, u.s[l + 1], B, st));  // :63-66
@@ -371,17 +372,18 @@ int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const floa
   for (int i = 0; i < L - l0; ++i) {
     int l = L - 1 - i, s = u.s[l];
     for (int j = 0; j < post; ++j) {
+      // the last post-smoothing conv adds the skip connection in its epilogue (:76)
       float *dst = other(cur);
-      TRY(npde::conv3x3(cur, s, wsnd + 9 * (i * post + j), 1, 1, u.mask[l], u.mbs[l], dst, s, B, st));
+      TRY(npde::conv3x3(cur, s, wsnd + 9 * (i * post + j), 1, 1, u.mask[l], u.mbs[l], dst, s, B, st,
+                        j == post - 1 ? u.skip[l] : nullptr));
       cur = dst;
     }
-    float *acc = const_cast<float *>(cur);
-    if (cur == src) {  // pre == post == 0 on a single level: do not write into the caller's input
-      acc = other(cur);
+    if (post == 0) {
+      float *acc = other(cur);  // never the caller's input, never the skip tensor
       TRY(d2d(acc, cur, sizeof(float) * (size_t)B * s * s, st));
+      TRY(npde::add_inplace(acc, u.skip[l], (size_t)B * s * s, st));  // :76
+      cur = acc;
     }
-    TRY(npde::add_inplace(acc, u.skip[l], (size_t)B * s * s, st));  // :76
-    cur = acc;
     if (l > l0) {
       float *dst = other(cur);
       TRY(npde::pad_up_crop(cur, s, u.mask[l - 1], u.mbs[l - 1], dst, B, st));  // :78-83

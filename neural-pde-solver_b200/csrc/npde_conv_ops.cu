@@ -30,7 +30,8 @@ __device__ __forceinline__ float fg_at(const float *__restrict__ mask, int S, in
 
 // out = conv3x3(in) [* fg]: row-major fmaf chain, first tap a plain product.
 __global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int stride, int pad,
-                          const float *__restrict__ mask, size_t mask_bstride, float *__restrict__ out, int Ho) {
+                          const float *__restrict__ mask, size_t mask_bstride, float *__restrict__ out, int Ho,
+                          const float *__restrict__ add) {
   int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
   if (i >= Ho || j >= Ho) return;
   const float *p = in.p + (size_t)b * in.bstride;
@@ -45,6 +46,7 @@ __global__ void k_conv3x3(ArrView in, int Hi, const float *__restrict__ w, int s
   acc = __fmaf_rn(__ldg(w + 7), ldzv(p, in, Hi, i0 + 2, j0 + 1), acc);
   acc = __fmaf_rn(__ldg(w + 8), ldzv(p, in, Hi, i0 + 2, j0 + 2), acc);
   if (mask) acc = __fmul_rn(acc, fg_at(mask + (size_t)b * mask_bstride, Ho, i, j));
+  if (add) acc = __fadd_rn(acc, __ldg(add + ((size_t)b * Ho + i) * Ho + j));
   out[((size_t)b * Ho + i) * Ho + j] = acc;
 }
 
@@ -59,7 +61,7 @@ constexpr size_t CONV_SAME_MIN_CELLS = (size_t)1 << 20;
 #endif
 __global__ void __launch_bounds__(TX * TY)
 k_conv3x3_same(ArrView in, int H, const float *__restrict__ w, const float *__restrict__ mask, size_t mask_bstride,
-               float *__restrict__ out) {
+               float *__restrict__ out, const float *__restrict__ add) {
   const int j = blockIdx.x * TX + threadIdx.x, b = blockIdx.z;
   const int i0 = (blockIdx.y * TY + threadIdx.y) * CONV_ROWS;
   if (j >= H || i0 >= H) return;
@@ -94,6 +96,7 @@ k_conv3x3_same(ArrView in, int H, const float *__restrict__ w, const float *__re
     acc = __fmaf_rn(wk[7], d1, acc);
     acc = __fmaf_rn(wk[8], d2, acc);
     if (mk) acc = __fmul_rn(acc, fg_at(mk, H, i, j));
+    if (add) acc = __fadd_rn(acc, __ldg(add + ((size_t)b * H + i) * H + j));
     out[((size_t)b * H + i) * H + j] = acc;
     u0 = m0; u1 = m1; u2 = m2;
     m0 = d0; m1 = d1; m2 = d2;
@@ -417,21 +420,22 @@ inline int wg_rows_per_block(int Hg) {
 namespace npde {
 
 int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const float *mask,
-            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
-  return conv3x3_view(ArrView{in, Hi, (long)Hi * Hi, 0, 0}, Hi, w9, stride, pad, mask, mask_bstride, out, Ho, B, st);
+            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st, const float *add) {
+  return conv3x3_view(ArrView{in, Hi, (long)Hi * Hi, 0, 0}, Hi, w9, stride, pad, mask, mask_bstride, out, Ho, B, st,
+                      add);
 }
 
 int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
-                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st) {
+                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st, const float *add) {
   // (8 rows per thread: only once there are enough cells to fill the machine with an eighth of the threads)
   if (stride == 1 && pad == 1 && Hi == Ho && !in.perm && (size_t)B * Ho * Ho >= CONV_SAME_MIN_CELLS) {
     dim3 grid((Ho + TX - 1) / TX, (Ho + TY * CONV_ROWS - 1) / (TY * CONV_ROWS), B);
-    NPDE_LAUNCH(k_conv3x3_same, grid, dim3(TX, TY), 0, st, in, Ho, w9, mask, mask_bstride, out);
+    NPDE_LAUNCH(k_conv3x3_same, grid, dim3(TX, TY), 0, st, in, Ho, w9, mask, mask_bstride, out, add);
     NPDE_CHECK_LAUNCH();
     return NPDE_OK;
   }
   NPDE_LAUNCH(k_conv3x3, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, in, Hi, w9, stride, pad, mask, mask_bstride,
-              out, Ho);
+              out, Ho, add);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -73,13 +73,14 @@ int prolong_view(const FieldView &x, const float *bc, int bc_kind, const FieldVi
 
 // npde_conv_ops.cu -- layer-by-layer building blocks (UNet, deep conv stacks, backward)
 // mask: level mask (B, S+2, S+2) with batch stride mask_bstride floats, or NULL.
+// add: optional (B,Ho,Ho) tensor added to the (masked) result -- the U-Net's skip connection fused into the conv
 int conv3x3(const float *in, int Hi, const float *w9, int stride, int pad, const float *mask,
-            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st);
+            size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st, const float *add = nullptr);
 int conv3x3_transpose(const float *g, int Hg, const float *w9, int stride, int pad, float *out, int Ho, int B,
                       cudaStream_t st);
 // same with the input read through an array view / the output written through one (frames of the fused U-Net path)
 int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad, const float *mask,
-                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st);
+                 size_t mask_bstride, float *out, int Ho, int B, cudaStream_t st, const float *add = nullptr);
 int pad_up_crop_view(const float *r, int s, const float *mask_out, size_t mask_bstride, const ArrViewMut &out, int B,
                      cudaStream_t st);
 int mul_fg(float *r, const float *mask, size_t mask_bstride, int S, int B, cudaStream_t st);
