@@ -219,9 +219,9 @@ int jacobi_steps_view(const FieldView &src, const FieldViewMut &buf0, const Fiel
   int flip = 0, left = n;
   const bool square = bcf.bc4 != nullptr;
   while (left > 0) {
-    int depth = 1;  // temporal blocking wherever there is no source term (square domain and mask geometries)
+    // temporal blocking everywhere: square domain and mask geometries, with and without a source term
     (void)square;
-    if (!f) depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+    int depth = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
     const bool final_launch = left - depth == 0;
     const FieldViewMut &dst = (final_launch && last) ? *last : (flip ? buf1 : buf0);
     if (!dst.p || dst.p == cur.p) return NPDE_ERR_ARG;
@@ -1083,7 +1083,8 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
       bcf.mask = npde::as_const(mp);
     }
     int left = d->k, flip = 0, done = 0;
-    const int full_adv = (jac_fast && !d->f && !want_err) ? ((d->bc_kind == NPDE_BC_MASK && depth > 4) ? 4 : depth) : 1;
+    const int full_adv =
+        (jac_fast && !want_err) ? (((d->bc_kind == NPDE_BC_MASK || d->f) && depth > 4) ? 4 : depth) : 1;
     auto launch = [&](const npde::FieldView &src, const npde::FieldViewMut &dst, int adv, cudaStream_t s) -> int {
       if (conv_fast) return npde::conv_stream(src, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, s);
       return npde::jacobi_stream(src, dst, bcf, fv, adv, B, N, s);

@@ -1120,7 +1120,8 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const int i0 = item.i0, i1 = item.i1;
   const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
   float *xout = p.out + (size_t)item.b * p.out_bstride + c.c0;
-  const float *fin = (T == 1 && p.f) ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
+  const float *fin = p.f ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
+  const bool FRING = T > 1 && fin != nullptr;  // source rows wait in a shared-memory ring like the bc rows
   float top = 0.f, bottom = 0.f, left = 0.f, right = 0.f;
   if (!MASK) {
     const float *bcb = p.bc4 + (size_t)item.b * 4;
@@ -1162,6 +1163,11 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
       mring[r * 64 + 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
+  uint4 *fring = mring + (MRING ? JAC_RING * 64 : 0);  // FRING: slot (row & 7): the source row, 16 bytes per lane
+  if (FRING) {
+#pragma unroll
+    for (int r = 0; r < JAC_RING; ++r) fring[r * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+  }
   // mask geometries: the ring need not be Dirichlet, so columns beyond the grid (pad columns of the permuted
   // layout, whatever they hold) must read as the zero padding of the stencil
   const unsigned img0 = (c.in_img & 1u) ? 0xffffffffu : 0u, img1 = (c.in_img & 2u) ? 0xffffffffu : 0u;
@@ -1171,7 +1177,8 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
     pf[0] = and2(pf[0], img0, img2);
     pf[1] = and2(pf[1], img1, img3);
   }
-  if (fin && it_first >= 1) load_row(fin + (size_t)(it_first - 1) * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
+  if (T == 1 && fin && it_first >= 1)
+    load_row(fin + (size_t)(it_first - 1) * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
   if (MASK && !MRING && it_first >= 1) {  // mask / value rows of the first output row it_first - 1
     load_row(min_ + (size_t)(it_first - 1) * p.bm_pitch, p.bm_perm != 0, ld_ok, c.in_img, pm[0], pm[1]);
     load_row(vin + (size_t)(it_first - 1) * p.bv_pitch, p.bv_perm != 0, ld_ok, c.in_img, pv[0], pv[1]);
@@ -1193,6 +1200,10 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
         if (T == 1 && fin) {
           o0 = sub2(o0, pff[0]);
           o1 = sub2(o1, pff[1]);
+        } else if (FRING && row >= 0 && row <= N - 1) {  // source row of grid row `row`, parked s steps ago
+          const uint4 fr = fring[(row & (JAC_RING - 1)) * 32 + lane];
+          o0 = sub2(o0, mk2(__uint_as_float(fr.x), __uint_as_float(fr.z)));
+          o1 = sub2(o1, mk2(__uint_as_float(fr.y), __uint_as_float(fr.w)));
         }
         if (MRING) {  // keep bits / values of grid row `row`, parked s steps ago
           if (row >= 0 && row <= N - 1) {
@@ -1238,8 +1249,12 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
       } else {
         pf[0] = pf[1] = zero2();
       }
-      if (T == 1 && fin) {  // next step's output row is `it`
+      if (fin) {  // next step's stage-1 output row is `it`
         if (it <= N - 1) load_row(fin + (size_t)it * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
+        if (FRING && it <= N - 1)
+          fring[(it & (JAC_RING - 1)) * 32 + lane] =
+              make_uint4(__float_as_uint(lo(pff[0])), __float_as_uint(lo(pff[1])), __float_as_uint(hi(pff[0])),
+                         __float_as_uint(hi(pff[1])));
         if (L2_AHEAD > 0 && it + L2_AHEAD <= x_last)
           prefetch_row(fin + (size_t)(it + L2_AHEAD) * p.f_pitch, lane, c.in_img);
       }
@@ -1454,8 +1469,10 @@ template <int T, bool MASK = false>
 int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 3) & ~3;
   static int cache = 0;
-  const size_t smem = MASK ? jacobi_mask_smem(T) : 0;
-  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>, smem, &cache);
+  // mask ring (keep bits + values) and source ring; the occupancy query assumes both
+  const size_t smem = (MASK ? jacobi_mask_smem(T) : 0) + ((T > 1 && p.f) ? (size_t)JAC_RING * 32 * 16 : 0);
+  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>,
+                                       (MASK ? jacobi_mask_smem(T) : 0) + (T > 1 ? (size_t)JAC_RING * 32 * 16 : 0), &cache);
   p.split = make_split(p.B, p.N, RC, T, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
   NPDE_LAUNCH((k_jacobi_stream<T, MASK>), grid, block, smem, st, p);
@@ -1579,7 +1596,7 @@ int conv_tail_stream(const FieldView &rin, const float *skip, const float *y, co
 #endif
 }
 
-int jacobi_stream_max_depth(const float *f) { return f ? 1 : 8; }
+int jacobi_stream_max_depth(const float *f) { return f ? 4 : 8; }
 
 int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int B, int N, cudaStream_t st) {
   ResidStreamParams p;
@@ -1617,7 +1634,7 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
   if (!perm_ok(in.p, in.pitch, in.bstride, in.perm, N) || !perm_ok(out.p, out.pitch, out.bstride, out.perm, N) ||
       !perm_ok(f.p, f.pitch, f.bstride, f.perm, N))
     return NPDE_ERR_ARG;
-  if (f.p && depth != 1) return NPDE_ERR_ARG;
+  if (f.p && depth > 4) return NPDE_ERR_ARG;  // the source ring holds 8 rows
   switch (depth) {
     case 1: return p.bm ? launch_jacobi<1, true>(p, st) : launch_jacobi<1>(p, st);
 #ifndef NPDE_DEV_ONLY_CONV3

@@ -120,6 +120,9 @@ def main():
         for depth in (1, 2, 4, 8):
             ms = timed(lambda: jac.iterate(x, bc, None, 64, out=out, temporal_depth=depth))
             emit("jacobi_1025_b64_depth%d" % depth, ms / 64, B * N * N, bytes_per_cell=8.0 / depth)
+        for depth in (1, 4):  # with a Poisson source: 12 B per cell-update at depth 1
+            ms = timed(lambda: jac.iterate(x, bc, f, 64, out=out, temporal_depth=depth))
+            emit("jacobi_1025_b64_poisson_depth%d" % depth, ms / 64, B * N * N, bytes_per_cell=12.0 / depth)
         ms = timed(lambda: npde.utils.fd_error(x, bc, None))
         emit("fd_error_1025_b64", ms, B * N * N, bytes_per_cell=4)
         mg = npde.MultigridIterator(6, 8, 8)
