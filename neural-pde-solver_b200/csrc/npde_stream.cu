@@ -1104,9 +1104,11 @@ struct JacobiStreamParams {
 // the grid come out as exact zeros, which is the zero padding the next stage expects.
 constexpr int JAC_RING = 8;  // rows, power of two, > largest T on a mask geometry
 constexpr size_t jacobi_mask_smem(int T) { return T > 1 ? (size_t)JAC_RING * 2 * 32 * 16 : 0; }
-template <int T, bool MASK = false>
+// HASF (T > 1 only; the T == 1 kernels test p.f at run time): a source term is present, its rows wait in a ring too.
+template <int T, bool MASK = false, bool HASF = false>
 __global__ void __launch_bounds__(npde::STREAM_THREADS)
 k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
+  static_assert(!HASF || T > 1, "T == 1 handles the source at run time");
   static_assert(!MASK || T < JAC_RING, "mask ring too short");
   constexpr bool MRING = MASK && T > 1;
   constexpr int RC = (T + 3) & ~3;  // column halo: whole lanes
@@ -1120,8 +1122,8 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
   const int i0 = item.i0, i1 = item.i1;
   const float *xin = p.in + (size_t)item.b * p.in_bstride + c.c0;
   float *xout = p.out + (size_t)item.b * p.out_bstride + c.c0;
-  const float *fin = p.f ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
-  const bool FRING = T > 1 && fin != nullptr;  // source rows wait in a shared-memory ring like the bc rows
+  constexpr bool FRING = HASF && T > 1;  // source rows wait in a shared-memory ring like the bc rows
+  const float *fin = ((T == 1 || HASF) && p.f) ? p.f + (size_t)item.b * p.f_bstride + c.c0 : nullptr;
   float top = 0.f, bottom = 0.f, left = 0.f, right = 0.f;
   if (!MASK) {
     const float *bcb = p.bc4 + (size_t)item.b * 4;
@@ -1249,7 +1251,7 @@ k_jacobi_stream(const NPDE_GRID_CONSTANT JacobiStreamParams p) {
       } else {
         pf[0] = pf[1] = zero2();
       }
-      if (fin) {  // next step's stage-1 output row is `it`
+      if ((T == 1 || HASF) && fin) {  // next step's stage-1 output row is `it`
         if (it <= N - 1) load_row(fin + (size_t)it * p.f_pitch, f_perm, ld_ok, c.in_img, pff[0], pff[1]);
         if (FRING && it <= N - 1)
           fring[(it & (JAC_RING - 1)) * 32 + lane] =
@@ -1465,19 +1467,25 @@ int launch_conv(ConvStreamParams &p, cudaStream_t st) {
 #endif
 }
 
-template <int T, bool MASK = false>
-int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
+template <int T, bool MASK, bool HASF>
+int launch_jacobi_f(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 3) & ~3;
   static int cache = 0;
-  // mask ring (keep bits + values) and source ring; the occupancy query assumes both
-  const size_t smem = (MASK ? jacobi_mask_smem(T) : 0) + ((T > 1 && p.f) ? (size_t)JAC_RING * 32 * 16 : 0);
-  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK>,
-                                       (MASK ? jacobi_mask_smem(T) : 0) + (T > 1 ? (size_t)JAC_RING * 32 * 16 : 0), &cache);
+  // mask ring (keep bits + values) and source ring
+  const size_t smem = (MASK ? jacobi_mask_smem(T) : 0) + (HASF ? (size_t)JAC_RING * 32 * 16 : 0);
+  int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK, HASF>, smem, &cache);
   p.split = make_split(p.B, p.N, RC, T, resident);
   dim3 grid((unsigned)((long)p.B * p.split.strips * p.split.bands)), block(npde::STREAM_THREADS);
-  NPDE_LAUNCH((k_jacobi_stream<T, MASK>), grid, block, smem, st, p);
+  NPDE_LAUNCH((k_jacobi_stream<T, MASK, HASF>), grid, block, smem, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
+}
+template <int T, bool MASK = false>
+int launch_jacobi(JacobiStreamParams &p, cudaStream_t st) {
+  if constexpr (T > 1 && T <= 4) {
+    if (p.f) return launch_jacobi_f<T, MASK, true>(p, st);
+  }
+  return launch_jacobi_f<T, MASK, false>(p, st);
 }
 
 }  // namespace
