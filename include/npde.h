@@ -202,7 +202,9 @@ typedef struct npde_iterate_desc {
   int k;               /* number of applications, >= 0 */
   int temporal_depth;  /* 0 = library default: grids up to NPDE_SMALL_MAX_N run the whole Jacobi / Conv loop in one
                         * on-chip kernel, larger ones stream with 4 Jacobi steps per HBM round trip; 1,2,4,8 = streaming
-                        * kernels with that many Jacobi steps per round trip (Conv: one step per launch) */
+                        * kernels with that many Jacobi steps per round trip (Conv: one step per launch, first-generation
+                        * strip kernel); -1 = Conv on the square domain: always the wide kernel on the batch-interleaved
+                        * layout (npde_pack), which the default picks by itself for large enough problems */
   const float *x_in;   /* (B,N,N) */
   float *x_out;        /* (B,N,N); may alias x_in */
   const float *bc;
@@ -217,6 +219,21 @@ typedef struct npde_iterate_desc {
 } npde_iterate_desc;
 
 int npde_iterate(const npde_iterate_desc *d, void *stream);
+
+/* ---- persistent device layout for drivers that keep fields resident between calls ----------------------
+ * The loops of generation.py:86-93 / runtime.py:78-79 / heat_model.py:49-50 call the iterator on the SAME
+ * tensors over and over.  A driver may convert them once into the library's batch-interleaved "W8" layout
+ * and step there, so that no call pays a layout pass:
+ *   element (b,i,c) of a (B,N,N) field  ->  i*pitch + (b*G8 + c/8)*8 + p8(c%8),
+ *   G8 = ceil(N/8), pitch = 8*B*G8 floats, p8 = position of column c0..c7 in (c0,c4,c1,c5,c2,c6,c3,c7);
+ *   padding columns hold zeros.  Buffers: npde_packed_floats(B,N) floats, 32-byte aligned. */
+size_t npde_packed_floats(int B, int N);
+int npde_pack(const float *x, float *packed, int B, int N, void *stream);    /* (B,N,N) -> W8 */
+int npde_unpack(const float *packed, float *x, int B, int N, void *stream);  /* W8 -> (B,N,N) */
+/* ConvIterator.forward (models/iterators/conv_iterator.py:33-51) on packed fields, square domain (bc (B,4)),
+ * 1 <= n_layers <= 4, w_host = HOST weights (n_layers,3,3); f_packed: packed source or NULL; in != out. */
+int npde_conv_step_packed(const float *in_packed, float *out_packed, const float *bc, const float *f_packed,
+                          const float *w_host, int n_layers, int act, int B, int N, void *stream);
 
 #ifdef __cplusplus
 }

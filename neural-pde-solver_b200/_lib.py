@@ -68,6 +68,10 @@ PROTOTYPES = {
     "npde_unet_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp,
                                   _vp, _int, _int, _vp, _size, _vp]),
     "npde_iterate": (_int, [ctypes.POINTER(IterateDesc), _vp]),
+    "npde_packed_floats": (_size, [_int, _int]),
+    "npde_pack": (_int, [_vp, _vp, _int, _int, _vp]),
+    "npde_unpack": (_int, [_vp, _vp, _int, _int, _vp]),
+    "npde_conv_step_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
 }
 
 _lib = None

@@ -17,8 +17,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libnpde_b200.so")
-SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_cg.cu", "npde_small.cu", "npde_api.cu"]
-HEADERS = [os.path.join(CSRC, "npde_common.cuh"), os.path.join(CSRC, "npde_internal.h"),
+SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_wide.cu", "npde_cg.cu", "npde_small.cu", "npde_api.cu"]
+HEADERS = [os.path.join(CSRC, "npde_common.cuh"), os.path.join(CSRC, "npde_internal.h"), os.path.join(CSRC, "npde_f2.cuh"),
            os.path.join(ROOT, "include", "npde.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=false"]  # no implicit contraction: every fused multiply-add is written as one
@@ -63,20 +63,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
-def build_variant(name, defines):
-    """DEVELOPMENT: a tuning build of the same library with extra -D flags (only the Conv3 / clamp
-    stream kernel is instantiated, see NPDE_DEV_ONLY_CONV3) -> tools/_build/libnpde_<name>.so.
-    Loaded through the NPDE_B200_LIB hook of _lib.py by tools/ab_bench.py; never shipped."""
+def build_variant(name, defines, source="npde_stream.cu", extra_flags=()):
+    """DEVELOPMENT: a tuning build of the same library with extra -D flags for ONE translation unit
+    (npde_stream.cu: only the Conv3 / clamp stream kernel is instantiated, see NPDE_DEV_ONLY_CONV3)
+    -> tools/_build/libnpde_<name>.so.  Loaded through the NPDE_B200_LIB hook of _lib.py by
+    tools/ab_bench.py / tools/ab_wide.py; never shipped."""
     out_dir = os.path.join(ROOT, "tools", "_build")
     os.makedirs(out_dir, exist_ok=True)
     build()
-    obj = os.path.join(out_dir, "npde_stream_%s.o" % name)
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-DNPDE_DEV_ONLY_CONV3"] + ["-D" + d for d in defines] + \
-          ["-c", "-o", obj, os.path.join(CSRC, "npde_stream.cu")]
+    obj = os.path.join(out_dir, "%s_%s.o" % (source[:-3], name))
+    dev = ["-DNPDE_DEV_ONLY_CONV3"] if source == "npde_stream.cu" else []
+    cmd = [_nvcc()] + NVCC_FLAGS + dev + ["-D" + d for d in defines] + list(extra_flags) + \
+          ["-c", "-o", obj, os.path.join(CSRC, source)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed: %s\n%s" % (" ".join(cmd), r.stderr))
-    objs = [obj if s == "npde_stream.cu" else os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
+    objs = [obj if s == source else os.path.join(OBJ, s.replace(".cu", ".o")) for s in SOURCES]
     out = os.path.join(out_dir, "libnpde_%s.so" % name)
     r = subprocess.run([_nvcc(), "-shared", "-o", out] + objs, capture_output=True, text=True)
     if r.returncode != 0:

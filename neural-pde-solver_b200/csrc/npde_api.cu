@@ -2,6 +2,8 @@
 // argument validation, workspace carving and the host-side schedules that
 // string kernels together (V-cycle, UNet, backward, the k-step loop).  Nothing
 // here synchronises or allocates.
+#include <stdlib.h>
+
 #include <atomic>
 #include <new>
 
@@ -443,6 +445,10 @@ struct IterWs {
     pitch = (N + 3) & ~3;
     bstride = (long)npde_align_up((size_t)pitch * N, 64);
     size_t cells = (size_t)B * bstride;  // >= B*N*N, so the generic loop can use them unpadded
+    if (iterator == NPDE_IT_CONV && bc_kind == NPDE_BC_SQUARE) {  // the wide kernel's batch-interleaved layout
+      const size_t wide = npde::wide_field_floats(B, N);
+      if (wide > cells) cells = wide;
+    }
     buf[0] = b.take<float>(cells);
     buf[1] = b.take<float>(cells);
     fpad = (iterator == NPDE_IT_JACOBI || iterator == NPDE_IT_CONV) ? b.take<float>(cells) : nullptr;
@@ -522,6 +528,19 @@ inline bool graph_worthwhile(size_t cells, int k) {
   return false;
 #else
   return cells <= ((size_t)8 << 20) && k >= 16;
+#endif
+}
+
+// the wide kernel wants enough strip-rows for every resident warp to get a piece of useful length
+inline bool wide_worthwhile(int B, int N) {
+#ifdef NPDE_EMU
+  (void)B;
+  return N >= 9;
+#else
+  const char *v = getenv("NPDE_WIDE");
+  if (v) return atoi(v) != 0;
+  const long groups = (long)B * ((N + 7) / 8);
+  return (groups + 29) / 30 * (long)N >= 4096;
 #endif
 }
 
@@ -1038,8 +1057,8 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     if (!level_sizes_ok(N, d->n_layers)) return NPDE_ERR_SIZE;
     if (it == NPDE_IT_UNET && !d->w) return NPDE_ERR_NULL;
   }
-  int depth = d->temporal_depth == 0 ? 4 : d->temporal_depth;  // 4 measured fastest at 1025^2 (halo 4 = one lane)
-  if (depth != 1 && depth != 2 && depth != 4 && depth != 8) return NPDE_ERR_ARG;
+  int depth = d->temporal_depth <= 0 ? 4 : d->temporal_depth;  // 4 measured fastest at 1025^2 (halo 4 = one lane)
+  if (d->temporal_depth < -1 || (depth != 1 && depth != 2 && depth != 4 && depth != 8)) return NPDE_ERR_ARG;
   // grids that fit in shared memory: all k steps (and their error rows) in one kernel, x read and written once.
   // An explicit temporal_depth selects the streaming kernels below instead.
   if (d->temporal_depth == 0 && d->k >= 1 && npde::small_iterate_supported(it, N, d->n_layers, d->w_host))
@@ -1064,6 +1083,21 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     if (d->err_fd)
       TRY(npde::fd_error_view(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd, B, N, w.red, w.red_bytes, st));
     if (d->k == 0) return d2d(d->x_out, d->x_in, sizeof(float) * cells, st);
+    // ---- wide path (npde_wide.cu): pack once, k launches on the batch-interleaved W8 layout, unpack once.
+    // Taken when there are enough strip-rows to fill the machine and no per-step error rows are wanted; an
+    // explicit temporal_depth selects the first-generation stream kernel below.
+    if (conv_fast && !want_err && d->k >= 3 && (d->temporal_depth == -1 || (d->temporal_depth == 0 && wide_worthwhile(B, N))) &&
+        npde::conv_wide_supported(d->bc_kind, d->n_layers, d->w_host, B, N)) {
+      const float *fw = nullptr;
+      if (d->f) {
+        TRY(npde::wide_pack(d->f, w.fpad, B, N, st));
+        fw = w.fpad;
+      }
+      TRY(npde::wide_pack(d->x_in, w.buf[0], B, N, st));
+      for (int t = 0; t < d->k; ++t)
+        TRY(npde::conv_wide(w.buf[t & 1], w.buf[(t + 1) & 1], d->bc, fw, d->w_host, d->n_layers, d->act, B, N, st));
+      return npde::wide_unpack(w.buf[d->k & 1], d->x_out, B, N, st);
+    }
     npde::FieldViewMut pad[2] = {{w.buf[0], w.pitch, w.bstride, 1}, {w.buf[1], w.pitch, w.bstride, 1}};
     npde::FieldViewMut last = npde::ref_view_mut(d->x_out, N);
     // the source is read in every step: give it 16-byte aligned rows once (128-bit loads)
@@ -1214,6 +1248,29 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     TRY(npde::fd_error(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd + (size_t)d->k * B, B, N, w.red,
                        w.red_bytes, st));
   return d2d(d->x_out, cur, sizeof(float) * cells, st);
+}
+
+size_t npde_packed_floats(int B, int N) { return (B > 0 && N > 0) ? npde::wide_field_floats(B, N) : 0; }
+
+int npde_pack(const float *x, float *packed, int B, int N, void *stream) {
+  TRY(npde::check_common(x, packed, B, N));
+  if ((uintptr_t)packed & 31) return NPDE_ERR_ARG;
+  return npde::wide_pack(x, packed, B, N, S(stream));
+}
+
+int npde_unpack(const float *packed, float *x, int B, int N, void *stream) {
+  TRY(npde::check_common(packed, x, B, N));
+  if ((uintptr_t)packed & 31) return NPDE_ERR_ARG;
+  return npde::wide_unpack(packed, x, B, N, S(stream));
+}
+
+int npde_conv_step_packed(const float *in_packed, float *out_packed, const float *bc, const float *f_packed,
+                          const float *w_host, int n_layers, int act, int B, int N, void *stream) {
+  TRY(npde::check_common(in_packed, out_packed, B, N));
+  if (!bc || !w_host) return NPDE_ERR_NULL;
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  if (n_layers < 1 || n_layers > 4) return NPDE_ERR_LAYERS;
+  return npde::conv_wide(in_packed, out_packed, bc, f_packed, w_host, n_layers, act, B, N, S(stream));
 }
 
 }  // extern "C"

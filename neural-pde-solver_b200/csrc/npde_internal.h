@@ -138,4 +138,16 @@ int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int 
 int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &bc, const FieldView &f, int depth,
                   int B, int N, cudaStream_t st);
 
+
+// npde_wide.cu -- second-generation fused Phi_H kernel on the batch-interleaved "W8" layout (square domain):
+// element (b,i,c) of a (B,N,N) field lives at  i*pitch + (b*G8 + c/8)*8 + perm8(c%8),  G8 = ceil(N/8),
+// pitch = 8*B*G8, perm8 = (c0,c4,c1,c5,c2,c6,c3,c7); padding columns hold zeros.
+size_t wide_field_floats(int B, int N);
+bool conv_wide_supported(int bc_kind, int n_layers, const float *w_host, int B, int N);
+int wide_pack(const float *x_ref, float *wide, int B, int N, cudaStream_t st);
+int wide_unpack(const float *wide, float *x_ref, int B, int N, cudaStream_t st);
+// one Phi_H application W8 -> W8 (in != out, 32-byte aligned); f_wide: the source in the W8 layout or nullptr
+int conv_wide(const float *in, float *out, const float *bc4, const float *f_wide, const float *w_host, int n_layers,
+              int act, int B, int N, cudaStream_t st);
+
 }  // namespace npde

@@ -1,0 +1,721 @@
+// npde_wide.cu -- the k-step loop of Phi_H = ConvIterator.forward (models/iterators/conv_iterator.py:33-51)
+// on the square domain, second generation of the fused register-streaming kernel ("wide strips").
+//
+// What changed against k_conv_stream (npde_stream.cu), and why:
+//   * Batch-interleaved field layout "W8".  Row i of ALL images is one contiguous virtual row
+//         [ image 0 row i | image 1 row i | ... | image B-1 row i ],
+//     every image padded to G8 = ceil(N/8) groups of eight columns, and inside a group the columns are
+//     stored as (c0,c4,c1,c5,c2,c6,c3,c7).  A warp strip is 32 consecutive groups of the VIRTUAL row, so
+//     strips tile B*G8*8 columns instead of each image's 2^n+1 separately: at 64 x 1025^2 the computed
+//     columns drop from 1152 to 1100 per image row (halo waste 12.4% -> 7.3%), and at 257^2 from 384 to 284.
+//     Ring columns and the padding between two images are ordinary "not interior" columns (the EDGE masks).
+//   * Eight adjacent columns per lane as four packed pairs Qk = {c_k, c_k+4}.  With this pairing the left
+//     and right operands of a 3-wide stencil are whole register pairs for every output pair except the two
+//     at the lane's ends, and those two are built with one register move each ({c-1,c3}, {c4,c8}), so EVERY
+//     tap of every stage is one FFMA2; one SHFL pair serves eight columns instead of four; a lane moves its
+//     row with one 256-bit access (LDG/STG.E.ENL2.256, new on sm_100).  About 170 instructions per
+//     8-column row step instead of 2 x 129, for the same 264 FMA-pipe cycles.
+//   * Work partition by equal counts of strip-rows (a CTA = one warp runs at most two pieces), so every SM
+//     sub-partition gets the same amount of work whatever B * strips is.
+// The arithmetic is unchanged: per output the oracle's order (oracle/npde_oracle.c conv3x3_img, orc_fd_step),
+// explicit fma.rn / mul.rn / sub.rn only, so iterates stay bit-identical to k_conv_stream and the CPU oracle.
+#include <stdlib.h>
+
+#include "npde_common.cuh"
+#include "npde_internal.h"
+
+#include "npde_f2.cuh"
+
+namespace {
+
+constexpr int WCOLS = 8;      // columns per lane
+constexpr int WVALID = 30;    // lanes 1..30 of a strip store; lanes 0 and 31 are the halo (radius <= 8 columns)
+constexpr int WSLOT = 1024;   // bytes of one row segment of a strip (32 lanes x 8 columns x 4 bytes)
+#ifndef NPDE_WRING
+#define NPDE_WRING 8
+#endif
+constexpr int WRING = NPDE_WRING;  // row segments in flight per warp (cp.async ring in shared memory)
+static_assert((WRING & (WRING - 1)) == 0 && WRING >= 2, "ring size: power of two");
+#ifndef NPDE_WIDE_ABL
+#define NPDE_WIDE_ABL 0  // tuning builds only: ablation bit mask (1 no STG, 2 no cp.async, 4 no SHFL, 8 no delay line, 16 no syncwarp)
+#endif
+#ifndef NPDE_WIDE_MIN_CTAS
+#define NPDE_WIDE_MIN_CTAS 8
+#endif
+
+struct WideParams {
+  const float *in;
+  float *out;
+  const float *f;    // NULL: Laplace; else the source in the W8 layout
+  const float *bc4;  // (B,4)
+  int B, N, G8, VG;  // G8 groups of 8 columns per image, VG = B*G8 groups per virtual row
+  int pitch;         // floats per virtual row = 8*VG
+  int strips;        // ceil(VG / WVALID)
+  // work partition (launch_wide_f): CTAs [0, strips*bands) take rows [band*band_rows, (band+1)*band_rows) of one
+  // strip each, in lock step; the remaining CTAs cut the flattened (strip,row) space of rows [main_rows, N) into
+  // equal runs of tail_chunk strip-rows (a run may continue in the next strip)
+  int bands, band_rows, main_rows, tail_chunk;
+  int act;
+  float w[4][9];
+};
+
+// ---- 256-bit global and 128-bit shared accesses of a lane's row: pairs q[k] = {c_k, c_k+4} ----------------
+#ifdef NPDE_EMU
+__device__ __forceinline__ void ld256(const float *p, f2 (&q)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = mk2(p[2 * k], p[2 * k + 1]);
+}
+__device__ __forceinline__ void st256_cols(float *p, const float (&o)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { p[2 * k] = o[k]; p[2 * k + 1] = o[k + 4]; }
+}
+__device__ __forceinline__ void lds128(const char *s, f2 &a, f2 &b) {
+  const float *p = reinterpret_cast<const float *>(s);
+  a = mk2(p[0], p[1]);
+  b = mk2(p[2], p[3]);
+}
+__device__ __forceinline__ void sts128(char *s, f2 a, f2 b) {
+  float *p = reinterpret_cast<float *>(s);
+  p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const float *g, bool valid) {
+  if (valid) memcpy(smem, g, 16);
+  else memset(smem, 0, 16);
+}
+#else
+__device__ __forceinline__ void ld256(const float *p, f2 (&q)[4]) {
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
+}
+// columns c0..c7 -> memory order (c0,c4,c1,c5,c2,c6,c3,c7), one STG.E.ENL2.256
+__device__ __forceinline__ void st256_cols(float *p, const float (&o)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[4]), "f"(o[1]),
+               "f"(o[5]), "f"(o[2]), "f"(o[6]), "f"(o[3]), "f"(o[7])
+               : "memory");
+}
+__device__ __forceinline__ void lds128(const char *s, f2 &a, f2 &b) {
+  const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s);
+  a = v.x;
+  b = v.y;
+}
+__device__ __forceinline__ void sts128(char *s, f2 a, f2 b) {
+  *reinterpret_cast<ulonglong2 *>(s) = make_ulonglong2(a, b);
+}
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const float *g, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g),
+               "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)); }
+#endif
+#ifdef NPDE_EMU
+__device__ __forceinline__ void pin_reg(unsigned &) {}
+#endif
+
+__device__ __forceinline__ float wsel_bits(float v, unsigned keep, unsigned val) {
+  return __uint_as_float((__float_as_uint(v) & keep) | val);
+}
+__device__ __noinline__ float wsigmoid_slow(float z) { return 1.0f / (1.0f + expf(-z)); }
+template <int ACT>
+__device__ __forceinline__ float wadd_act(float y, float h) {
+  if (ACT == NPDE_ACT_CLAMP) {
+#ifdef NPDE_EMU
+    return fminf(fmaxf(__fadd_rn(y, h), 0.0f), 1.0f);
+#else
+    float z;  // one FADD.SAT: round(y + h) clamped to [0, 1]
+    asm("add.rn.sat.f32 %0, %1, %2;" : "=f"(z) : "f"(y), "f"(h));
+    return z;
+#endif
+  }
+  const float z = __fadd_rn(y, h);
+  if (ACT == NPDE_ACT_SIGMOID) return wsigmoid_slow(z);
+  return z;
+}
+
+template <int L>
+struct WState {
+  f2 X[2][4];      // X[P]: x row `it` (arrived during the previous step), X[P^1]: row it-1 (centre row of Psi)
+  float xhl, xhr;  // outer neighbours of x row it-1: column c-1 (left lane's c7) and c8 (right lane's c0)
+  f2 yu[4];        // 0.25 * x[it-2]: first tap of Psi for output row it-1
+  f2 S[L][2][4];   // S[k-1][P]: partial sums of stage k that have seen taps w0..w5 (this step finishes them),
+                   // S[k-1][P^1]: taps w0..w2
+  f2 pff[4];       // f row it-1, fetched one step earlier
+};
+
+struct WCtx {
+  unsigned keep[8];  // per column c0..c7: all ones if interior column, else 0 (EDGE strips)
+  unsigned gval[8];  // Dirichlet value bits of a ring column, else 0
+  bool ld_ok, st_ok; // the lane's group exists / belongs to the strip's valid range
+  bool fill_ok[2];   // the two 16-byte chunks this lane copies into a ring slot exist
+  const float *fill, *ffill;  // chunk `lane` of the next x / f row segment to start into the ring
+  const float *safe; // any valid, 16-byte aligned address of the input field
+  float *pout;       // this lane's group in the output row of the current step
+  char *delay;       // slot 0 of the y delay line (shared memory)
+  char *ring;        // slot 0 of the x row ring (the f ring follows it)
+  unsigned a_off, b_off;      // this lane's two 16-byte chunks inside a slot ({Q0,Q1} and {Q2,Q3}), swizzled
+  unsigned fill_off;          // where chunk `lane` of a segment goes inside a slot (chunk lane+32: + 512)
+  unsigned rslot;    // ring slot (byte offset) that holds x row it+1
+  float top, bottom;
+  int N, i0, i1, x_last, f_last, pitch, lane_l, lane_r;
+};
+
+// left / right operand pairs of a row r[0..3] with outer neighbours hl (c-1) and hr (c8)
+#define NPDE_W_OPERANDS(r, hl, hr)            \
+  const f2 opl0 = mk2((hl), lo((r)[3]));      \
+  const f2 opr3 = mk2(hi((r)[0]), (hr))
+// three taps (wl, wc, wr) of one stencil row applied to the four output pairs a[0..3]
+__device__ __forceinline__ void wtaps(const f2 (&r)[4], f2 opl0, f2 opr3, float wl, float wc, float wr, f2 (&a)[4]) {
+  const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
+  a[0] = fma2(l2, opl0, a[0]); a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[1] = fma2(l2, r[0], a[1]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
+  a[2] = fma2(l2, r[1], a[2]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
+  a[3] = fma2(l2, r[2], a[3]); a[3] = fma2(c2, r[3], a[3]); a[3] = fma2(r2, opr3, a[3]);
+}
+// same for the first stencil row of an output: the first tap is a plain product (oracle conv3x3_img)
+__device__ __forceinline__ void wtaps_first(const f2 (&r)[4], f2 opl0, f2 opr3, float wl, float wc, float wr,
+                                            f2 (&a)[4]) {
+  const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
+  a[0] = mul2(l2, opl0); a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[1] = mul2(l2, r[0]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
+  a[2] = mul2(l2, r[1]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
+  a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = fma2(r2, opr3, a[3]);
+}
+__device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, float &hl, float &hr) {
+  if (NPDE_WIDE_ABL & 4) { hl = hi(r[3]); hr = lo(r[0]); return; }
+  hl = __shfl_sync(NPDE_FULL_MASK, hi(r[3]), lane_l);  // c7 of the left lane
+  hr = __shfl_sync(NPDE_FULL_MASK, lo(r[0]), lane_r);  // c0 of the right lane
+}
+
+// start the copy of one row segment (this strip's 32 groups = 1 KB) into a ring slot: lane l moves chunks l and l+32
+template <bool EDGE>
+__device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const WCtx &x) {
+  if (NPDE_WIDE_ABL & 2) return;
+  if (!(NPDE_WIDE_ABL & 16)) __syncwarp();  // lanes write each other's bytes: everybody is done reading the slot's previous row
+  if (EDGE) {
+    // a chunk outside the virtual row is zero-filled (source size 0; the address passed is a valid one anyway)
+    cp_async16_zfill(slot + x.fill_off, x.fill_ok[0] ? chunk : x.safe, x.fill_ok[0]);
+    cp_async16_zfill(slot + x.fill_off + 512, x.fill_ok[1] ? chunk + 4 * 32 : x.safe, x.fill_ok[1]);
+  } else {
+    cp_async16(slot + x.fill_off, chunk);
+    cp_async16(slot + x.fill_off + 512, chunk + 4 * 32);
+  }
+}
+
+// One step: input row `it` is in s.X[P].  Stage 0 (Psi, residual) works on row it-1, conv stage k (1..L) on row
+// it-1-k, each consuming the row the previous stage produced in this step; the epilogue stores row it-1-L.
+// MAIN: every stage row is an interior row, the output row belongs to this piece and the rows to fetch exist
+//       (no row tests); x (and f) rows arrive through the cp.async ring.
+// EDGE: the strip contains ring / padding / out-of-range columns: stage outputs are masked to the interior
+//       columns and G inserts the Dirichlet values.
+// P:    step parity (the two x slots and the two partial-sum rows of a stage swap roles every step; a variant
+//       that rotates three slots per stage to avoid consume-then-overwrite register moves needs a 3x unrolled
+//       loop of 10 KB and measured 4% slower: instruction fetch).
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P>
+__device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParams &p, int it, unsigned &woff) {
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  constexpr unsigned DMASK = DS * (unsigned)WSLOT - 1u;
+  constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
+  const int N = x.N;
+  const unsigned roff = (woff + (DS - L) * (unsigned)WSLOT) & DMASK;  // y written L steps ago
+  f2 rc[4];
+  float rl, rr;
+
+  // ---- stage 0: y = Psi(x) - f and r_0 = y - x for row it-1 ----
+  {
+    const f2 (&D)[4] = s.X[P];
+    f2 (&C)[4] = s.X[P ^ 1];
+    const int r0 = it - 1;
+    const f2 q = bc2(0.25f);
+    NPDE_W_OPERANDS(C, s.xhl, s.xhr);
+    f2 y[4];  // taps in the oracle's order: up (in yu), left, right, down
+    y[0] = fma2(q, opl0, s.yu[0]); y[0] = fma2(q, C[1], y[0]); y[0] = fma2(q, D[0], y[0]);
+    y[1] = fma2(q, C[0], s.yu[1]); y[1] = fma2(q, C[2], y[1]); y[1] = fma2(q, D[1], y[1]);
+    y[2] = fma2(q, C[1], s.yu[2]); y[2] = fma2(q, C[3], y[2]); y[2] = fma2(q, D[2], y[2]);
+    y[3] = fma2(q, C[2], s.yu[3]); y[3] = fma2(q, opr3, y[3]); y[3] = fma2(q, D[3], y[3]);
+    if (HASF) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
+      // x.ffill points at f row it + WRING - 1 (rows below 1 are never started: the pointer begins at row >= 1):
+      // it joins the copy group of x row it + WRING below
+      if (it + WRING - 1 <= x.f_last && (MAIN || it + WRING - 1 >= 1)) {
+        wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
+        x.ffill += x.pitch;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rc[k] = sub2(y[k], C[k]);
+    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc[0] = rc[1] = rc[2] = rc[3] = zero2();
+    if (EDGE) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rc[k] = and2(rc[k], x.keep[k], x.keep[k + 4]);
+    }
+    whalo(rc, x.lane_l, x.lane_r, rl, rr);
+    if (NPDE_WIDE_ABL & 8) {
+    } else {  // y waits L steps in the delay line
+      sts128(x.delay + woff + x.a_off, y[0], y[1]);
+      sts128(x.delay + woff + x.b_off, y[2], y[3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.yu[k] = mul2(q, C[k]);  // first tap of the next output row: up = x[it-1]
+    whalo(D, x.lane_l, x.lane_r, s.xhl, s.xhr);           // row `it` is the next centre row
+    // ---- start the copy of x row it + WRING into the ring slot that was read one step ago ----
+    if (it + WRING <= x.x_last) {
+      wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
+      x.fill += x.pitch;
+    }
+    cp_async_commit();
+  }
+
+  // ---- conv stages 1 .. L on rows it-2 .. it-1-L ----
+#pragma unroll
+  for (int k = 1; k <= L; ++k) {
+    const int rk = it - 1 - k;
+    const float *w = p.w[k - 1];
+    f2 (&mid)[4] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
+    f2 (&top)[4] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
+    NPDE_W_OPERANDS(rc, rl, rr);
+    f2 fin[4] = {mid[0], mid[1], mid[2], mid[3]};
+    wtaps(rc, opl0, opr3, w[6], w[7], w[8], fin);
+    wtaps(rc, opl0, opr3, w[3], w[4], w[5], top);        // becomes the "mid" row of the next step
+    wtaps_first(rc, opl0, opr3, w[0], w[1], w[2], mid);  // fresh "top" row of the next step
+    if (k < L) {
+      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = fin[2] = fin[3] = zero2();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rc[j] = EDGE ? and2(fin[j], x.keep[j], x.keep[j + 4]) : fin[j];
+      whalo(rc, x.lane_l, x.lane_r, rl, rr);
+    } else {
+      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+        float o[8];
+        if (MAIN || (rk >= 1 && rk <= N - 2)) {
+          f2 ya, yb, yc, yd;
+          if (NPDE_WIDE_ABL & 8) {
+            ya = s.yu[0]; yb = s.yu[1]; yc = s.yu[2]; yd = s.yu[3];
+          } else {
+            lds128(x.delay + roff + x.a_off, ya, yb);
+            lds128(x.delay + roff + x.b_off, yc, yd);
+          }
+          o[0] = wadd_act<ACT>(lo(ya), lo(fin[0])); o[4] = wadd_act<ACT>(hi(ya), hi(fin[0]));
+          o[1] = wadd_act<ACT>(lo(yb), lo(fin[1])); o[5] = wadd_act<ACT>(hi(yb), hi(fin[1]));
+          o[2] = wadd_act<ACT>(lo(yc), lo(fin[2])); o[6] = wadd_act<ACT>(hi(yc), hi(fin[2]));
+          o[3] = wadd_act<ACT>(lo(yd), lo(fin[3])); o[7] = wadd_act<ACT>(hi(yd), hi(fin[3]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+        }
+        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value (or 0: padding)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = wsel_bits(o[c], x.keep[c], x.gval[c]);
+        }
+        if (NPDE_WIDE_ABL & 1) {
+          if (o[0] + o[1] + o[2] + o[3] + o[4] + o[5] + o[6] + o[7] == 123.456f) st256_cols(x.pout, o);
+        } else if (x.st_ok) st256_cols(x.pout, o);
+      }
+      if (MAIN || rk >= 0) x.pout += x.pitch;  // invariant: pout points at row max(rk + 1, 0) afterwards
+    }
+  }
+  // ---- row it-1 is dead; row it+1 has landed (at most WRING - 1 younger copy groups pending): move it to registers
+  {
+    f2 (&C)[4] = s.X[P ^ 1];
+    cp_async_wait<WRING - 1>();
+    if (!(NPDE_WIDE_ABL & 16)) __syncwarp();  // a lane's bytes were copied by other lanes
+    if (MAIN || it + 1 <= x.x_last) {
+      lds128(x.ring + x.rslot + x.a_off, C[0], C[1]);
+      lds128(x.ring + x.rslot + x.b_off, C[2], C[3]);
+    } else {
+      C[0] = C[1] = C[2] = C[3] = zero2();
+    }
+    if (HASF) {  // f row `it` (used by stage 0 of the next step) travelled in the same copy group
+      if (MAIN || (it >= 1 && it <= x.f_last)) {
+        lds128(x.ring + WRING * WSLOT + x.rslot + x.a_off, s.pff[0], s.pff[1]);
+        lds128(x.ring + WRING * WSLOT + x.rslot + x.b_off, s.pff[2], s.pff[3]);
+      } else {
+        s.pff[0] = s.pff[1] = s.pff[2] = s.pff[3] = zero2();
+      }
+    }
+    x.rslot = (x.rslot + (unsigned)WSLOT) & RMASK;
+  }
+  woff = (woff + (unsigned)WSLOT) & DMASK;
+}
+
+// rows [i0, i1) of one strip
+template <int L, int ACT, bool HASF>
+__device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i0, int i1, char *smem) {
+  constexpr int R = L + 1;
+  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  WCtx x;
+  const int lane = threadIdx.x & 31, N = p.N;
+  x.lane_l = (lane + 31) & 31;
+  x.lane_r = (lane + 1) & 31;
+  x.N = N;
+  x.i0 = i0;
+  x.i1 = i1;
+  x.pitch = p.pitch;
+  x.safe = p.in;
+  x.delay = smem;
+  x.ring = smem + DS * WSLOT;
+  x.rslot = 0;
+  const int sw = (lane >> 2) & 1;
+  x.a_off = 32u * lane + 16u * sw;
+  x.b_off = 32u * lane + 16u * (1 - sw);
+  x.fill_off = 16u * (lane ^ ((lane >> 3) & 1));
+  // virtual group of this lane, its image and first column
+  const int v0 = strip * WVALID - 1;
+  const int vg = v0 + lane;
+  const bool in_range = vg >= 0 && vg < p.VG;
+  const int b = in_range ? vg / p.G8 : 0;
+  const int col0 = in_range ? (vg - b * p.G8) * WCOLS : 0;
+  x.ld_ok = in_range;
+  x.st_ok = in_range && lane >= 1 && lane <= WVALID;
+  {
+    const int va = v0 + (lane >> 1), vb = v0 + 16 + (lane >> 1);  // groups of chunks `lane` and `lane + 32`
+    x.fill_ok[0] = va >= 0 && va < p.VG;
+    x.fill_ok[1] = vb >= 0 && vb < p.VG;
+  }
+  const float *bcb = p.bc4 + (size_t)b * 4;
+  x.top = __ldg(bcb + 0);
+  x.bottom = __ldg(bcb + 1);
+  const float left = __ldg(bcb + 2), right = __ldg(bcb + 3);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int col = col0 + c;
+    const bool interior = in_range && col >= 1 && col <= N - 2;
+    x.keep[c] = interior ? 0xffffffffu : 0u;
+    x.gval[c] = !in_range ? 0u : (col == 0 ? __float_as_uint(left) : (col == N - 1 ? __float_as_uint(right) : 0u));
+    pin_reg(x.keep[c]);
+    pin_reg(x.gval[c]);
+  }
+  // uniform: the strip needs the EDGE code unless its 32 groups are interior groups of ONE image
+  bool edge_strip = true;
+  if (v0 >= 0 && v0 + 31 < p.VG) {
+    const int b0 = v0 / p.G8, g0 = v0 - b0 * p.G8;
+    const int g_hi = (N - 9) >= 0 ? (N - 9) / 8 : -1;  // last group whose eight columns are all interior
+    edge_strip = !(g0 >= 1 && g0 + 31 <= g_hi);
+  }
+
+  WState<L> s;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s.X[h][k] = zero2();
+#pragma unroll
+      for (int l = 0; l < L; ++l) s.S[l][h][k] = zero2();
+    }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s.yu[k] = s.pff[k] = zero2();
+  s.xhl = s.xhr = 0.0f;
+  __syncwarp();  // a previous piece of this warp is done with the shared memory
+#pragma unroll
+  for (int d = 0; d < DS; ++d) {
+    sts128(x.delay + d * WSLOT + x.a_off, zero2(), zero2());
+    sts128(x.delay + d * WSLOT + x.b_off, zero2(), zero2());
+  }
+  __syncwarp();
+
+  // input rows it = it_first .. it_last; the output row of a step is it - 1 - L
+  const int it_first = max(i0 - R, 0);  // rows above the grid are zeros == the initial state
+  const int it_last = i1 + L;
+  x.x_last = min(i1 - 1 + R, N - 1);    // last input row that exists and matters
+  x.f_last = min(x.x_last, N - 2);      // last row of f that is ever read
+  const size_t lane_off = (size_t)max(vg, 0) * WCOLS;
+  const float *xin = p.in + lane_off;
+  const float *fin_ = HASF ? p.f + lane_off : nullptr;
+  // chunk `lane` of this strip's row segment; strip 0 starts one group left of the row (never dereferenced there)
+  const long seg_off = (long)v0 * WCOLS + 4 * lane;
+  // the first step runs with parity 0: slot 0 receives row it_first
+  if (x.ld_ok) ld256(xin + (size_t)it_first * p.pitch, s.X[0]);
+  if (HASF && it_first - 1 >= 1 && x.ld_ok) ld256(fin_ + (size_t)(it_first - 1) * p.pitch, s.pff);
+  x.pout = p.out + lane_off + (size_t)max(it_first - 1 - L, 0) * p.pitch;
+  // Every later row arrives through the cp.async ring, in the warm-up and drain steps as well (a plain load per
+  // step exposes one DRAM latency per row: ~0.8 us x 11 generic steps per piece).  x row `it_first` is in
+  // registers; rows it_first+1 .. it_first+WRING-1 start now (f: one row behind, rows >= 1 only).
+  x.rslot = 0;
+  x.fill = p.in + (size_t)(it_first + 1) * p.pitch + seg_off;
+  x.ffill = HASF ? p.f + (size_t)max(it_first, 1) * p.pitch + seg_off : nullptr;
+#pragma unroll
+  for (int d = 0; d < WRING - 1; ++d) {
+    if (it_first + 1 + d <= x.x_last) {
+      wring_fill<true>(x.ring + d * WSLOT, x.fill, x);
+      x.fill += x.pitch;
+    }
+    if (HASF && it_first + d >= 1 && it_first + d <= x.f_last) {
+      wring_fill<true>(x.ring + (WRING + d) * WSLOT, x.ffill, x);
+      x.ffill += x.pitch;
+    }
+    cp_async_commit();
+  }
+  unsigned woff = 0;
+
+  // MAIN range of `it`: stage rows it-1-L .. it-1 interior, output row it-1-L inside the piece, x row it+1 exists
+  const int main_lo = max(L + 2, i0 + L + 1);
+  const int main_hi = min(N - 2, x.x_last - 1);
+  int it = it_first;  // (it - it_first) is even at the top of this loop: parities 0, 1 per trip
+  while (it <= it_last) {
+    if (it >= main_lo && it + 1 <= main_hi) {
+      if (edge_strip) {
+        do {
+          wide_step<L, ACT, HASF, true, true, 0>(s, x, p, it, woff);
+          wide_step<L, ACT, HASF, true, true, 1>(s, x, p, it + 1, woff);
+          it += 2;
+        } while (it + 1 <= main_hi);
+      } else {
+        do {
+          wide_step<L, ACT, HASF, true, false, 0>(s, x, p, it, woff);
+          wide_step<L, ACT, HASF, true, false, 1>(s, x, p, it + 1, woff);
+          it += 2;
+        } while (it + 1 <= main_hi);
+      }
+    } else {
+      wide_step<L, ACT, HASF, false, true, 0>(s, x, p, it, woff);
+      if (it + 1 <= it_last) wide_step<L, ACT, HASF, false, true, 1>(s, x, p, it + 1, woff);
+      it += 2;
+    }
+  }
+  cp_async_wait<0>();  // (nothing is pending here: no row beyond x_last is ever started)
+}
+
+template <int L, int ACT, bool HASF>
+__global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_WIDE_MIN_CTAS)
+k_conv_wide(const NPDE_GRID_CONSTANT WideParams p) {
+  NPDE_DYN_SMEM(float4, wsm);
+  const int n_main = p.strips * p.bands;
+  if ((int)blockIdx.x < n_main) {
+    const int strip = (int)blockIdx.x % p.strips, band = (int)blockIdx.x / p.strips;
+    const int i0 = band * p.band_rows, i1 = min(i0 + p.band_rows, p.main_rows);
+    if (i0 < i1) wide_piece<L, ACT, HASF>(p, strip, i0, i1, reinterpret_cast<char *>(wsm));
+    return;
+  }
+  const int tail_rows = p.N - p.main_rows;
+  const long total = (long)p.strips * tail_rows;
+  long r0 = (long)((int)blockIdx.x - n_main) * p.tail_chunk;
+  const long r1 = min(r0 + (long)p.tail_chunk, total);
+  while (r0 < r1) {
+    const int strip = (int)(r0 / tail_rows);
+    const int j0 = (int)(r0 - (long)strip * tail_rows);
+    const int n = (int)min((long)(tail_rows - j0), r1 - r0);
+    wide_piece<L, ACT, HASF>(p, strip, p.main_rows + j0, p.main_rows + j0 + n, reinterpret_cast<char *>(wsm));
+    r0 += n;
+  }
+}
+
+// ---- layout conversion: reference (B,N,N) <-> W8 ----------------------------------------------------------
+// One warp per (row, 32 groups): coalesced 4-byte accesses on the reference side (rows of a 2^n+1 grid are only
+// 4-byte aligned), a 1 KB staging row in shared memory, one 256-bit access per lane on the W8 side.
+// Padding columns of the W8 field are written as zeros.
+constexpr int PACK_WARPS = 4;
+template <bool TO_WIDE>
+__global__ void __launch_bounds__(32 * PACK_WARPS)
+k_wide_convert(const float *__restrict__ src, float *__restrict__ dst, int B, int N, int G8, int VG) {
+  __shared__ __align__(16) float stage[PACK_WARPS][256];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int seg = blockIdx.x * PACK_WARPS + wrp;  // 32 groups of the virtual row
+  const int row = blockIdx.y;
+  const int vg0 = seg * 32;
+  if (vg0 >= VG) return;
+  const size_t wrow = (size_t)row * VG * 8;
+  float *st = stage[wrp];
+  if (TO_WIDE) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = 32 * k + lane;  // element of the segment in column order
+      const int vg = vg0 + (e >> 3), c = e & 7;
+      float v = 0.0f;
+      if (vg < VG) {
+        const int b = vg / G8, col = (vg - b * G8) * 8 + c;
+        if (col < N) v = __ldg(src + ((size_t)b * N + row) * N + col);
+      }
+      st[(e & ~7) | ((c & 3) << 1) | (c >> 2)] = v;  // (c0,c4,c1,c5,c2,c6,c3,c7)
+    }
+    __syncwarp();
+    if (vg0 + lane < VG) {
+      const float4 a = *reinterpret_cast<const float4 *>(st + 8 * lane), bq = *reinterpret_cast<const float4 *>(st + 8 * lane + 4);
+      float4 *d = reinterpret_cast<float4 *>(dst + wrow + (size_t)(vg0 + lane) * 8);
+      d[0] = a;
+      d[1] = bq;
+    }
+  } else {
+    if (vg0 + lane < VG) {
+      const float4 *sp = reinterpret_cast<const float4 *>(src + wrow + (size_t)(vg0 + lane) * 8);
+      *reinterpret_cast<float4 *>(st + 8 * lane) = __ldg(sp);
+      *reinterpret_cast<float4 *>(st + 8 * lane + 4) = __ldg(sp + 1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = 32 * k + lane;
+      const int vg = vg0 + (e >> 3), c = e & 7;
+      if (vg < VG) {
+        const int b = vg / G8, col = (vg - b * G8) * 8 + c;
+        if (col < N) dst[((size_t)b * N + row) * N + col] = st[(e & ~7) | ((c & 3) << 1) | (c >> 2)];
+      }
+    }
+  }
+}
+
+struct WideGeom {
+  int G8, VG, pitch, strips;
+};
+WideGeom wide_geom(int B, int N) {
+  WideGeom g;
+  g.G8 = (N + 7) / 8;
+  g.VG = B * g.G8;
+  g.pitch = g.VG * 8;
+  g.strips = (g.VG + WVALID - 1) / WVALID;
+  return g;
+}
+
+template <int L>
+constexpr size_t wide_smem(bool hasf) {
+  return (size_t)WSLOT * (((L + 1 <= 4) ? 4 : 8) + (hasf ? 2 : 1) * WRING);
+}
+
+// resident warps of the kernel on the current device (cached per device)
+int wide_slots(const void *kernel, size_t smem, int *cache /* [NPDE_MAX_DEVICES] */) {
+#ifdef NPDE_EMU
+  (void)kernel; (void)smem; (void)cache;
+  return 5;  // small and odd on purpose: pieces that straddle strips, several pieces per strip
+#else
+  int dev = 0, sms = 0, blocks = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
+  if (cache[dev] > 0) return cache[dev];
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, npde::STREAM_THREADS, smem) != cudaSuccess || blocks < 1)
+    blocks = 1;
+  cache[dev] = sms * blocks;
+  return cache[dev];
+#endif
+}
+
+int wide_env_int(const char *name, int dflt) {
+#ifdef NPDE_EMU
+  (void)name;
+  return dflt;
+#else
+  const char *v = getenv(name);
+  return v ? atoi(v) : dflt;
+#endif
+}
+
+template <int L, int ACT, bool HASF>
+int launch_wide_f(WideParams &p, cudaStream_t st) {
+  static int cache[64] = {0};
+  const size_t smem = wide_smem<L>(HASF);
+  auto kern = k_conv_wide<L, ACT, HASF>;
+#ifndef NPDE_EMU
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  const int slots = wide_slots((const void *)kern, smem, cache);
+  // One piece of work per resident warp, all of the same height h = ceil(strips * N / slots), so that every SM
+  // sub-partition gets the same amount of work.  As many whole bands of h rows per strip as fit run in lock step
+  // (the warps of a band walk down the same rows at the same time: their 1 KB segments are contiguous in memory,
+  // 118 vs 126 us per launch at 64 x 1025^2 against pieces at unrelated rows); what is left of the rows goes to
+  // the remaining warps as equal runs of the flattened (strip,row) space.  A piece pays L + R warm-up rows, so
+  // pieces are kept >= minrows long.  NPDE_WIDE_BANDS=b (tuning): b whole bands per strip and nothing else.
+#ifdef NPDE_EMU
+  const int minrows = 6;
+#else
+  const int minrows = wide_env_int("NPDE_WIDE_MINROWS", 24);
+#endif
+  const int force_bands = wide_env_int("NPDE_WIDE_BANDS", 0);
+  const long work = (long)p.strips * p.N;
+  long h = (work + slots - 1) / slots;
+  if (h < minrows) h = minrows;
+  if (h > p.N) h = p.N;
+  int bands = (int)(p.N / h);                  // whole bands of h rows
+  if ((long)bands * p.strips > slots) bands = slots / p.strips;
+  if (force_bands > 0) {
+    bands = force_bands;
+    h = (p.N + bands - 1) / bands;
+  }
+  p.bands = bands;
+  p.band_rows = (int)h;
+  p.main_rows = (int)min((long)bands * h, (long)p.N);
+  int tail_rows = p.N - p.main_rows;
+  if (bands > 0 && tail_rows > 0 && tail_rows < 2 * (L + 1)) {  // a sliver: stretch the bands over it instead
+    p.band_rows = (p.N + bands - 1) / bands;
+    p.main_rows = p.N;
+    tail_rows = 0;
+  }
+  p.tail_chunk = (int)h;
+  long n_tail = 0;
+  if (tail_rows > 0) {
+    const long tail_work = (long)p.strips * tail_rows;
+    long left = (long)slots - (long)bands * p.strips;  // warps without a band piece
+    if (left < 1) left = 1;
+    long chunk = (tail_work + left - 1) / left;
+    if (chunk < minrows) chunk = minrows;
+    p.tail_chunk = (int)chunk;
+    n_tail = (tail_work + chunk - 1) / chunk;
+  }
+  dim3 grid((unsigned)((long)bands * p.strips + n_tail)), block(npde::STREAM_THREADS);
+  NPDE_LAUNCH((k_conv_wide<L, ACT, HASF>), grid, block, smem, st, p);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+template <int L>
+int launch_wide(WideParams &p, cudaStream_t st) {
+  switch (p.act) {
+    case NPDE_ACT_NONE:
+      return p.f ? launch_wide_f<L, NPDE_ACT_NONE, true>(p, st) : launch_wide_f<L, NPDE_ACT_NONE, false>(p, st);
+    case NPDE_ACT_CLAMP:
+      return p.f ? launch_wide_f<L, NPDE_ACT_CLAMP, true>(p, st) : launch_wide_f<L, NPDE_ACT_CLAMP, false>(p, st);
+    case NPDE_ACT_SIGMOID:
+      return p.f ? launch_wide_f<L, NPDE_ACT_SIGMOID, true>(p, st) : launch_wide_f<L, NPDE_ACT_SIGMOID, false>(p, st);
+    default: return NPDE_ERR_ACT;
+  }
+}
+
+}  // namespace
+
+namespace npde {
+
+size_t wide_field_floats(int B, int N) {
+  const WideGeom g = wide_geom(B, N);
+  return (size_t)g.pitch * N;
+}
+
+bool conv_wide_supported(int bc_kind, int n_layers, const float *w_host, int B, int N) {
+  return bc_kind == NPDE_BC_SQUARE && n_layers >= 1 && n_layers <= 4 && w_host != nullptr && B >= 1 && N >= 3;
+}
+
+int wide_pack(const float *x_ref, float *wide, int B, int N, cudaStream_t st) {
+  const WideGeom g = wide_geom(B, N);
+  dim3 grid((unsigned)((g.VG + 32 * PACK_WARPS - 1) / (32 * PACK_WARPS)), (unsigned)N), block(32 * PACK_WARPS);
+  NPDE_LAUNCH(k_wide_convert<true>, grid, block, 0, st, x_ref, wide, B, N, g.G8, g.VG);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int wide_unpack(const float *wide, float *x_ref, int B, int N, cudaStream_t st) {
+  const WideGeom g = wide_geom(B, N);
+  dim3 grid((unsigned)((g.VG + 32 * PACK_WARPS - 1) / (32 * PACK_WARPS)), (unsigned)N), block(32 * PACK_WARPS);
+  NPDE_LAUNCH(k_wide_convert<false>, grid, block, 0, st, wide, x_ref, B, N, g.G8, g.VG);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int conv_wide(const float *in, float *out, const float *bc4, const float *f_wide, const float *w_host, int n_layers,
+              int act, int B, int N, cudaStream_t st) {
+  if (!in || !out || !bc4 || !w_host) return NPDE_ERR_NULL;
+  if (in == out) return NPDE_ERR_ARG;
+  if (((uintptr_t)in | (uintptr_t)out | (uintptr_t)f_wide) & 31) return NPDE_ERR_ARG;
+  const WideGeom g = wide_geom(B, N);
+  WideParams p;
+  p.in = in; p.out = out; p.f = f_wide; p.bc4 = bc4;
+  p.B = B; p.N = N; p.G8 = g.G8; p.VG = g.VG; p.pitch = g.pitch; p.strips = g.strips;
+  p.bands = 1; p.band_rows = N; p.main_rows = N; p.tail_chunk = N; p.act = act;
+#ifdef NPDE_WIDE_DEBUG
+  if (wide_env_int("NPDE_WIDE_PITCH0", 0)) p.pitch = 0;  // tuning builds only: every row is row 0 (compute-only timing)
+#endif
+  for (int l = 0; l < 4; ++l)
+    for (int t = 0; t < 9; ++t) p.w[l][t] = (l < n_layers) ? w_host[l * 9 + t] : 0.0f;
+  switch (n_layers) {
+    case 1: return launch_wide<1>(p, st);
+    case 2: return launch_wide<2>(p, st);
+    case 3: return launch_wide<3>(p, st);
+    case 4: return launch_wide<4>(p, st);
+    default: return NPDE_ERR_LAYERS;
+  }
+}
+
+}  // namespace npde

@@ -827,3 +827,45 @@ def test_graph_replay_paths_vs_oracle(oracle, mask, has_f):
     for _ in range(18):
         refu = oracle.unet_step(refu, bc, f, wf, wp, ws, 2, 2, 1, "clamp")
     assert_bitwise(be.n(yu), refu, "18 U-Net steps, replayed pairs")
+
+
+# ------------------------------------------ second-generation Phi_H kernel (npde_wide.cu) --
+@pytest.mark.parametrize("B,N,L,has_f,act,k", [(3, 129, 3, False, "clamp", 5), (2, 257, 3, True, "none", 4),
+                                               (7, 33, 2, True, "clamp", 6), (13, 17, 1, False, "clamp", 3),
+                                               (4, 9, 4, False, "none", 3), (1, 65, 3, False, "sigmoid", 3),
+                                               (31, 17, 3, True, "clamp", 4), (2, 12, 3, False, "clamp", 3)])
+def test_wide_kernel_vs_oracle(be, oracle, B, N, L, has_f, act, k, tmp_path, monkeypatch):
+    """k_conv_wide: batch-interleaved W8 layout, eight columns per lane, strips that span several images and
+    pieces that straddle strips (the emulator build cuts the work into 5 pieces of >= 6 rows).  k fused steps
+    through npde_iterate (pack -> k launches -> unpack) against the CPU oracle, bit for bit (sigmoid: 1e-5)."""
+    rng = np.random.RandomState(B * 1000 + N + L)
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator(act, L)
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    trace = tmp_path / "launches.txt"
+    if be.kind == "emu":
+        monkeypatch.setenv("NPDE_EMU_TRACE", str(trace))
+    else:
+        monkeypatch.setenv("NPDE_WIDE", "1")
+    with torch.no_grad():
+        yk = be.F.iterate(be.npde._lib.IT_CONV, xd, bcd, fd, k, w=torch.stack([l.weight.reshape(9) for l in it.layers]),
+                          w_host=w, n_layers=L, act=act, temporal_depth=-1)[0]
+    ref = oracle.iterate("conv", x, bc, f, w, act, k)[0]
+    if act == "sigmoid":
+        assert rel_err(be.n(yk), ref) <= 1e-5
+    else:
+        assert_bitwise(be.n(yk), ref, "%d wide Phi_H steps" % k)
+    if be.kind == "emu":
+        names = trace.read_text().split()
+        assert sum("k_conv_wide" in n for n in names) == k, names
+        assert sum("k_wide_convert" in n for n in names) == (3 if has_f else 2), names

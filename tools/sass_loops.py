@@ -43,7 +43,8 @@ def parse(lines):
 
 def main():
     pat = sys.argv[1]
-    ins = parse(function_sass(pat))
+    lib = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else LIB
+    ins = parse(function_sass(pat, lib))
     if not ins:
         print("no function matches", pat)
         return 1
