@@ -312,7 +312,7 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(out_host.numel() * 4 + err_host.numel() * 4)},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_conv_stream<3,clamp,no-f>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "k_conv_wide<3,clamp,no-f>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": kernel_ms,
                      "cell_updates_per_s_kernel": B * N * N / (kernel_ms * 1e-3)},

@@ -222,12 +222,12 @@ int small_iterate(int iterator, const float *x_in, float *x_out, const float *bc
     for (int t = 0; t < 9; ++t) p.w.w[l][t] = (!p.jacobi && l < n_layers) ? w_host[l * 9 + t] : 0.0f;
   const size_t smem = sizeof(float) * 5 * (size_t)(N + 2) * (N + 2);
 #ifndef NPDE_EMU
-  static bool configured = false;
-  if (!configured) {
+  {
+    // the opt-in is a per-device function attribute: set it on every call (cheap) rather than once per process,
+    // so that a second GPU used by the same process gets it too
     const size_t most = sizeof(float) * 5 * (size_t)(NPDE_SMALL_MAX_N + 2) * (NPDE_SMALL_MAX_N + 2);
     cudaError_t e = cudaFuncSetAttribute((const void *)k_small_iterate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
   }
 #endif
   NPDE_LAUNCH(k_small_iterate, dim3(B), dim3(SMALL_THREADS), smem, st, p);

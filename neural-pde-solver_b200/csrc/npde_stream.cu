@@ -31,6 +31,8 @@
 //   - Arithmetic order is the oracle's: row-major fmaf chain, first tap a plain product
 //     (oracle/npde_oracle.c conv3x3_img / orc_fd_step), so iterates are bit-identical to the
 //     CPU restatement.
+#include <atomic>
+
 #include "npde_common.cuh"
 #include "npde_internal.h"
 
@@ -1278,20 +1280,29 @@ Split make_split(int B, int N, int halo_cols, int halo_rows, int resident_warps)
   return s;
 }
 
-int resident_warps_cached(const void *kernel, size_t smem, int *cache) {
+// Resident warps of a kernel on the CURRENT device.  The occupancy answer is a property of (kernel, device): the
+// cache is one relaxed atomic per device (a racing first call on two threads computes the same value twice).
+constexpr int MAX_DEVICES = 64;
+struct OccCache {
+  std::atomic<int> v[MAX_DEVICES];
+  OccCache() { for (auto &a : v) a.store(0, std::memory_order_relaxed); }
+};
+int resident_warps_cached(const void *kernel, size_t smem, OccCache *cache) {
 #ifdef NPDE_EMU
   (void)kernel; (void)smem; (void)cache;
   return 8;  // small on purpose: exercises several bands per image in the emulator
 #else
-  if (*cache > 0) return *cache;
   int dev = 0, sms = 0, blocks = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148 * 16;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148 * 16;
+  const int hit = cache->v[dev].load(std::memory_order_relaxed);
+  if (hit > 0) return hit;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, npde::STREAM_THREADS, smem) != cudaSuccess ||
       blocks < 1)
     blocks = 1;
-  *cache = sms * blocks * (npde::STREAM_THREADS / 32);
-  return *cache;
+  const int val = sms * blocks * (npde::STREAM_THREADS / 32);
+  cache->v[dev].store(val, std::memory_order_relaxed);
+  return val;
 #endif
 }
 
@@ -1313,7 +1324,7 @@ int launch_conv(ConvStreamParams &p, cudaStream_t st) {
   constexpr int R = L + 1, RC = (R + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
   // y delay line (+ keep-mask delay line) + x row ring (+ f row ring)
   const size_t smem = (size_t)512 * ((p.bm ? 2 : 1) * DS + (p.f ? 2 : 1) * RING_D) * (npde::STREAM_THREADS / 32);
-  static int cache[4] = {0, 0, 0, 0};
+  static OccCache cache[4];
 #ifdef NPDE_DEV_ONLY_CONV3
   int resident = resident_warps_cached((const void *)k_conv_stream<L, NPDE_ACT_CLAMP, false, false>, smem, &cache[0]);
 #else
@@ -1344,7 +1355,7 @@ int launch_conv(ConvStreamParams &p, cudaStream_t st) {
 template <int T, bool MASK, bool HASF>
 int launch_jacobi_f(JacobiStreamParams &p, cudaStream_t st) {
   constexpr int RC = (T + 3) & ~3;
-  static int cache = 0;
+  static OccCache cache;
   // mask ring (keep bits + values) and source ring
   const size_t smem = (MASK ? jacobi_mask_smem(T) : 0) + (HASF ? (size_t)JAC_RING * 32 * 16 : 0);
   int resident = resident_warps_cached((const void *)k_jacobi_stream<T, MASK, HASF>, smem, &cache);
@@ -1428,7 +1439,7 @@ template <int L, int ACT>
 static int launch_tail(TailStreamParams &p, cudaStream_t st) {
   constexpr int RC = (L + 3) & ~3, DS = (L + 1 <= 4) ? 4 : 8;
   const size_t smem = (size_t)512 * DS;
-  static int cache[2] = {0, 0};
+  static OccCache cache[2];
   int resident = p.bm ? resident_warps_cached((const void *)k_tail_stream<L, ACT, true>, smem, &cache[1])
                       : resident_warps_cached((const void *)k_tail_stream<L, ACT, false>, smem, &cache[0]);
   p.split = make_split(p.B, p.N, RC, L, resident);
@@ -1486,7 +1497,7 @@ int fd_error_max_stream(const FieldView &x, const FieldView &f, float *err, int 
   p.f = f.p; p.f_pitch = f.pitch; p.f_bstride = f.bstride; p.f_perm = f.p ? f.perm : 0;
   p.err = err; p.B = B; p.N = N;
   if (!perm_ok(x.p, x.pitch, x.bstride, x.perm, N) || !perm_ok(f.p, f.pitch, f.bstride, f.perm, N)) return NPDE_ERR_ARG;
-  static int cache = 0;
+  static OccCache cache;
   int resident = resident_warps_cached((const void *)k_resid_stream, 0, &cache);
   p.split = make_split(B, N, 4, 1, resident);
   cudaError_t e = cudaMemsetAsync(err, 0, sizeof(float) * (size_t)B, st);

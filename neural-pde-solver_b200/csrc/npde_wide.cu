@@ -15,11 +15,12 @@
 //     tap of every stage is one FFMA2; one SHFL pair serves eight columns instead of four; a lane moves its
 //     row with one 256-bit access (LDG/STG.E.ENL2.256, new on sm_100).  About 170 instructions per
 //     8-column row step instead of 2 x 129, for the same 264 FMA-pipe cycles.
-//   * Work partition by equal counts of strip-rows (a CTA = one warp runs at most two pieces), so every SM
-//     sub-partition gets the same amount of work whatever B * strips is.
+//   * Work partition: bands x strips one-warp CTAs in one wave, the strips of a band in lock step (launch_wide_f).
 // The arithmetic is unchanged: per output the oracle's order (oracle/npde_oracle.c conv3x3_img, orc_fd_step),
 // explicit fma.rn / mul.rn / sub.rn only, so iterates stay bit-identical to k_conv_stream and the CPU oracle.
 #include <stdlib.h>
+
+#include <atomic>
 
 #include "npde_common.cuh"
 #include "npde_internal.h"
@@ -32,13 +33,13 @@ constexpr int WCOLS = 8;      // columns per lane
 constexpr int WVALID = 30;    // lanes 1..30 of a strip store; lanes 0 and 31 are the halo (radius <= 8 columns)
 constexpr int WSLOT = 1024;   // bytes of one row segment of a strip (32 lanes x 8 columns x 4 bytes)
 #ifndef NPDE_WRING
-#define NPDE_WRING 8
+#define NPDE_WRING 4
 #endif
-constexpr int WRING = NPDE_WRING;  // row segments in flight per warp (cp.async ring in shared memory)
+// Row segments in flight per warp (cp.async ring in shared memory).  4 measured best: at L = 1, where the kernel is
+// memory bound, 102-107 us per launch against 111 with 8 (a deeper ring scatters the DRAM accesses in flight over
+// more rows); at L = 3 the depth does not matter.
+constexpr int WRING = NPDE_WRING;
 static_assert((WRING & (WRING - 1)) == 0 && WRING >= 2, "ring size: power of two");
-#ifndef NPDE_WIDE_ABL
-#define NPDE_WIDE_ABL 0  // tuning builds only: ablation bit mask (1 no STG, 2 no cp.async, 4 no SHFL, 8 no delay line, 16 no syncwarp)
-#endif
 #ifndef NPDE_WIDE_MIN_CTAS
 #define NPDE_WIDE_MIN_CTAS 8
 #endif
@@ -51,10 +52,7 @@ struct WideParams {
   int B, N, G8, VG;  // G8 groups of 8 columns per image, VG = B*G8 groups per virtual row
   int pitch;         // floats per virtual row = 8*VG
   int strips;        // ceil(VG / WVALID)
-  // work partition (launch_wide_f): CTAs [0, strips*bands) take rows [band*band_rows, (band+1)*band_rows) of one
-  // strip each, in lock step; the remaining CTAs cut the flattened (strip,row) space of rows [main_rows, N) into
-  // equal runs of tail_chunk strip-rows (a run may continue in the next strip)
-  int bands, band_rows, main_rows, tail_chunk;
+  int bands, band_rows;  // a CTA (one warp) takes rows [band*band_rows, (band+1)*band_rows) of one strip
   int act;
   float w[4][9];
 };
@@ -146,7 +144,8 @@ struct WCtx {
   unsigned gval[8];  // Dirichlet value bits of a ring column, else 0
   bool ld_ok, st_ok; // the lane's group exists / belongs to the strip's valid range
   bool fill_ok[2];   // the two 16-byte chunks this lane copies into a ring slot exist
-  const float *fill, *ffill;  // chunk `lane` of the next x / f row segment to start into the ring
+  const float *pin, *pfin;    // this lane's group in the next x / f row fetched with a plain load (generic steps)
+  const float *fill, *ffill;  // chunk `lane` of the next row segment to start into the ring (main loop)
   const float *safe; // any valid, 16-byte aligned address of the input field
   float *pout;       // this lane's group in the output row of the current step
   char *delay;       // slot 0 of the y delay line (shared memory)
@@ -180,7 +179,6 @@ __device__ __forceinline__ void wtaps_first(const f2 (&r)[4], f2 opl0, f2 opr3, 
   a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = fma2(r2, opr3, a[3]);
 }
 __device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, float &hl, float &hr) {
-  if (NPDE_WIDE_ABL & 4) { hl = hi(r[3]); hr = lo(r[0]); return; }
   hl = __shfl_sync(NPDE_FULL_MASK, hi(r[3]), lane_l);  // c7 of the left lane
   hr = __shfl_sync(NPDE_FULL_MASK, lo(r[0]), lane_r);  // c0 of the right lane
 }
@@ -188,8 +186,7 @@ __device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, 
 // start the copy of one row segment (this strip's 32 groups = 1 KB) into a ring slot: lane l moves chunks l and l+32
 template <bool EDGE>
 __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const WCtx &x) {
-  if (NPDE_WIDE_ABL & 2) return;
-  if (!(NPDE_WIDE_ABL & 16)) __syncwarp();  // lanes write each other's bytes: everybody is done reading the slot's previous row
+  __syncwarp();  // lanes write each other's bytes: everybody is done reading the slot's previous row
   if (EDGE) {
     // a chunk outside the virtual row is zero-filled (source size 0; the address passed is a valid one anyway)
     cp_async16_zfill(slot + x.fill_off, x.fill_ok[0] ? chunk : x.safe, x.fill_ok[0]);
@@ -234,11 +231,17 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
     if (HASF) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
-      // x.ffill points at f row it + WRING - 1 (rows below 1 are never started: the pointer begins at row >= 1):
-      // it joins the copy group of x row it + WRING below
-      if (it + WRING - 1 <= x.f_last && (MAIN || it + WRING - 1 >= 1)) {
-        wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
-        x.ffill += x.pitch;
+      if (MAIN) {
+        // x.ffill points at f row it + WRING - 1: it joins the copy group of x row it + WRING below
+        if (it + WRING - 1 <= x.f_last) {
+          wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
+          x.ffill += x.pitch;
+        }
+      } else {
+        const int nf = it;  // f row used by stage 0 of the next step
+        if (nf <= x.x_last && nf >= 1 && nf <= N - 2 && x.ld_ok) ld256(x.pfin, s.pff);
+        else s.pff[0] = s.pff[1] = s.pff[2] = s.pff[3] = zero2();
+        x.pfin += x.pitch;
       }
     }
 #pragma unroll
@@ -249,20 +252,25 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
       for (int k = 0; k < 4; ++k) rc[k] = and2(rc[k], x.keep[k], x.keep[k + 4]);
     }
     whalo(rc, x.lane_l, x.lane_r, rl, rr);
-    if (NPDE_WIDE_ABL & 8) {
-    } else {  // y waits L steps in the delay line
-      sts128(x.delay + woff + x.a_off, y[0], y[1]);
-      sts128(x.delay + woff + x.b_off, y[2], y[3]);
-    }
+    sts128(x.delay + woff + x.a_off, y[0], y[1]);  // y waits L steps in the delay line
+    sts128(x.delay + woff + x.b_off, y[2], y[3]);
 #pragma unroll
     for (int k = 0; k < 4; ++k) s.yu[k] = mul2(q, C[k]);  // first tap of the next output row: up = x[it-1]
     whalo(D, x.lane_l, x.lane_r, s.xhl, s.xhr);           // row `it` is the next centre row
-    // ---- start the copy of x row it + WRING into the ring slot that was read one step ago ----
-    if (it + WRING <= x.x_last) {
-      wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
-      x.fill += x.pitch;
+    // ---- row it-1 is dead: fetch x row it+1 ----
+    if (MAIN) {
+      if (it + WRING <= x.x_last) {  // x.fill points at row it + WRING: into the slot that was read one step ago
+        wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
+        x.fill += x.pitch;
+      }
+      cp_async_commit();
+    } else {
+      // warm-up / drain / ring-row steps: a plain load (running these steps from the cp.async ring as well
+      // measured 4% slower overall)
+      if (it + 1 <= x.x_last && x.ld_ok) ld256(x.pin, C);
+      else C[0] = C[1] = C[2] = C[3] = zero2();
+      x.pin += x.pitch;
     }
-    cp_async_commit();
   }
 
   // ---- conv stages 1 .. L on rows it-2 .. it-1-L ----
@@ -287,12 +295,8 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
         float o[8];
         if (MAIN || (rk >= 1 && rk <= N - 2)) {
           f2 ya, yb, yc, yd;
-          if (NPDE_WIDE_ABL & 8) {
-            ya = s.yu[0]; yb = s.yu[1]; yc = s.yu[2]; yd = s.yu[3];
-          } else {
-            lds128(x.delay + roff + x.a_off, ya, yb);
-            lds128(x.delay + roff + x.b_off, yc, yd);
-          }
+          lds128(x.delay + roff + x.a_off, ya, yb);
+          lds128(x.delay + roff + x.b_off, yc, yd);
           o[0] = wadd_act<ACT>(lo(ya), lo(fin[0])); o[4] = wadd_act<ACT>(hi(ya), hi(fin[0]));
           o[1] = wadd_act<ACT>(lo(yb), lo(fin[1])); o[5] = wadd_act<ACT>(hi(yb), hi(fin[1]));
           o[2] = wadd_act<ACT>(lo(yc), lo(fin[2])); o[6] = wadd_act<ACT>(hi(yc), hi(fin[2]));
@@ -305,31 +309,19 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = wsel_bits(o[c], x.keep[c], x.gval[c]);
         }
-        if (NPDE_WIDE_ABL & 1) {
-          if (o[0] + o[1] + o[2] + o[3] + o[4] + o[5] + o[6] + o[7] == 123.456f) st256_cols(x.pout, o);
-        } else if (x.st_ok) st256_cols(x.pout, o);
+        if (x.st_ok) st256_cols(x.pout, o);
       }
       if (MAIN || rk >= 0) x.pout += x.pitch;  // invariant: pout points at row max(rk + 1, 0) afterwards
     }
   }
-  // ---- row it-1 is dead; row it+1 has landed (at most WRING - 1 younger copy groups pending): move it to registers
-  {
-    f2 (&C)[4] = s.X[P ^ 1];
+  if (MAIN) {  // row it+1 has landed (at most WRING - 1 younger groups pending): move it to registers
     cp_async_wait<WRING - 1>();
-    if (!(NPDE_WIDE_ABL & 16)) __syncwarp();  // a lane's bytes were copied by other lanes
-    if (MAIN || it + 1 <= x.x_last) {
-      lds128(x.ring + x.rslot + x.a_off, C[0], C[1]);
-      lds128(x.ring + x.rslot + x.b_off, C[2], C[3]);
-    } else {
-      C[0] = C[1] = C[2] = C[3] = zero2();
-    }
-    if (HASF) {  // f row `it` (used by stage 0 of the next step) travelled in the same copy group
-      if (MAIN || (it >= 1 && it <= x.f_last)) {
-        lds128(x.ring + WRING * WSLOT + x.rslot + x.a_off, s.pff[0], s.pff[1]);
-        lds128(x.ring + WRING * WSLOT + x.rslot + x.b_off, s.pff[2], s.pff[3]);
-      } else {
-        s.pff[0] = s.pff[1] = s.pff[2] = s.pff[3] = zero2();
-      }
+    __syncwarp();  // a lane's bytes were copied by other lanes
+    lds128(x.ring + x.rslot + x.a_off, s.X[P ^ 1][0], s.X[P ^ 1][1]);
+    lds128(x.ring + x.rslot + x.b_off, s.X[P ^ 1][2], s.X[P ^ 1][3]);
+    if (HASF) {  // f row `it` travelled in the same copy group
+      lds128(x.ring + WRING * WSLOT + x.rslot + x.a_off, s.pff[0], s.pff[1]);
+      lds128(x.ring + WRING * WSLOT + x.rslot + x.b_off, s.pff[2], s.pff[3]);
     }
     x.rslot = (x.rslot + (unsigned)WSLOT) & RMASK;
   }
@@ -424,25 +416,11 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   // the first step runs with parity 0: slot 0 receives row it_first
   if (x.ld_ok) ld256(xin + (size_t)it_first * p.pitch, s.X[0]);
   if (HASF && it_first - 1 >= 1 && x.ld_ok) ld256(fin_ + (size_t)(it_first - 1) * p.pitch, s.pff);
+  // running pointers: pin -> row it+1 of x, pfin -> row it of f, pout -> output row it-1-L (clamped at 0)
+  x.pin = xin + (size_t)(it_first + 1) * p.pitch;
+  x.pfin = HASF ? fin_ + (size_t)it_first * p.pitch : nullptr;
+  x.fill = x.ffill = nullptr;
   x.pout = p.out + lane_off + (size_t)max(it_first - 1 - L, 0) * p.pitch;
-  // Every later row arrives through the cp.async ring, in the warm-up and drain steps as well (a plain load per
-  // step exposes one DRAM latency per row: ~0.8 us x 11 generic steps per piece).  x row `it_first` is in
-  // registers; rows it_first+1 .. it_first+WRING-1 start now (f: one row behind, rows >= 1 only).
-  x.rslot = 0;
-  x.fill = p.in + (size_t)(it_first + 1) * p.pitch + seg_off;
-  x.ffill = HASF ? p.f + (size_t)max(it_first, 1) * p.pitch + seg_off : nullptr;
-#pragma unroll
-  for (int d = 0; d < WRING - 1; ++d) {
-    if (it_first + 1 + d <= x.x_last) {
-      wring_fill<true>(x.ring + d * WSLOT, x.fill, x);
-      x.fill += x.pitch;
-    }
-    if (HASF && it_first + d >= 1 && it_first + d <= x.f_last) {
-      wring_fill<true>(x.ring + (WRING + d) * WSLOT, x.ffill, x);
-      x.ffill += x.pitch;
-    }
-    cp_async_commit();
-  }
   unsigned woff = 0;
 
   // MAIN range of `it`: stage rows it-1-L .. it-1 interior, output row it-1-L inside the piece, x row it+1 exists
@@ -451,50 +429,56 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   int it = it_first;  // (it - it_first) is even at the top of this loop: parities 0, 1 per trip
   while (it <= it_last) {
     if (it >= main_lo && it + 1 <= main_hi) {
-      if (edge_strip) {
-        do {
-          wide_step<L, ACT, HASF, true, true, 0>(s, x, p, it, woff);
-          wide_step<L, ACT, HASF, true, true, 1>(s, x, p, it + 1, woff);
-          it += 2;
-        } while (it + 1 <= main_hi);
-      } else {
-        do {
-          wide_step<L, ACT, HASF, true, false, 0>(s, x, p, it, woff);
-          wide_step<L, ACT, HASF, true, false, 1>(s, x, p, it + 1, woff);
-          it += 2;
-        } while (it + 1 <= main_hi);
-      }
+      // fill the ring: x row `it` is in registers, rows it+1 .. it+WRING-1 start now (f: one row behind)
+      x.rslot = 0;
+      x.fill = p.in + (size_t)(it + 1) * p.pitch + seg_off;
+      if (HASF) x.ffill = p.f + (size_t)it * p.pitch + seg_off;
+#define NPDE_W_MAIN_LOOP(EDGE_)                                                     \
+  do {                                                                              \
+    _Pragma("unroll") for (int d = 0; d < WRING - 1; ++d) {                         \
+      if (it + 1 + d <= x.x_last) {                                                 \
+        wring_fill<EDGE_>(x.ring + d * WSLOT, x.fill, x);                           \
+        x.fill += x.pitch;                                                          \
+      }                                                                             \
+      if (HASF && it + d <= x.f_last) {                                             \
+        wring_fill<EDGE_>(x.ring + (WRING + d) * WSLOT, x.ffill, x);                \
+        x.ffill += x.pitch;                                                         \
+      }                                                                             \
+      cp_async_commit();                                                            \
+    }                                                                               \
+    do {                                                                            \
+      wide_step<L, ACT, HASF, true, EDGE_, 0>(s, x, p, it, woff);                   \
+      wide_step<L, ACT, HASF, true, EDGE_, 1>(s, x, p, it + 1, woff);               \
+      it += 2;                                                                      \
+    } while (it + 1 <= main_hi);                                                    \
+  } while (0)
+      if (edge_strip) NPDE_W_MAIN_LOOP(true);
+      else NPDE_W_MAIN_LOOP(false);
+#undef NPDE_W_MAIN_LOOP
+      cp_async_wait<0>();
+      __syncwarp();
+      // back to plain loads: row `it` is in registers (slot of parity 0)
+      x.pin = xin + (size_t)(it + 1) * p.pitch;
+      if (HASF) x.pfin = fin_ + (size_t)it * p.pitch;
     } else {
       wide_step<L, ACT, HASF, false, true, 0>(s, x, p, it, woff);
       if (it + 1 <= it_last) wide_step<L, ACT, HASF, false, true, 1>(s, x, p, it + 1, woff);
       it += 2;
     }
   }
-  cp_async_wait<0>();  // (nothing is pending here: no row beyond x_last is ever started)
 }
 
 template <int L, int ACT, bool HASF>
 __global__ void __launch_bounds__(npde::STREAM_THREADS, NPDE_WIDE_MIN_CTAS)
 k_conv_wide(const NPDE_GRID_CONSTANT WideParams p) {
   NPDE_DYN_SMEM(float4, wsm);
-  const int n_main = p.strips * p.bands;
-  if ((int)blockIdx.x < n_main) {
-    const int strip = (int)blockIdx.x % p.strips, band = (int)blockIdx.x / p.strips;
-    const int i0 = band * p.band_rows, i1 = min(i0 + p.band_rows, p.main_rows);
-    if (i0 < i1) wide_piece<L, ACT, HASF>(p, strip, i0, i1, reinterpret_cast<char *>(wsm));
-    return;
-  }
-  const int tail_rows = p.N - p.main_rows;
-  const long total = (long)p.strips * tail_rows;
-  long r0 = (long)((int)blockIdx.x - n_main) * p.tail_chunk;
-  const long r1 = min(r0 + (long)p.tail_chunk, total);
-  while (r0 < r1) {
-    const int strip = (int)(r0 / tail_rows);
-    const int j0 = (int)(r0 - (long)strip * tail_rows);
-    const int n = (int)min((long)(tail_rows - j0), r1 - r0);
-    wide_piece<L, ACT, HASF>(p, strip, p.main_rows + j0, p.main_rows + j0 + n, reinterpret_cast<char *>(wsm));
-    r0 += n;
-  }
+  // strip index fastest: the warps of a band walk down the same rows at the same time, so their 1 KB row segments
+  // are contiguous in memory (one long DRAM burst per row of the band).  The work item depends on blockIdx only:
+  // ptxas can prove that the strip bookkeeping and the loop versioning are warp-uniform and keeps the weights in
+  // uniform registers.
+  const int strip = (int)blockIdx.x % p.strips, band = (int)blockIdx.x / p.strips;
+  const int i0 = band * p.band_rows, i1 = min(i0 + p.band_rows, p.N);
+  if (i0 < i1) wide_piece<L, ACT, HASF>(p, strip, i0, i1, reinterpret_cast<char *>(wsm));
 }
 
 // ---- layout conversion: reference (B,N,N) <-> W8 ----------------------------------------------------------
@@ -569,19 +553,22 @@ constexpr size_t wide_smem(bool hasf) {
 }
 
 // resident warps of the kernel on the current device (cached per device)
-int wide_slots(const void *kernel, size_t smem, int *cache /* [NPDE_MAX_DEVICES] */) {
+int wide_slots(const void *kernel, size_t smem, std::atomic<int> *cache /* one entry per device */) {
 #ifdef NPDE_EMU
   (void)kernel; (void)smem; (void)cache;
-  return 5;  // small and odd on purpose: pieces that straddle strips, several pieces per strip
+  return 7;  // small on purpose: several bands per strip in the emulator
 #else
   int dev = 0, sms = 0, blocks = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
-  if (cache[dev] > 0) return cache[dev];
+  const int hit = cache[dev].load(std::memory_order_relaxed);
+  if (hit > 0) return hit;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, npde::STREAM_THREADS, smem) != cudaSuccess || blocks < 1)
     blocks = 1;
-  cache[dev] = sms * blocks;
-  return cache[dev];
+  // one-warp CTAs are dealt to the four SM sub-partitions in turn: keep their count per SM a multiple of four
+  if (blocks >= 4) blocks &= ~3;
+  cache[dev].store(sms * blocks, std::memory_order_relaxed);
+  return sms * blocks;
 #endif
 }
 
@@ -597,56 +584,36 @@ int wide_env_int(const char *name, int dflt) {
 
 template <int L, int ACT, bool HASF>
 int launch_wide_f(WideParams &p, cudaStream_t st) {
-  static int cache[64] = {0};
+  static std::atomic<int> cache[64];  // zero-initialised (static storage)
   const size_t smem = wide_smem<L>(HASF);
   auto kern = k_conv_wide<L, ACT, HASF>;
 #ifndef NPDE_EMU
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   const int slots = wide_slots((const void *)kern, smem, cache);
-  // One piece of work per resident warp, all of the same height h = ceil(strips * N / slots), so that every SM
-  // sub-partition gets the same amount of work.  As many whole bands of h rows per strip as fit run in lock step
-  // (the warps of a band walk down the same rows at the same time: their 1 KB segments are contiguous in memory,
-  // 118 vs 126 us per launch at 64 x 1025^2 against pieces at unrelated rows); what is left of the rows goes to
-  // the remaining warps as equal runs of the flattened (strip,row) space.  A piece pays L + R warm-up rows, so
-  // pieces are kept >= minrows long.  NPDE_WIDE_BANDS=b (tuning): b whole bands per strip and nothing else.
+  // Work partition: bands x strips one-warp CTAs in ONE wave, as many whole bands per strip as there are resident
+  // warps for, the strips of a band in lock step.  The throughput of an SM sub-partition saturates with two resident
+  // warps (~430 cycles per warp and row step at L = 3 against 264 FMA-pipe cycles; a lone warp needs 545), so the
+  // launch time is (rows per band + warm-up) x that, whatever the number of strips: 118-121 us per launch for
+  // B = 60 .. 68 at 1025^2.  Everything tried to also use the resident warps that whole bands leave idle
+  // (64 x 1025^2: 276 strips x 4 bands = 1104 CTAs for 1184 warps) lost more on the memory side than it won:
+  // equal runs of the flattened (strip,row) space 126 us, the same with the strips ordered by the row offset of
+  // their piece boundaries ("diagonal lock step") 124 us, 4 bands + a flattened tail 137 us, two band heights
+  // (4 or 5 bands per strip) 120 us -- against 115-119 us for 4 whole bands (profiles/r2_wide_ab.txt).
+  // A piece pays L + R warm-up rows, so bands are kept >= minrows rows long.  NPDE_WIDE_BANDS=b (tuning) forces b.
 #ifdef NPDE_EMU
   const int minrows = 6;
 #else
   const int minrows = wide_env_int("NPDE_WIDE_MINROWS", 24);
 #endif
+  int bands = slots / (p.strips > 0 ? p.strips : 1);
+  if (bands > p.N / minrows) bands = p.N / minrows;
+  if (bands < 1) bands = 1;
   const int force_bands = wide_env_int("NPDE_WIDE_BANDS", 0);
-  const long work = (long)p.strips * p.N;
-  long h = (work + slots - 1) / slots;
-  if (h < minrows) h = minrows;
-  if (h > p.N) h = p.N;
-  int bands = (int)(p.N / h);                  // whole bands of h rows
-  if ((long)bands * p.strips > slots) bands = slots / p.strips;
-  if (force_bands > 0) {
-    bands = force_bands;
-    h = (p.N + bands - 1) / bands;
-  }
-  p.bands = bands;
-  p.band_rows = (int)h;
-  p.main_rows = (int)min((long)bands * h, (long)p.N);
-  int tail_rows = p.N - p.main_rows;
-  if (bands > 0 && tail_rows > 0 && tail_rows < 2 * (L + 1)) {  // a sliver: stretch the bands over it instead
-    p.band_rows = (p.N + bands - 1) / bands;
-    p.main_rows = p.N;
-    tail_rows = 0;
-  }
-  p.tail_chunk = (int)h;
-  long n_tail = 0;
-  if (tail_rows > 0) {
-    const long tail_work = (long)p.strips * tail_rows;
-    long left = (long)slots - (long)bands * p.strips;  // warps without a band piece
-    if (left < 1) left = 1;
-    long chunk = (tail_work + left - 1) / left;
-    if (chunk < minrows) chunk = minrows;
-    p.tail_chunk = (int)chunk;
-    n_tail = (tail_work + chunk - 1) / chunk;
-  }
-  dim3 grid((unsigned)((long)bands * p.strips + n_tail)), block(npde::STREAM_THREADS);
+  if (force_bands > 0) bands = force_bands;
+  p.band_rows = (p.N + bands - 1) / bands;
+  p.bands = (p.N + p.band_rows - 1) / p.band_rows;
+  dim3 grid((unsigned)((long)p.bands * p.strips)), block(npde::STREAM_THREADS);
   NPDE_LAUNCH((k_conv_wide<L, ACT, HASF>), grid, block, smem, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
@@ -703,10 +670,7 @@ int conv_wide(const float *in, float *out, const float *bc4, const float *f_wide
   WideParams p;
   p.in = in; p.out = out; p.f = f_wide; p.bc4 = bc4;
   p.B = B; p.N = N; p.G8 = g.G8; p.VG = g.VG; p.pitch = g.pitch; p.strips = g.strips;
-  p.bands = 1; p.band_rows = N; p.main_rows = N; p.tail_chunk = N; p.act = act;
-#ifdef NPDE_WIDE_DEBUG
-  if (wide_env_int("NPDE_WIDE_PITCH0", 0)) p.pitch = 0;  // tuning builds only: every row is row 0 (compute-only timing)
-#endif
+  p.bands = 1; p.band_rows = N; p.act = act;
   for (int l = 0; l < 4; ++l)
     for (int t = 0; t < 9; ++t) p.w[l][t] = (l < n_layers) ? w_host[l * 9 + t] : 0.0f;
   switch (n_layers) {

@@ -11,9 +11,45 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import ACT, AGG, BC_MASK, BC_SQUARE, IterateDesc, check, lib
+from ._lib import ACT, AGG, BC_MASK, BC_SQUARE, IterateDesc, check
 
 _workspaces = {}
+
+
+class _Ptr(ctypes.c_void_p):
+    """A raw device pointer that remembers which device it lives on (for the same-device check below)."""
+    device = None
+
+
+class _Guarded(object):
+    """The C library launches on the process's CURRENT device (kernels, capture streams, occupancy queries),
+    whereas the reference's torch ops run wherever their tensors live.  Every C-ABI call therefore goes through
+    this proxy: it makes the device of the stream argument current for the duration of the call and refuses
+    tensors that live on different devices (the library would fail with "invalid resource handle" or, worse,
+    touch the wrong memory)."""
+
+    def __getattr__(self, name):
+        fn = getattr(_lib.lib(), name)
+
+        def call(*args):
+            dev = getattr(args[-1], "device", None) if args else None
+            if dev is None or dev.type != "cuda":
+                return fn(*args)
+            for a in args:
+                d = getattr(a, "device", None)
+                if d is not None and d != dev:
+                    raise RuntimeError("%s: tensors on different devices (%s vs %s)" % (name, d, dev))
+            with torch.cuda.device(dev):
+                return fn(*args)
+
+        return call
+
+
+_guarded = _Guarded()
+
+
+def lib():
+    return _guarded
 
 
 def _require(t, name):
@@ -31,12 +67,19 @@ def _opt(t, name):
 
 
 def _ptr(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    p = _Ptr(t.data_ptr())
+    p.device = t.device
+    return p
 
 
 def _stream(t):
+    """The current stream of t's device, tagged with that device (see _Guarded); None on the emulator."""
     if t.is_cuda:
-        return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        p = _Ptr(torch.cuda.current_stream(t.device).cuda_stream)
+        p.device = t.device
+        return p
     return None
 
 
@@ -265,7 +308,8 @@ class ConvUnrollFn(torch.autograd.Function):
         tape = torch.empty((k, B, N, N), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_CONV_FWD, B, N, kind, L, 0, 0, 0), x)
-        wh = None if w_host is None else ctypes.c_void_p(np.ascontiguousarray(w_host, np.float32).ctypes.data)
+        w_host_c = None if w_host is None else np.ascontiguousarray(w_host, np.float32)  # stays alive over the call
+        wh = None if w_host_c is None else ctypes.c_void_p(w_host_c.ctypes.data)
         check(lib().npde_conv_iterate_tape(_ptr(x), _ptr(bc), kind, _ptr(f), _ptr(wd), wh, L, _act(act), int(k),
                                            _ptr(tape), _ptr(y), B, N, ws, wsb, _stream(x)), "npde_conv_iterate_tape")
         ctx.save_for_backward(tape, bc, f if f is not None else x.new_empty(0), wd)
@@ -403,6 +447,13 @@ def iterate(iterator, x, bc, f, k, *, w=None, w_host=None, n_layers=0, pre=0, po
     w = None if w is None else _require(w, "w").reshape(-1)
     B, N, _ = x.shape
     kind = bc_kind(x, bc)
+    for name, t in (("bc", bc), ("f", f), ("gt", gt), ("w", w)):
+        if t is not None and t.device != x.device:
+            raise RuntimeError("iterate: %s is on %s, x on %s" % (name, t.device, x.device))
+    if out is not None:  # its pointer goes to the library as is: anything else would be a silent stray write
+        if not isinstance(out, torch.Tensor) or out.dtype != torch.float32 or out.shape != x.shape or \
+                out.device != x.device or not out.is_contiguous():
+            raise ValueError("iterate: out must be a contiguous float32 tensor with x's shape and device")
     y = torch.empty_like(x) if out is None else out
     e2 = torch.empty((k, B), dtype=torch.float32, device=x.device) if want_l2 else None
     efd = torch.empty((k + 1, B), dtype=torch.float32, device=x.device) if want_fd else None
