@@ -1,26 +1,33 @@
 #!/usr/bin/env python
 """bench.py -- cell-updates/s of the fused Jacobi + learned-H iterator at 1025^2.
 
-    python bench.py --gpus N --steps K --warmup W           # this repo's CUDA path
-    python bench.py --impl reference ...                     # CPU baseline arm (oracle port, all host threads)
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference ...                      # CPU arm: the UNMODIFIED reference on the host cores
+    python bench.py --scaling weak ...                        # 64 problems PER GPU instead of 64 in total
+    python bench.py --workload train ...                      # BASELINE config 4 as the headline line
 
-Workload (BASELINE.json configs[2]): ConvIterator (3-layer H, clamp) + Jacobi on the
-square Dirichlet problem, N = 1025, batch 64 PER GPU (weak scaling: independent
-problems, no data-path collective), f = None, synthetic random fields / bc /
-weights.  One "step" = one pass of the reference's solve loop body
-(generation.py:86-93): 100 applications of Phi_H followed by one fd_error
-residual check.  1 cell-update = Phi_H applied to one grid cell (all B*N^2 cells
-count), so a step is B*N^2*100 cell-updates.
+Workload (BASELINE.json configs[2]): ConvIterator (3-layer H, clamp) + Jacobi on the square Dirichlet problem,
+N = 1025, batch 64, f = None, synthetic random fields / bc / weights.  One "step" = one pass of the reference's solve
+loop body (generation.py:86-93): 100 applications of Phi_H followed by one fd_error residual check.
+1 cell-update = Phi_H applied to one grid cell (all B*N^2 cells count), so a step is B*N^2*100 cell-updates.
 
-value : device-resident throughput (inputs already in HBM), CUDA events.
-e2e   : same step through the public API with HOST buffers: pinned x, bc copied
-        host->device, iterate + residual, solution and residual copied back.
-Inputs (269 MB per field) exceed the 126 MB L2, so no explicit flush is needed.
+Multi-GPU: the problems of the batch are independent, so ranks take contiguous batch slices and no collective is on
+the data path.  Default `--scaling strong` is configs[2] as written (64 problems in TOTAL: 64/N per GPU); the line
+also carries the weak-scaling figure (64 per GPU) under "weak_scaling" when N > 1.  The training step of configs[3]
+(512 x 257^2 in total, K = 20 unrolled steps, Adam, NCCL all-reduce of the weight gradient) is measured in the
+same run under "train_step", so that the scaling record contains a real collective.
+
+value : device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
+e2e   : same step through the public API with HOST buffers: pinned x, bc copied host->device, iterate + residual,
+        solution and residual copied back -- all inside the timed region.
+Inputs at N = 1: 269 MB per field > 126 MB L2, no flush needed; for smaller per-GPU batches (strong scaling at
+N >= 4) the fields fit the L2 and `config.l2` says so: that is the state a solver loop runs in.
 """
 import argparse
 import importlib
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -32,13 +39,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GRID_N = 1025
-BATCH_PER_GPU = 64
+BATCH = 64            # configs[2]: batch 64
 N_LAYERS = 3
 ACT = "clamp"
-INNER = 100  # iterations per step (generation.py:89 checks the residual every 100 iterations)
+INNER = 100           # iterations per step (generation.py:89 checks the residual every 100 iterations)
 METRIC = "cell-updates/s (Jacobi+learned H, Conv3) at 1025^2"
 UNIT = "cell-updates/s"
 ALGO_BYTES_PER_CELL_UPDATE = 8.0  # read x + write y, fp32 (square, f = None)
+TRAIN_N, TRAIN_BATCH, TRAIN_K = 257, 512, 20  # configs[3]
 
 
 def peaks():
@@ -49,7 +57,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_problem(B, N, seed):
+def make_problem(B, N, seed, n_layers=N_LAYERS):
     rng = np.random.RandomState(seed)
     bc = rng.rand(B, 4).astype(np.float32)
     x = rng.rand(B, N, N).astype(np.float32)
@@ -57,12 +65,23 @@ def make_problem(B, N, seed):
     x[:, -1, :] = bc[:, 1:2]
     x[:, :, 0] = bc[:, 2:3]
     x[:, :, -1] = bc[:, 3:4]
-    w = ((rng.rand(N_LAYERS, 3, 3) - 0.5) * 0.2).astype(np.float32)
+    w = ((rng.rand(n_layers, 3, 3) - 0.5) * 0.2).astype(np.float32)
     return x, bc, w
 
 
+def workload_config(world, scaling, per_gpu):
+    """Identical in both arms (ours / reference): the workload, not how an arm samples it."""
+    field_mb = per_gpu * GRID_N * GRID_N * 4 / 1e6
+    l2 = ("inputs (%.0f MB per field) exceed the 126 MB L2" % field_mb) if field_mb > 126 else \
+        ("%.0f MB per field: the ping-pong fields stay L2-resident between launches, as in a solver loop" % field_mb)
+    return {"workload": "conv3_jacobi_square_1025_b64", "grid": GRID_N, "global_batch": per_gpu * world,
+            "batch_per_gpu": per_gpu, "n_layers": N_LAYERS, "activation": ACT, "iterations_per_step": INNER,
+            "step": "100 x Phi_H + fd_error", "scaling": scaling, "l2": l2,
+            "parallelism": "batch-sharded x%d, no collective on the data path" % world}
+
+
 class ClockSampler(object):
-    """SM clock and throttle reasons sampled through NVML every 5 ms while the timed region runs
+    """SM clock and throttle reasons sampled through NVML every few ms while the timed region runs
     (nvidia-smi's own loop mode is too slow for a region of ~100 ms)."""
 
     def __init__(self, index):
@@ -115,10 +134,31 @@ class ClockSampler(object):
                 "samples": len(self.sm), "reasons": sorted(self.reasons)}
 
 
-def cpu_oracle_throughput(x, bc, w, budget_s):
+# ------------------------------------------------------------------------------------------- CPU arms --
+def reference_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "models", "iterators", "conv_iterator.py"))
+
+
+def time_reference(B, N, warmup, steps, threads=0):
+    """The UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build) in a subprocess without GPUs:
+    seconds per Phi_H application of the whole batch.  See oracle/ref_arm.py."""
+    env = dict(os.environ)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):  # torchrun exports OMP_NUM_THREADS=1: use all host cores
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_arm.py"), "--B", str(B), "--N", str(N), "--layers",
+           str(N_LAYERS), "--act", ACT, "--warmup", str(warmup), "--steps", str(steps), "--threads", str(threads)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
+    if r.returncode != 0:
+        raise RuntimeError("reference arm failed: " + r.stderr[-800:])
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def time_port(x, bc, w, budget_s):
     """Oracle port (oracle/npde_oracle.c, OpenMP over the batch) on the host cores: bounded sample."""
     import oracle
     oracle.build()
+    cores = oracle.set_threads(os.cpu_count() or 1)
     t0 = time.perf_counter()
     y, _, _ = oracle.iterate("conv", x, bc, None, w, ACT, 1)  # warm-up, also sizes the sample
     t1 = time.perf_counter() - t0
@@ -127,40 +167,198 @@ def cpu_oracle_throughput(x, bc, w, budget_s):
     oracle.iterate("conv", y, bc, None, w, ACT, k)
     dt = time.perf_counter() - t0
     B, N, _ = x.shape
-    return B * N * N * k / dt, k, dt
+    return B * N * N * k / dt, k, dt, cores
 
 
 def run_reference(args):
+    """CPU arm of the driver: the reference's own PyTorch CPU path (all host threads) on the same workload; each
+    step is ONE of the 100 Phi_H applications of a step on the whole 64 x 1025^2 batch (a bounded sample)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    import oracle
-    oracle.build()
-    cores = oracle.set_threads(os.cpu_count() or 1)  # all host cores, whatever OMP_NUM_THREADS torchrun exported
-    B, N = BATCH_PER_GPU, GRID_N
-    x, bc, w = make_problem(B, N, 666)
-    cur = x
-    for _ in range(args.warmup):
-        cur, _, _ = oracle.iterate("conv", cur, bc, None, w, ACT, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cur, _, _ = oracle.iterate("conv", cur, bc, None, w, ACT, 1)
-    dt = time.perf_counter() - t0
-    value = B * N * N * args.steps / dt
-    sample = "per step: 1 of the %d Phi_H iterations of a step, on the full %dx%d^2 batch" % (INNER, B, N)
+    per_gpu = BATCH if args.scaling == "weak" else max(BATCH // world, 1)
+    B, N = BATCH, GRID_N  # the CPU arm always runs the 64-problem batch of configs[2] (per cell-update figure)
+    sample = "per step: 1 of the %d Phi_H applications of a step, on the whole %d x %d^2 batch" % (INNER, B, N)
+    if reference_available():
+        res = time_reference(B, N, max(args.warmup, 1), args.steps)
+        secs = res["seconds_per_iteration"]
+        value = B * N * N * len(secs) / sum(secs)
+        ms = sum(secs) / len(secs) * 1e3
+        kind, cores = "reference", res["threads"]
+        how = "models/iterators/conv_iterator.py ConvIterator.forward, torch %s CPU, %d threads of %d cores" % (
+            res["torch"], res["threads"], res["cores"])
+    else:
+        x, bc, w = make_problem(B, N, 666)
+        import oracle
+        oracle.build()
+        cores = oracle.set_threads(os.cpu_count() or 1)
+        cur = x
+        for _ in range(args.warmup):
+            cur, _, _ = oracle.iterate("conv", cur, bc, None, w, ACT, 1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cur, _, _ = oracle.iterate("conv", cur, bc, None, w, ACT, 1)
+        dt = time.perf_counter() - t0
+        value, ms, kind = B * N * N * args.steps / dt, dt / args.steps * 1e3, "port"
+        how = "oracle/npde_oracle.c (C/OpenMP restatement; oracle/_ref is not staged on this box)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "conv3_jacobi_square_1025_b64", "grid": N, "batch_per_gpu": B, "n_layers": N_LAYERS,
-                   "activation": ACT, "iterations_per_step": 1, "note": "CPU arm: oracle port of the reference "
-                   "iterator (the reference itself is Python/PyTorch and cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world, args.scaling, per_gpu),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "how": how},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------- GPU arm --
+def pin_to_local_cpus(local, n_local):
+    """Bind this rank to the CPUs next to its GPU (NVML's ideal affinity) before any pinned buffer is allocated, so
+    that the staging buffers are first-touched NUMA-locally; if NVML reports the same set for every GPU (one NUMA
+    node, as on the pool's boxes) split that set evenly between the local ranks instead."""
+    info = {"method": "none"}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        ideal = [i * 64 + bit for i, wd in enumerate(words) for bit in range(64) if (int(wd) >> bit) & 1]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in ideal if c in allowed] or allowed
+        if n_local > 1 and len(cpus) >= 2 * n_local:
+            share = len(cpus) // n_local
+            cpus = cpus[local * share:(local + 1) * share]
+            info["method"] = "nvml ideal set split over %d local ranks" % n_local
+        else:
+            info["method"] = "nvml ideal set"
+        os.sched_setaffinity(0, cpus)
+        info["cpus"] = "%d-%d (%d)" % (cpus[0], cpus[-1], len(cpus))
+    except Exception as exc:  # noqa: BLE001 -- affinity is an optimisation, never a failure
+        info["error"] = repr(exc)[:120]
+    return info
+
+
+class ConvWorkload(object):
+    """configs[2] on one rank: per_gpu problems of 1025^2, Conv3 / clamp, device-resident and end-to-end steps."""
+
+    def __init__(self, npde, torch, dev, rank, per_gpu):
+        self.npde, self.torch, self.dev, self.B, self.N = npde, torch, dev, per_gpu, GRID_N
+        x_np, bc_np, w_np = make_problem(BATCH, GRID_N, 666)  # the 64 problems of the job; this rank's slice
+        lo = (rank * per_gpu) % BATCH
+        sel = [(lo + i) % BATCH for i in range(per_gpu)]
+        self.x_np, self.bc_np, self.w_np = x_np[sel], bc_np[sel], w_np
+        self.it = npde.ConvIterator(ACT, N_LAYERS).to(dev)
+        with torch.no_grad():
+            for l, wl in zip(self.it.layers, w_np):
+                l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+        self.x_host = torch.from_numpy(self.x_np).pin_memory()
+        self.bc_host = torch.from_numpy(self.bc_np).pin_memory()
+        self.out_host = torch.empty_like(self.x_host).pin_memory()
+        self.err_host = torch.empty(per_gpu).pin_memory()
+        self.x_dev = self.x_host.to(dev)
+        self.bc_dev = self.bc_host.to(dev)
+        self.out_dev = torch.empty_like(self.x_dev)
+        self.units_per_step = float(per_gpu) * self.N * self.N * INNER
+        # end to end: consecutive steps are software-pipelined on three streams with double-buffered device tensors
+        # -- H2D of step s+1 and D2H of step s-1 overlap the compute of step s -- which is how a caller feeding a
+        # stream of batches through the public API (every call takes the current CUDA stream) would drive it.
+        self.copy_in, self.copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        self.x_bufs = [torch.empty_like(self.x_dev) for _ in range(2)]
+        self.bc_bufs = [torch.empty_like(self.bc_dev) for _ in range(2)]
+        self.out_bufs = [torch.empty_like(self.x_dev) for _ in range(2)]
+        self.err_bufs = [torch.empty(per_gpu, device=dev) for _ in range(2)]
+
+    def step_resident(self):
+        y, _, _ = self.it.iterate(self.x_dev, self.bc_dev, None, INNER, out=self.out_dev)
+        return self.npde.utils.fd_error(y, self.bc_dev, None)
+
+    def run_e2e(self, n_steps, compute=True):
+        torch, dev = self.torch, self.dev
+        stream = torch.cuda.current_stream(dev)
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        comp_done = [torch.cuda.Event() for _ in range(2)]
+        d2h_done = [torch.cuda.Event() for _ in range(2)]
+        for s_ in range(n_steps):
+            i = s_ % 2
+            with torch.cuda.stream(self.copy_in):
+                if s_ >= 2:
+                    self.copy_in.wait_event(comp_done[i])  # step s-2 has consumed this input buffer
+                self.x_bufs[i].copy_(self.x_host, non_blocking=True)
+                self.bc_bufs[i].copy_(self.bc_host, non_blocking=True)
+                h2d_done[i].record(self.copy_in)
+            stream.wait_event(h2d_done[i])
+            if s_ >= 2:
+                stream.wait_event(d2h_done[i])  # step s-2's result has left this output buffer
+            if compute:
+                y, _, _ = self.it.iterate(self.x_bufs[i], self.bc_bufs[i], None, INNER, out=self.out_bufs[i])
+                self.err_bufs[i].copy_(self.npde.utils.fd_error(y, self.bc_bufs[i], None))
+            comp_done[i].record(stream)
+            with torch.cuda.stream(self.copy_out):
+                self.copy_out.wait_event(comp_done[i])
+                self.out_host.copy_(self.out_bufs[i], non_blocking=True)
+                self.err_host.copy_(self.err_bufs[i], non_blocking=True)
+                d2h_done[i].record(self.copy_out)
+        torch.cuda.synchronize()  # the caller holds every solution and residual now
+
+    def h2d_bytes(self):
+        return int(self.x_host.numel() * 4 + self.bc_host.numel() * 4)
+
+    def d2h_bytes(self):
+        return int(self.out_host.numel() * 4 + self.err_host.numel() * 4)
+
+
+def train_opt(world_batch):
+    import argparse as ap
+    return ap.Namespace(iterator="conv", activation=ACT, conv_n_layers=N_LAYERS, mg_n_layers=3, mg_pre_smoothing=2,
+                        mg_post_smoothing=2, cg_n_iters=4, geometry="square", is_train=True, optimizer="adam",
+                        lr_init=1e-3, max_iter_steps=TRAIN_K, max_iter_steps_from_gt=TRAIN_K, lambda_gt=0.0,
+                        batch_size=world_batch)
+
+
+def measure_train(npde, torch, dist, dev, rank, world, steps, warmup, barrier, max_over_ranks):
+    """configs[3]: one training step of HeatModel (models/heat_model.py:31-75) on 512 x 257^2 problems in total
+    (512 / N per GPU), N_unroll ~ U{1..20} drawn from the same seed on every rank, Adam, the 27-float weight gradient
+    and the loss all-reduced over NCCL.  Two variants: the reference's last-step gradient, and backprop through all
+    unrolled steps.  ms per step = CUDA events over `steps` steps, max over ranks."""
+    per_gpu = max(TRAIN_BATCH // world, 1)
+    rng = np.random.RandomState(4000 + rank)
+    bc = rng.rand(per_gpu, 4).astype(np.float32)
+    x = rng.rand(per_gpu, TRAIN_N, TRAIN_N).astype(np.float32)
+    xd, bcd = torch.from_numpy(x).to(dev), torch.from_numpy(bc).to(dev)
+    xd = npde.utils.set_boundary(xd, bcd)
+    gt, _, _ = npde.JacobiIterator().iterate(xd, bcd, None, 400)  # a smoother field as the regression target
+    out = {"global_batch": per_gpu * world, "batch_per_gpu": per_gpu, "grid": TRAIN_N, "max_unroll": TRAIN_K,
+           "optimizer": "adam", "allreduce": ("nccl, %d floats + loss per step" % (9 * N_LAYERS)) if world > 1 else None,
+           "cell_updates_per_step_mean": per_gpu * world * TRAIN_N * TRAIN_N * (TRAIN_K + 1) / 2.0}
+    for key, full in (("last_step_grad", False), ("full_bptt", True)):
+        model = npde.HeatModel(train_opt(per_gpu * world), world=True if world > 1 else None, full_bptt=full)
+        model.iterator.to(dev)
+        with torch.no_grad():
+            rs = np.random.RandomState(7)
+            for l in model.iterator.layers:
+                l.weight.copy_(torch.from_numpy(((rs.rand(3, 3) - 0.5) * 0.2).astype(np.float32)).view(1, 1, 3, 3))
+        np.random.seed(1234)  # the unroll lengths must agree on every rank
+        for _ in range(warmup):
+            model.train(xd, gt, bcd, None)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            model.train(xd, gt, bcd, None)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+        out[key] = {"ms_per_step": ms, "steps": steps}
+        if world > 1:  # the replicas must stay bit-identical
+            flat = torch.cat([p.detach().reshape(-1) for p in model.iterator.parameters()])
+            ref = flat.clone()
+            dist.broadcast(ref, 0)
+            out[key]["replicas_identical"] = bool(torch.equal(flat, ref))
+    return out
 
 
 def run_gpu(args):
@@ -172,68 +370,15 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_local = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a GPU (use --impl reference for the CPU arm)")
+    affinity = pin_to_local_cpus(local, n_local) if world > 1 else {"method": "single rank: not pinned"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    B, N = BATCH_PER_GPU, GRID_N
-    x_np, bc_np, w_np = make_problem(B, N, 666 + rank)
-    it = npde.ConvIterator(ACT, N_LAYERS).to(dev)
-    with torch.no_grad():
-        for l, wl in zip(it.layers, w_np):
-            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
-    x_host = torch.from_numpy(x_np).pin_memory()
-    bc_host = torch.from_numpy(bc_np).pin_memory()
-    out_host = torch.empty_like(x_host).pin_memory()
-    err_host = torch.empty(B).pin_memory()
-    x_dev = x_host.to(dev)
-    bc_dev = bc_host.to(dev)
-    out_dev = torch.empty_like(x_dev)
-    units_per_step = float(B) * N * N * INNER
-
-    def step_resident():
-        y, _, _ = it.iterate(x_dev, bc_dev, None, INNER, out=out_dev)
-        return npde.utils.fd_error(y, bc_dev, None)
-
-    # end to end: every step copies its inputs from pinned host memory and its result (solution + residual)
-    # back.  Consecutive steps are software-pipelined on three streams with double-buffered device tensors --
-    # H2D of step s+1 and D2H of step s-1 overlap the compute of step s -- which is how a caller feeding a stream
-    # of batches through the public API (every call takes the current CUDA stream) would drive it.
-    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-    x_bufs = [torch.empty_like(x_dev) for _ in range(2)]
-    bc_bufs = [torch.empty_like(bc_dev) for _ in range(2)]
-    out_bufs = [torch.empty_like(x_dev) for _ in range(2)]
-    err_bufs = [torch.empty(B, device=dev) for _ in range(2)]
-
-    def run_e2e(n_steps):
-        compute = torch.cuda.current_stream(dev)
-        h2d_done = [torch.cuda.Event() for _ in range(2)]
-        comp_done = [torch.cuda.Event() for _ in range(2)]
-        d2h_done = [torch.cuda.Event() for _ in range(2)]
-        for s_ in range(n_steps):
-            i = s_ % 2
-            with torch.cuda.stream(copy_in):
-                if s_ >= 2:
-                    copy_in.wait_event(comp_done[i])  # step s-2 has consumed this input buffer
-                x_bufs[i].copy_(x_host, non_blocking=True)
-                bc_bufs[i].copy_(bc_host, non_blocking=True)
-                h2d_done[i].record(copy_in)
-            compute.wait_event(h2d_done[i])
-            if s_ >= 2:
-                compute.wait_event(d2h_done[i])  # step s-2's result has left this output buffer
-            y, _, _ = it.iterate(x_bufs[i], bc_bufs[i], None, INNER, out=out_bufs[i])
-            err_bufs[i].copy_(npde.utils.fd_error(y, bc_bufs[i], None))
-            comp_done[i].record(compute)
-            with torch.cuda.stream(copy_out):
-                copy_out.wait_event(comp_done[i])
-                out_host.copy_(out_bufs[i], non_blocking=True)
-                err_host.copy_(err_bufs[i], non_blocking=True)
-                d2h_done[i].record(copy_out)
-        torch.cuda.synchronize()  # the caller holds every solution and residual now
 
     def barrier():
         if world > 1:
@@ -247,47 +392,73 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput ------------------------------------------------------
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            step_resident()
+    def measure_resident(wl, steps, warmup, sample_clocks):
+        """`steps` device-resident steps: whole-job ms (max over ranks), average launch of the fused kernel, clocks."""
+        for _ in range(warmup):
+            wl.step_resident()
         sampler = ClockSampler(local)
-        if rank == 0:
+        if sample_clocks and rank == 0:
             sampler.start()
-        launches0 = lib.npde_debug_launch_count()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.npde_debug_launch_count()
         barrier()
         e0.record()
         for a, b in ev:
             a.record()
-            y, _, _ = it.iterate(x_dev, bc_dev, None, INNER, out=out_dev)
+            y, _, _ = wl.it.iterate(wl.x_dev, wl.bc_dev, None, INNER, out=wl.out_dev)
             b.record()
-            npde.utils.fd_error(y, bc_dev, None)
+            npde.utils.fd_error(y, wl.bc_dev, None)
         e1.record()
         barrier()
         launches = lib.npde_debug_launch_count() - launches0
         total_ms = max_over_ranks(e0.elapsed_time(e1))
-        kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / (args.steps * INNER)  # avg launch of the fused kernel
-        clocks = sampler.stop() if rank == 0 else None
+        kernel_ms = sum(a.elapsed_time(b) for a, b in ev) / (steps * INNER)  # avg launch of the fused kernel
+        clocks = sampler.stop() if (sample_clocks and rank == 0) else None
+        return total_ms, kernel_ms, int(launches), clocks
 
-        # ---- end to end through the public API with host buffers ---------------------------
-        run_e2e(max(args.warmup, 2))
+    def measure_e2e(wl, steps, warmup, compute=True):
+        wl.run_e2e(max(warmup, 2), compute)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        run_e2e(args.steps)
+        wl.run_e2e(steps, compute)
         e1.record()
         barrier()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+        return max_over_ranks(e0.elapsed_time(e1))
 
-    value = units_per_step * args.steps * world / (total_ms * 1e-3)
-    e2e_value = units_per_step * args.steps * world / (e2e_ms * 1e-3)
+    if args.scaling == "strong" and BATCH % world:
+        raise RuntimeError("strong scaling shards %d problems: --gpus must divide it" % BATCH)
+    per_gpu = BATCH if args.scaling == "weak" else BATCH // world
+    with torch.no_grad():
+        wl = ConvWorkload(npde, torch, dev, rank, per_gpu)
+        total_ms, kernel_ms, launches, clocks = measure_resident(wl, args.steps, args.warmup, True)
+        e2e_ms = measure_e2e(wl, args.steps, args.warmup)
+        copy_ms = measure_e2e(wl, max(args.steps // 3, 3), 2, compute=False)  # what the host links deliver alone
+        copy_steps = max(args.steps // 3, 3)
+        weak = None
+        if world > 1 and args.scaling == "strong":
+            wlw = ConvWorkload(npde, torch, dev, rank, BATCH)
+            ws = max(args.steps // 3, 3)
+            w_ms, w_kernel_ms, _, _ = measure_resident(wlw, ws, 3, False)
+            w_e2e = measure_e2e(wlw, ws, 2)
+            weak = {"batch_per_gpu": BATCH, "global_batch": BATCH * world, "steps": ws,
+                    "value": wlw.units_per_step * ws * world / (w_ms * 1e-3),
+                    "e2e_value": wlw.units_per_step * ws * world / (w_e2e * 1e-3),
+                    "avg_launch_ms": w_kernel_ms, "unit": UNIT}
+            del wlw
+    train = None
+    if not args.no_train:
+        train = measure_train(npde, torch, dist, dev, rank, world, max(args.steps // 2, 5), 3, barrier, max_over_ranks)
+
+    value = wl.units_per_step * args.steps * world / (total_ms * 1e-3)
+    e2e_value = wl.units_per_step * args.steps * world / (e2e_ms * 1e-3)
     peak, peak_src = peaks()
-    algo_bytes = ALGO_BYTES_PER_CELL_UPDATE * B * N * N  # per launch of the fused kernel (one Phi_H over the batch)
+    algo_bytes = ALGO_BYTES_PER_CELL_UPDATE * per_gpu * GRID_N * GRID_N  # per launch of the fused kernel
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_conv3_1025_b64.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and per_gpu == BATCH:
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
 
@@ -296,51 +467,110 @@ def run_gpu(args):
             dist.destroy_process_group()
         return 0
 
+    config = workload_config(world, args.scaling, per_gpu)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "conv3_jacobi_square_1025_b64", "grid": N, "batch_per_gpu": B, "global_batch": B * world,
-                   "n_layers": N_LAYERS, "activation": ACT, "iterations_per_step": INNER,
-                   "step": "100 x Phi_H (npde_iterate) + fd_error", "l2": "inputs (269 MB/field) exceed the 126 MB L2",
-                   "parallelism": "batch-sharded x%d, no collective" % world},
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": config,
         "value_per_gpu": value / world,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                 "pipeline": "3 streams, double-buffered: H2D(s+1) | compute(s) | D2H(s-1); every step's copies are "
                             "inside the timed region",
-                "h2d_bytes_per_step": int(x_host.numel() * 4 + bc_host.numel() * 4),
-                "d2h_bytes_per_step": int(out_host.numel() * 4 + err_host.numel() * 4)},
-        "gpu_launches": int(launches),
+                "h2d_bytes_per_step": wl.h2d_bytes(), "d2h_bytes_per_step": wl.d2h_bytes(),
+                "copies_only_ms_per_step": copy_ms / copy_steps,
+                "copies_only_note": "the same pipeline without the compute: the ceiling the host links set",
+                "cpu_affinity": affinity},
+        "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_conv_wide<3,clamp,no-f>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k_conv_wide<3,clamp,no-f>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": kernel_ms,
-                     "cell_updates_per_s_kernel": B * N * N / (kernel_ms * 1e-3)},
+                     "avg_launch_note": "CUDA events around each 100-launch npde_iterate call / 100: includes the two "
+                                        "layout passes (pack, unpack) of the call",
+                     "cell_updates_per_s_kernel": per_gpu * GRID_N * GRID_N / (kernel_ms * 1e-3)},
     }
+    if weak is not None:
+        line["weak_scaling"] = weak
+    if train is not None:
+        line["train_step"] = train
     if world == 1 and not args.no_ttr:
         # BASELINE's second metric, "time-to-1e-6 residual", on the same batch shape: plain Jacobi from the reference's
         # 'avg' start (test.py:115) until max_b fd_error < 1e-6, checked every 2000 iterations (generation.py:72-99
         # with the tolerance tightened); identical iteration count to the reference by construction (bit-identical
         # iterates, max-norm criterion).  Outside every timed region above.
-        xs = npde.utils.initialize(x_dev.clone(), bc_dev, "avg")
+        xs = npde.utils.initialize(wl.x_dev.clone(), wl.bc_dev, "avg")
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        res = npde.utils.solve_to_tolerance(npde.JacobiIterator(), xs, bc_dev, None, tol=1e-6, check_every=2000,
+        res = npde.utils.solve_to_tolerance(npde.JacobiIterator(), xs, wl.bc_dev, None, tol=1e-6, check_every=2000,
                                             max_iters=args.ttr_max_iters)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         line["time_to_residual"] = {"value": dt, "unit": "s", "tolerance": 1e-6, "iterator": "jacobi", "init": "avg",
                                     "iterations": int(res["iterations"]), "converged": bool(res["converged"]),
                                     "final_residual": float(res["history"][-1][1]),
-                                    "cell_updates_per_s": B * N * N * float(res["iterations"]) / dt}
+                                    "cell_updates_per_s": per_gpu * GRID_N * GRID_N * float(res["iterations"]) / dt}
     if world == 1 and not args.no_cpu:
-        import oracle
-        oracle.build()
-        cores = oracle.set_threads(os.cpu_count() or 1)
-        v, k, dt = cpu_oracle_throughput(x_np, bc_np, w_np, args.cpu_budget)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d Phi_H iterations on the full %dx%d^2 batch (%.1f s)" % (k, B, N, dt)}
+        x64, bc64, w64 = make_problem(BATCH, GRID_N, 666)
+        sample = "%d Phi_H applications on the whole %d x %d^2 batch"
+        if reference_available():
+            res = time_reference(BATCH, GRID_N, 1, 3)
+            secs = res["seconds_per_iteration"]
+            line["cpu_baseline"] = {"value": BATCH * GRID_N * GRID_N * len(secs) / sum(secs), "unit": UNIT,
+                                    "cores": res["threads"], "kind": "reference",
+                                    "sample": (sample % (len(secs), BATCH, GRID_N)) + " (%.1f s)" % sum(secs),
+                                    "how": "unmodified reference ConvIterator.forward, torch %s CPU" % res["torch"]}
+        v, k, dt, cores = time_port(x64, bc64, w64, args.cpu_budget)
+        port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": (sample % (k, BATCH, GRID_N)) + " (%.1f s)" % dt}
+        if "cpu_baseline" in line:
+            line["cpu_baseline_port"] = port
+        else:
+            line["cpu_baseline"] = port
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_train_line(args):
+    """--workload train: configs[3] as the headline line (metric: cell-updates/s inside the training step)."""
+    import torch
+    import torch.distributed as dist
+    npde = importlib.import_module("neural-pde-solver_b200")
+    npde._lib.lib()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    tr = measure_train(npde, torch, dist, dev, rank, world, args.steps, max(args.warmup, 3), barrier, max_over_ranks)
+    if rank == 0:
+        ms = tr["full_bptt"]["ms_per_step"]
+        line = {"metric": "cell-updates/s inside the training step (forward, backprop through all unrolled steps)",
+                "value": 2.0 * tr["cell_updates_per_step_mean"] / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "train_conv3_257_b512_k20", "grid": TRAIN_N, "global_batch": tr["global_batch"],
+                           "max_unroll": TRAIN_K, "optimizer": "adam",
+                           "parallelism": "dp%d, NCCL all-reduce of %d floats" % (world, 9 * N_LAYERS)},
+                "train_step": tr}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -352,15 +582,21 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: 64 problems in total (configs[2] as written); weak: 64 per GPU")
+    ap.add_argument("--workload", default="solve", choices=["solve", "train"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-ttr", action="store_true", help="skip the time-to-1e-6-residual leg (about 7 s on a B200)")
+    ap.add_argument("--no-train", action="store_true", help="skip the configs[3] training-step leg")
     ap.add_argument("--ttr-max-iters", type=int, default=600000)
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--cpu-budget", type=float, default=10.0, help="seconds of CPU work for the port's cpu_baseline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train_line(args)
     return run_gpu(args)
 
 

@@ -54,6 +54,10 @@ extern "C" {
 #define NPDE_AGG_MAX 0  /* heat_utils.py:126-127 */
 #define NPDE_AGG_MEAN 1 /* heat_utils.py:128-129 */
 
+#define NPDE_INIT_ZERO 0   /* heat_utils.py:80-82,86-87 */
+#define NPDE_INIT_RANDOM 1 /* heat_utils.py:77-79,88-89: the uniform numbers come from the caller's generator */
+#define NPDE_INIT_AVG 2    /* heat_utils.py:90-91 (square domain; ignored on a mask geometry like the reference) */
+
 #define NPDE_IT_JACOBI 0    /* models/iterators/jacobi_iterator.py:7-20  */
 #define NPDE_IT_CONV 1      /* models/iterators/conv_iterator.py:8-54    */
 #define NPDE_IT_MULTIGRID 2 /* models/iterators/jacobi_iterator.py:23-78 */
@@ -87,6 +91,11 @@ size_t npde_workspace_bytes(int op, int B, int N, int bc_kind, int n_layers, int
 
 /* G: utils/heat_utils.py:44-59 set_boundary (in place on x). */
 int npde_set_boundary(float *x, const float *bc, int bc_kind, int B, int N, void *stream);
+
+/* utils/heat_utils.py:70-94 initialize, in place on x (B,N,N).  Square domain: interior <- 0 | rnd | mean(bc), ring
+ * untouched; mask geometry: x <- G(0 | rnd).  rnd: uniform numbers from the caller's generator, (B,N-2,N-2) on the
+ * square domain and (B,N,N) on a mask geometry; NULL unless mode == NPDE_INIT_RANDOM. */
+int npde_initialize(float *x, const float *bc, int bc_kind, int mode, const float *rnd, int B, int N, void *stream);
 
 /* utils/heat_utils.py:61-68 pad_boundary: xin (B,N-2,N-2) -> y (B,N,N) = G(zero_pad(xin)). */
 int npde_pad_boundary(const float *xin, const float *bc, int bc_kind, float *y, int B, int N, void *stream);

@@ -2,9 +2,9 @@
 
 There is exactly one implementation of every operator: the CUDA library.  If it
 has not been built, importing any operator raises; there is no CPU or PyTorch
-fallback.  (tests/ can point the binding at the host-compiled SIMT emulator of
-the same sources with ``_use_emulator`` -- test infrastructure, never used by
-the package itself.)
+fallback and no hook to install one.  (The CPU test-suite binds the
+host-compiled SIMT emulator build of the same sources by swapping the module
+state from tests/emu_backend.py -- the package itself never does.)
 """
 import ctypes
 import os
@@ -17,6 +17,7 @@ OK = 0
 BC_SQUARE, BC_MASK = 0, 1
 ACT = {"none": 0, "clamp": 1, "sigmoid": 2}
 AGG = {"max": 0, "mean": 1}
+INIT = {"zero": 0, "random": 1, "avg": 2}
 IT_JACOBI, IT_CONV, IT_MULTIGRID, IT_UNET = 0, 1, 2, 3
 WS_REDUCE, WS_CONV_FWD, WS_CONV_BWD, WS_MG, WS_UNET_FWD, WS_UNET_BWD, WS_CG, WS_CONV_BPTT, WS_ITERATE = 0, 1, 2, 3, 4, 5, 6, 7, 16
 MAX_CONV_LAYERS = 8
@@ -44,6 +45,7 @@ PROTOTYPES = {
     "npde_strerror": (ctypes.c_char_p, [_int]),
     "npde_workspace_bytes": (_size, [_int] * 8),
     "npde_set_boundary": (_int, [_vp, _vp, _int, _int, _int, _vp]),
+    "npde_initialize": (_int, [_vp, _vp, _int, _int, _vp, _int, _int, _vp]),
     "npde_pad_boundary": (_int, [_vp, _vp, _int, _vp, _int, _int, _vp]),
     "npde_fd_step": (_int, [_vp, _vp, _int, _vp, _vp, _int, _int, _vp]),
     "npde_fd_error": (_int, [_vp, _vp, _int, _vp, _int, _vp, _int, _int, _vp, _size, _vp]),
@@ -105,22 +107,10 @@ def lib():
     return _lib
 
 
-def is_emulated():
+def host_pointers():
+    """True iff the bound library takes HOST pointers -- only the emulator build that tests/emu_backend.py binds;
+    the product (libnpde_b200.so) never does, so every wrapper insists on CUDA tensors."""
     return _emulated
-
-
-def _use_emulator(path):
-    """TESTS ONLY: bind the host-compiled SIMT emulator build of the same CUDA sources
-    (tests/emu).  It takes host pointers, so CPU tensors are accepted while it is active."""
-    global _lib, _emulated
-    _lib = _bind(path)
-    _emulated = True
-
-
-def _use_cuda_library():
-    global _lib, _emulated
-    _lib = None
-    _emulated = False
 
 
 def check(code, where):

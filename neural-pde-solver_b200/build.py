@@ -86,32 +86,5 @@ def build_variant(name, defines, source="npde_stream.cu", extra_flags=()):
     return out
 
 
-def build_emulator(force=False):
-    """TEST INFRASTRUCTURE: the same .cu sources compiled for the host against
-    tests/emu/cuda_emu.h (a SIMT emulator) -> tests/emu/_build/libnpde_emu.so.
-    Used by the CPU test-suite to check index logic without a GPU; never loaded
-    by the product path."""
-    emu_dir = os.path.join(ROOT, "tests", "emu")
-    out = os.path.join(emu_dir, "_build", "libnpde_emu.so")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    if force or _stale(out, srcs + HEADERS + [os.path.join(emu_dir, "cuda_emu.h")]):
-        os.makedirs(os.path.dirname(out), exist_ok=True)
-        flags = ["g++", "-O2", "-std=c++17", "-DNPDE_EMU", "-ffp-contract=off", "-fPIC", "-I" + emu_dir]
-        objs = [os.path.join(os.path.dirname(out), os.path.basename(s_)[:-3] + ".emu.o") for s_ in srcs]
-
-        def cc(pair):
-            src, obj = pair
-            r = subprocess.run(flags + ["-x", "c++", "-c", src, "-o", obj], capture_output=True, text=True)
-            if r.returncode != 0:
-                raise RuntimeError("emulator build failed:\n" + r.stderr)
-
-        with ThreadPoolExecutor(max_workers=6) as ex:  # the translation units in parallel
-            list(ex.map(cc, zip(srcs, objs)))
-        r = subprocess.run(["g++", "-shared", "-o", out] + objs, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("emulator link failed:\n" + r.stderr)
-    return out
-
-
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -615,6 +615,15 @@ int npde_set_boundary(float *x, const float *bc, int bc_kind, int B, int N, void
   return npde::set_boundary(x, bc, bc_kind, B, N, S(stream));
 }
 
+int npde_initialize(float *x, const float *bc, int bc_kind, int mode, const float *rnd, int B, int N, void *stream) {
+  TRY(npde::check_common(x, x, B, N));
+  TRY(npde::check_bc(bc, bc_kind));
+  if (mode < NPDE_INIT_ZERO || mode > NPDE_INIT_AVG) return NPDE_ERR_ARG;
+  if (mode == NPDE_INIT_RANDOM && !rnd) return NPDE_ERR_NULL;
+  if (bc_kind == NPDE_BC_MASK && mode == NPDE_INIT_AVG) return NPDE_OK;  // heat_utils.py:77-83: no branch for 'avg'
+  return npde::initialize(x, bc, bc_kind, mode, rnd, B, N, S(stream));
+}
+
 int npde_pad_boundary(const float *xin, const float *bc, int bc_kind, float *y, int B, int N, void *stream) {
   TRY(npde::check_common(xin, y, B, N));
   TRY(npde::check_bc(bc, bc_kind));

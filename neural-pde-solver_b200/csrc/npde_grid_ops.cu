@@ -46,6 +46,29 @@ __global__ void k_pad_boundary(const float *__restrict__ xin, BcView bc, float *
   y[((size_t)b * N + i) * N + j] = npde_apply_G(v, bc, b, i, j, N);
 }
 
+// utils/heat_utils.py:70-94 initialize.  Square domain: the interior takes 0 / rnd / mean(bc) and the ring is left
+// alone (in place, :85-90); mean = (((top + bottom) + left) + right) * 0.25, ATen's order for a row of four.
+// Mask geometry: x <- G(0 | rnd) (:78-83).  rnd: (B,N-2,N-2) on the square domain, (B,N,N) on a mask geometry.
+__global__ void k_initialize(float *x, BcView bc, int mode, const float *__restrict__ rnd, int N) {
+  int j = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= N || j >= N) return;
+  const size_t o = ((size_t)b * N + i) * N + j;
+  if (bc.kind == NPDE_BC_MASK) {
+    const float v = mode == NPDE_INIT_RANDOM ? __ldg(rnd + o) : 0.0f;
+    x[o] = npde_apply_G(v, bc, b, i, j, N);
+    return;
+  }
+  if (i < 1 || i > N - 2 || j < 1 || j > N - 2) return;
+  float v = 0.0f;
+  if (mode == NPDE_INIT_RANDOM) {
+    v = __ldg(rnd + ((size_t)b * (N - 2) + (i - 1)) * (N - 2) + (j - 1));
+  } else if (mode == NPDE_INIT_AVG) {
+    const float *c = bc.bc + (size_t)b * 4;
+    v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__ldg(c), __ldg(c + 1)), __ldg(c + 2)), __ldg(c + 3)), 0.25f);
+  }
+  x[o] = v;
+}
+
 // ------------------------------------------------------------ Psi + G -----
 __global__ void k_fd_step(const float *__restrict__ x, BcView bc, const float *__restrict__ f,
                           float *__restrict__ y, int N) {
@@ -284,6 +307,13 @@ int set_boundary(float *x, const float *bc, int bc_kind, int B, int N, cudaStrea
   } else {
     NPDE_LAUNCH(k_set_boundary_square, dim3((4 * N + 127) / 128, B), dim3(128), 0, st, x, v, N);
   }
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int initialize(float *x, const float *bc, int bc_kind, int mode, const float *rnd, int B, int N, cudaStream_t st) {
+  BcView v{bc, bc_kind};
+  NPDE_LAUNCH(k_initialize, grid2d(N, N, B), dim3(TX, TY), 0, st, x, v, mode, rnd, N);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -46,6 +46,7 @@ int cg_step(const float *x, int n_iters, float *y, int B, int N, void *ws, cudaS
 int reduce_chunks(int N);
 size_t reduce_ws_bytes(int B, int N);
 int set_boundary(float *x, const float *bc, int bc_kind, int B, int N, cudaStream_t st);
+int initialize(float *x, const float *bc, int bc_kind, int mode, const float *rnd, int B, int N, cudaStream_t st);
 int pad_boundary(const float *xin, const float *bc, int bc_kind, float *y, int B, int N, cudaStream_t st);
 int fd_step_simple(const float *x, const float *bc, int bc_kind, const float *f, float *y, int B, int N,
                    cudaStream_t st);

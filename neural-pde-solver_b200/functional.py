@@ -55,7 +55,7 @@ def lib():
 def _require(t, name):
     if not isinstance(t, torch.Tensor):
         raise TypeError("%s must be a torch.Tensor" % name)
-    if not t.is_cuda and not _lib.is_emulated():
+    if not t.is_cuda and not _lib.host_pointers():
         raise RuntimeError("%s must be a CUDA tensor: npde-b200 has no CPU path" % name)
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
@@ -133,6 +133,19 @@ def set_boundary_(x, bc):
     bc = _require(bc, "bc")
     B, N, _ = xc.shape
     check(lib().npde_set_boundary(_ptr(xc), _ptr(bc), bc_kind(xc, bc), B, N, _stream(xc)), "npde_set_boundary")
+    return x
+
+
+def initialize_(x, bc, mode, rnd=None):
+    """utils/heat_utils.py:70-94 in place on a contiguous (B,N,N) tensor; rnd: the uniform numbers for 'random'."""
+    xc = _field(x)
+    if xc.data_ptr() != x.data_ptr():
+        raise ValueError("initialize_ needs a contiguous tensor")
+    bc = _require(bc, "bc")
+    rnd = _opt(rnd, "rnd")
+    B, N, _ = xc.shape
+    check(lib().npde_initialize(_ptr(xc), _ptr(bc), bc_kind(xc, bc), _lib.INIT[mode], _ptr(rnd), B, N, _stream(xc)),
+          "npde_initialize")
     return x
 
 

@@ -7,6 +7,7 @@ single C-ABI calls instead of F.conv2d / F.interpolate / slice-assign chains.
 """
 import torch
 
+from . import _lib
 from . import functional as F_
 from ._lib import IT_CONV, IT_JACOBI, IT_MULTIGRID, IT_UNET  # noqa: F401  (re-exported)
 # the reference's `utils` namespace also carries these (utils/__init__.py:1-5)
@@ -44,26 +45,43 @@ def pad_boundary(x, bc):
 
 
 def initialize(x, bc, initialization):
-    """utils/heat_utils.py:70-94 (runs once per batch, outside the hot loop: the random /
-    constant fill is plain torch, G is the kernel)."""
+    """utils/heat_utils.py:70-94.  One kernel (npde_initialize); the uniform numbers of 'random' come from torch's
+    generator, drawn on the CPU exactly like the reference does (`torch.rand(...)`, :89) so that a seeded run
+    starts from the same field.  The reference's drivers call this on the CPU batch the DataLoader produced,
+    before the model moves it to the GPU (train.py:29, test.py:31): host tensors are data preparation, not the
+    hot path, and take the reference's own torch expressions."""
     batch_size, image_size, _ = x.size()
-    if is_bc_mask(x, bc):
-        if initialization == 'random':
-            x = torch.rand_like(x)
-            x = set_boundary(x, bc)
+    mask = is_bc_mask(x, bc)
+    if not x.is_cuda and not _lib.host_pointers():
+        if mask:
+            if initialization in ('random', 'zero'):
+                x = torch.rand_like(x) if initialization == 'random' else torch.zeros_like(x)
+                x = x * (1 - bc[:, 1]) + bc[:, 0]  # heat_utils.py:51-53
         elif initialization == 'zero':
-            x = torch.zeros_like(x)
-            x = set_boundary(x, bc)
-    else:
-        if initialization == 'zero':
             x[:, 1:-1, 1:-1] = 0
         elif initialization == 'random':
-            x[:, 1:-1, 1:-1] = torch.rand(batch_size, image_size - 2, image_size - 2).to(x.device)
+            x[:, 1:-1, 1:-1] = torch.rand(batch_size, image_size - 2, image_size - 2)
         elif initialization == 'avg':
-            # mean of the four wall temperatures on the host: same rounding as the reference's CPU path
-            x[:, 1:-1, 1:-1] = torch.mean(bc.cpu(), dim=1).view(batch_size, 1, 1).to(x.device)
+            x[:, 1:-1, 1:-1] = torch.mean(bc, dim=1).view(batch_size, 1, 1)
         else:
             raise NotImplementedError
+        return x
+    if mask:
+        if initialization == 'random':
+            y = torch.empty_like(x).contiguous()
+            return F_.initialize_(y, bc, 'random', torch.rand(x.shape).to(x.device))  # rand_like draws on x's device
+        if initialization == 'zero':
+            return F_.initialize_(torch.empty_like(x).contiguous(), bc, 'zero')
+        return x  # the reference has no other branch on a mask geometry
+    if initialization not in ('zero', 'random', 'avg'):
+        raise NotImplementedError
+    rnd = None
+    if initialization == 'random':
+        rnd = torch.rand(batch_size, image_size - 2, image_size - 2).to(x.device)
+    if x.is_contiguous():
+        return F_.initialize_(x, bc, initialization, rnd)
+    y = F_.initialize_(x.contiguous(), bc, initialization, rnd)  # in place like the reference: copy back
+    x.copy_(y)
     return x
 
 

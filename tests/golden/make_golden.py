@@ -523,7 +523,28 @@ def gen_solvers():
     np.save(os.path.join(HERE, "get_iterator_contract_cg.npy"), np.array(rows, dtype=object), allow_pickle=True)
 
 
-GENERATORS = {"solvers": gen_solvers, "ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
+def gen_initialize():
+    """utils.initialize (utils/heat_utils.py:70-94) on both bc encodings and every mode, seeded like a driver run
+    (torch.manual_seed(666) right before the call): inputs, the reference's outputs and the seed."""
+    for tag, N, B in (("square17", 17, 5), ("square33", 33, 3)):
+        seed()
+        x0, bc, _ = square_problem(B, N, False)
+        out = {}
+        for mode in ("zero", "random", "avg"):
+            torch.manual_seed(4242)
+            out[mode] = npy(utils.initialize(x0.clone(), bc, mode))
+        save("init_" + tag, x=npy(x0), bc=npy(bc), seed=np.array([4242]), **out)
+    for tag, N, B, geo in (("cyl33", 33, 3, "cylinders"), ("lshape17", 17, 4, "Lshape")):
+        seed()
+        x0, bc, _ = mask_problem(B, N, geo)
+        out = {}
+        for mode in ("zero", "random", "avg"):
+            torch.manual_seed(4242)
+            out[mode] = npy(utils.initialize(x0.clone(), bc, mode))
+        save("init_" + tag, x=npy(x0), bc=npy(bc), seed=np.array([4242]), **out)
+
+
+GENERATORS = {"initialize": gen_initialize, "solvers": gen_solvers, "ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
               "backward": gen_backward, "bptt": gen_bptt, "drivers": gen_drivers, "pipeline": gen_pipeline}
 
 if __name__ == "__main__":

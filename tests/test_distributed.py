@@ -34,10 +34,10 @@ def _setup(rank, world, port):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    npde = importlib.import_module("neural-pde-solver_b200")
-    build = importlib.import_module("neural-pde-solver_b200.build")
-    npde._lib._use_emulator(build.build_emulator())
-    return npde
+    if os.path.join(ROOT, "tests") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import emu_backend
+    return emu_backend.use_emulator()
 
 
 def _problem(B, N, seed):
@@ -116,11 +116,10 @@ def _single_process(npde_backend):
 
 @pytest.fixture()
 def emu_npde():
-    npde = importlib.import_module("neural-pde-solver_b200")
-    build = importlib.import_module("neural-pde-solver_b200.build")
-    npde._lib._use_emulator(build.build_emulator())
+    import emu_backend
+    npde = emu_backend.use_emulator()
     yield npde
-    npde._lib._use_cuda_library()
+    emu_backend.use_cuda_library(npde)
 
 
 def test_batch_sharding_world2(tmp_path, emu_npde):
@@ -155,3 +154,20 @@ def test_data_parallel_training_world2(tmp_path, emu_npde):
     wts = np.stack([l.weight.detach().numpy()[0, 0] for l in model.iterator.layers])
     assert np.allclose(parts[0]["w"], wts, rtol=0, atol=1e-6), np.abs(parts[0]["w"] - wts).max()
     assert np.allclose(parts[0]["losses"], np.array(losses), rtol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("full_bptt", ["0", "1"])
+def test_data_parallel_training_nccl_2gpu(full_bptt):
+    """HeatModel(opt, world=True) on two B200s over NCCL (tools/dp_train_check.py under torchrun): the replicas stay
+    bit-identical and match a single-process run on the whole batch to 1e-6, last-step gradient and backprop through
+    all unrolled steps.  Needs two GPUs (two ranks must never share one GPU: B200_PROFILING.md)."""
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, NPDE_FULL_BPTT=full_bptt)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "dp_train_check.py")]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "replicas identical: True" in r.stdout, r.stdout[-2000:]

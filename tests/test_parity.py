@@ -17,6 +17,7 @@ import numpy as np
 import pytest
 import torch
 
+import emu_backend
 from conftest import assert_bitwise, golden_names, load_golden, rel_err
 
 ACTS = {0: "none", 1: "clamp", 2: "sigmoid"}
@@ -28,12 +29,11 @@ class Backend(object):
         self.kind = kind
         self.npde = importlib.import_module("neural-pde-solver_b200")
         if kind == "emu":
-            build = importlib.import_module("neural-pde-solver_b200.build")
-            self.npde._lib._use_emulator(build.build_emulator())
+            emu_backend.use_emulator(self.npde)
             self.device = torch.device("cpu")
         else:
             assert torch.cuda.is_available(), "gpu tests need a CUDA device"
-            self.npde._lib._use_cuda_library()
+            emu_backend.use_cuda_library(self.npde)
             self.npde._lib.lib()  # raises if libnpde_b200.so is missing: no fallback
             self.device = torch.device("cuda:0")
         self.F = self.npde.functional
@@ -51,7 +51,7 @@ class Backend(object):
 def be(request):
     b = Backend(request.param)
     yield b
-    b.npde._lib._use_cuda_library()
+    emu_backend.use_cuda_library(b.npde)
 
 
 # ------------------------------------------------------------ grid operators --
@@ -869,3 +869,36 @@ def test_wide_kernel_vs_oracle(be, oracle, B, N, L, has_f, act, k, tmp_path, mon
         names = trace.read_text().split()
         assert sum("k_conv_wide" in n for n in names) == k, names
         assert sum("k_wide_convert" in n for n in names) == (3 if has_f else 2), names
+
+
+# ----------------------------------------------------------------- initialize --
+@pytest.mark.parametrize("name", golden_names("init_"))
+def test_initialize_vs_reference(be, name):
+    """utils.initialize (utils/heat_utils.py:70-94) through npde_initialize against the reference's own outputs:
+    all modes, both bc encodings, bit for bit -- 'random' included (same torch generator, same draw)."""
+    g = load_golden(name)
+    bc = be.t(g["bc"])
+    for mode in ("zero", "random", "avg"):
+        x = be.t(g["x"]).clone()
+        torch.manual_seed(int(g["seed"][0]))
+        y = be.utils.initialize(x, bc, mode)
+        assert_bitwise(be.n(y), g[mode], "initialize(%s)" % mode)
+        if g["bc"].ndim == 2:  # square domain: in place (heat_utils.py:85-91)
+            assert y.data_ptr() == x.data_ptr()
+    if g["bc"].ndim == 2:
+        with pytest.raises(NotImplementedError):
+            be.utils.initialize(be.t(g["x"]).clone(), bc, "bogus")
+
+
+def test_initialize_on_host_batches():
+    """The reference's drivers initialise the CPU batch of the DataLoader before the model moves it to the GPU
+    (train.py:29, test.py:31): host tensors take the reference's torch expressions, every mode, both encodings."""
+    npde = emu_backend.use_cuda_library()
+    for name in golden_names("init_"):
+        g = load_golden(name)
+        bc = torch.from_numpy(g["bc"])
+        for mode in ("zero", "random", "avg"):
+            torch.manual_seed(int(g["seed"][0]))
+            y = npde.utils.initialize(torch.from_numpy(g["x"]).clone(), bc, mode)
+            assert not y.is_cuda
+            assert_bitwise(y.numpy(), g[mode], "host initialize(%s) %s" % (mode, name))

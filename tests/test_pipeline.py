@@ -15,6 +15,7 @@ import pytest
 import torch
 
 from conftest import assert_bitwise, golden_names, load_golden, rel_err
+import emu_backend
 from test_parity import Backend, BACKENDS
 
 
@@ -22,7 +23,7 @@ from test_parity import Backend, BACKENDS
 def be(request):
     b = Backend(request.param)
     yield b
-    b.npde._lib._use_cuda_library()
+    emu_backend.use_cuda_library(b.npde)
 
 
 geo = importlib.import_module("neural-pde-solver_b200.geometries")
