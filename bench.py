@@ -509,6 +509,27 @@ def run_gpu(args):
                                     "iterations": int(res["iterations"]), "converged": bool(res["converged"]),
                                     "final_residual": float(res["history"][-1][1]),
                                     "cell_updates_per_s": per_gpu * GRID_N * GRID_N * float(res["iterations"]) / dt}
+    if world == 1 and not args.no_ttr:
+        # the same metric for the LEARNED iterator of configs[1]: UNet(3,2,2) with weights trained by the reference's own
+        # HeatModel.train at 33^2 (tests/golden/trained_unet322.npz) on 256 x 257^2 L-shape geometries, zero start,
+        # until max_b fd_error < 1e-6 (checked every 10 iterations); tools/config2_solve.py has the full table.
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import config2_solve
+            unet, shape = config2_solve.trained_unet(dev)
+            unet.is_bc_mask = True
+            np.random.seed(666)
+            _, v, m = npde.utils.get_geometry("Lshape", 257, 256, 1)
+            bcm = torch.from_numpy(np.stack([v, m], 1).astype(np.float32)).to(dev)
+            x0 = npde.utils.initialize(torch.zeros(256, 257, 257, device=dev), bcm, "zero")
+            res, dt = config2_solve.solve(unet, x0, bcm, 1e-6, 10, 20000, False)
+            line["time_to_residual_learned"] = {
+                "value": dt, "unit": "s", "tolerance": 1e-6, "iterator": "unet(%d,%d,%d)" % shape,
+                "weights": "trained by the reference (HeatModel.train) at 33^2", "config": "256 x 257^2 Lshape, zero start",
+                "iterations": int(res["iterations"]), "converged": bool(res["converged"]),
+                "final_residual": float(res["history"][-1][1])}
+        except Exception as exc:  # noqa: BLE001 -- a secondary figure must not take the headline line down
+            line["time_to_residual_learned"] = {"error": repr(exc)[:200]}
     if world == 1 and not args.no_cpu:
         x64, bc64, w64 = make_problem(BATCH, GRID_N, 666)
         sample = "%d Phi_H applications on the whole %d x %d^2 batch"

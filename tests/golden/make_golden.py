@@ -523,6 +523,69 @@ def gen_solvers():
     np.save(os.path.join(HERE, "get_iterator_contract_cg.npy"), np.array(rows, dtype=object), allow_pickle=True)
 
 
+def jacobi_to_tolerance(x, bc, f, tol=1e-6, cap=60000):
+    """generation.py:72-99 with the tolerance tightened: Jacobi until max fd_error < tol."""
+    for i in range(cap):
+        x = utils.fd_step(x, bc, f)
+        if (i + 1) % 100 == 0 and utils.fd_error(x, bc, f).max().item() < tol:
+            break
+    return x
+
+
+def gen_trained():
+    """Learned iterators TRAINED BY THE REFERENCE ITSELF (HeatModel.train, scripts/train.sh hyper-parameters: Adam
+    1e-3, max_iter_steps 20, lambda_gt 0, random initialisation) on small square problems, and BASELINE configs[0]
+    with them: 32 x 65^2, 800 evaluation steps through HeatModel.evaluate from the 'avg' start (test.py:93-120),
+    the error curves and the Metrics the reference reports.  Also the iterations each problem needs to reach
+    fd_error < 1e-6 with the reference's own iterators (the north star's "identical iterations-to-tolerance")."""
+    for tag, opt, B, N, n_train in (("conv3", make_opt(max_iter_steps=20), 16, 17, 600),
+                                    ("unet322", make_opt(iterator="unet", mg_n_layers=3, mg_pre_smoothing=2,
+                                                         mg_post_smoothing=2, max_iter_steps=20), 16, 33, 300)):
+        seed()
+        x, bc, _ = square_problem(B, N, False)
+        gt = jacobi_to_tolerance(x.clone(), bc, None)
+        model = HeatModel(opt)
+        np.random.seed(1234)
+        losses = []
+        for _ in range(n_train):
+            x0 = utils.initialize(x.clone(), bc, "random")
+            losses.append(model.train(x0, gt, bc, None)["loss"]["loss_x"])
+        print(tag, "training loss %.3e -> %.3e" % (np.mean(losses[:10]), np.mean(losses[-10:])))
+        sd = {k.replace(".", "/"): npy(v) for k, v in model.iterator.state_dict().items()}
+        # ---- configs[0]: 32 x 65^2, 800 steps, evaluate() from the 'avg' start
+        seed(667)
+        Be, Ne = 32, 65
+        xe, bce, _ = square_problem(Be, Ne, False)
+        gte = jacobi_to_tolerance(xe.clone(), bce, None)
+        xe = utils.initialize(xe, bce, "avg")
+        model.setup(is_train=False)
+        with torch.no_grad():
+            results, xf = model.evaluate(xe.clone(), gte, bce, None, 800)
+        metrics = utils.Metrics(scale=1, error_threshold=0.01)
+        metrics.update(results)
+        mres = metrics.get_results()
+        # ---- iterations to fd_error < 1e-6, per problem, with the reference's iterators (first 8 problems)
+        first = {}
+        with torch.no_grad():
+            for name, step in (("model", model.iter_step), ("jacobi", JacobiIterator().iter_step)):
+                cur = xe[:8].clone()
+                fb = np.full(8, -1)
+                for t in range(1, 40001):
+                    cur = step(cur, bce[:8], None)
+                    e = utils.fd_error(cur, bce[:8], None).numpy()
+                    fb[(fb < 0) & (e < 1e-6)] = t
+                    if (fb >= 0).all():
+                        break
+                first[name] = fb
+        print(tag, "Metrics", mres, "first crossings", first)
+        save("trained_" + tag, x=npy(xe), bc=npy(bce), gt=npy(gte), model_errors=npy(results["model errors"]),
+             jacobi_errors=npy(results.get("Jacobi errors", results["model errors"])), x_final=npy(xf),
+             metrics=np.array([mres["Jacobi"], mres["model"], mres["ratio"]], np.float64),
+             first_model=first["model"], first_jacobi=first["jacobi"],
+             meta=np.array([opt.conv_n_layers, opt.mg_n_layers, opt.mg_pre_smoothing, opt.mg_post_smoothing]),
+             **{"w/" + k: v for k, v in sd.items()})
+
+
 def gen_initialize():
     """utils.initialize (utils/heat_utils.py:70-94) on both bc encodings and every mode, seeded like a driver run
     (torch.manual_seed(666) right before the call): inputs, the reference's outputs and the seed."""
@@ -544,7 +607,7 @@ def gen_initialize():
         save("init_" + tag, x=npy(x0), bc=npy(bc), seed=np.array([4242]), **out)
 
 
-GENERATORS = {"initialize": gen_initialize, "solvers": gen_solvers, "ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
+GENERATORS = {"trained": gen_trained, "initialize": gen_initialize, "solvers": gen_solvers, "ops": gen_ops, "conv": gen_conv, "multigrid": gen_multigrid, "unet": gen_unet,
               "backward": gen_backward, "bptt": gen_bptt, "drivers": gen_drivers, "pipeline": gen_pipeline}
 
 if __name__ == "__main__":
