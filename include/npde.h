@@ -229,6 +229,20 @@ typedef struct npde_iterate_desc {
 
 int npde_iterate(const npde_iterate_desc *d, void *stream);
 
+/* generation.py:72-99 get_solution as ONE device-side loop: apply the iterator of `d` (d->k, err_l2, err_fd and
+ * temporal_depth are ignored) until max_b fd_error(x_b, 'max') < tol, looking at the residual every `check_every`
+ * applications like the reference's `(i + 1) % 100 == 0`, at most max_iters applications (rounded up to a multiple of
+ * check_every).  The loop is a CUDA graph with a WHILE node whose condition the residual kernel writes on the device:
+ * the call only enqueues, the host never waits.  result: 16 bytes of DEVICE memory, npde_solve_result.
+ * Workspace: npde_workspace_bytes(NPDE_WS_ITERATE + iterator, ..., k = check_every). */
+typedef struct npde_solve_result {
+  int iterations;  /* applications performed (0 if x_in already met the tolerance) */
+  int converged;   /* 1 iff the last residual checked is < tol */
+  float residual;  /* the last residual checked: max_b fd_error */
+  float residual0; /* max_b fd_error of x_in */
+} npde_solve_result;
+int npde_solve(const npde_iterate_desc *d, float tol, int check_every, int max_iters, void *result, void *stream);
+
 /* ---- persistent device layout for drivers that keep fields resident between calls ----------------------
  * The loops of generation.py:86-93 / runtime.py:78-79 / heat_model.py:49-50 call the iterator on the SAME
  * tensors over and over.  A driver may convert them once into the library's batch-interleaved "W8" layout

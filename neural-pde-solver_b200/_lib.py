@@ -70,6 +70,7 @@ PROTOTYPES = {
     "npde_unet_step_bwd": (_int, [_vp, _vp, _int, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp,
                                   _vp, _int, _int, _vp, _size, _vp]),
     "npde_iterate": (_int, [ctypes.POINTER(IterateDesc), _vp]),
+    "npde_solve": (_int, [ctypes.POINTER(IterateDesc), ctypes.c_float, _int, _int, _vp, _vp]),
     "npde_packed_floats": (_size, [_int, _int]),
     "npde_pack": (_int, [_vp, _vp, _int, _int, _vp]),
     "npde_unpack": (_int, [_vp, _vp, _int, _int, _vp]),

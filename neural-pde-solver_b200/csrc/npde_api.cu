@@ -586,6 +586,43 @@ int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kin
   return NPDE_OK;
 }
 
+
+// ------------------------------------------------------------------ npde_solve ---
+// One warp: largest residual of the batch, bookkeeping, and (on the device) the WHILE condition of the loop.
+struct SolveResult {
+  int iterations, converged;
+  float residual, residual0;
+};
+#ifdef NPDE_EMU
+__global__ void k_solve_check(const float *err, int B, float tol, int add, int max_iters, SolveResult *r, int first) {
+#else
+__global__ void k_solve_check(const float *err, int B, float tol, int add, int max_iters, SolveResult *r, int first,
+                              cudaGraphConditionalHandle handle) {
+#endif
+  float m = 0.0f;
+  bool nan = false;
+  for (int b = threadIdx.x; b < B; b += 32) {
+    const float e = err[b];
+    nan = nan || (e != e);
+    m = fmaxf(m, e);
+  }
+  m = npde_warp_max(m);
+  if (npde_warp_max(nan ? 1.0f : 0.0f) > 0.0f) m = __int_as_float(0x7fc00000);  // a NaN residual never converges
+  if (threadIdx.x == 0) {
+    if (first) {
+      r->iterations = 0;
+      r->residual0 = m;
+    } else {
+      r->iterations += add;
+    }
+    r->residual = m;
+    r->converged = (m < tol) ? 1 : 0;
+#ifndef NPDE_EMU
+    cudaGraphSetConditional(handle, (!(m < tol) && r->iterations < max_iters) ? 1u : 0u);
+#endif
+  }
+}
+
 }  // namespace
 
 // ======================================================================= C ABI
@@ -1257,6 +1294,173 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     TRY(npde::fd_error(cur, d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, d->err_fd + (size_t)d->k * B, B, N, w.red,
                        w.red_bytes, st));
   return d2d(d->x_out, cur, sizeof(float) * cells, st);
+}
+
+int npde_solve(const npde_iterate_desc *d, float tol, int check_every, int max_iters, void *result, void *stream) {
+  if (!d || !result) return NPDE_ERR_NULL;
+  TRY(npde::check_common(d->x_in, d->x_out, d->B, d->N));
+  TRY(npde::check_bc(d->bc, d->bc_kind));
+  if (check_every < 1 || max_iters < 1 || !(tol > 0.0f)) return NPDE_ERR_ARG;
+  const int B = d->B, N = d->N, it = d->iterator;
+  if (it < NPDE_IT_JACOBI || it > NPDE_IT_UNET) return NPDE_ERR_ARG;
+  if ((it == NPDE_IT_CONV || it == NPDE_IT_UNET) && (d->act < NPDE_ACT_NONE || d->act > NPDE_ACT_SIGMOID))
+    return NPDE_ERR_ACT;
+  if (it == NPDE_IT_CONV && (d->n_layers < 0 || d->n_layers > NPDE_MAX_CONV_LAYERS)) return NPDE_ERR_LAYERS;
+  if (it == NPDE_IT_CONV && d->n_layers > 0 && !d->w) return NPDE_ERR_NULL;
+  if (it == NPDE_IT_MULTIGRID || it == NPDE_IT_UNET) {
+    if (d->n_layers < 1 || d->n_layers > NPDE_MAX_LEVELS || d->pre < 0 || d->post < 0) return NPDE_ERR_LAYERS;
+    if (!level_sizes_ok(N, d->n_layers)) return NPDE_ERR_SIZE;
+    if (it == NPDE_IT_UNET && !d->w) return NPDE_ERR_NULL;
+  }
+  size_t need = npde_workspace_bytes(NPDE_WS_ITERATE + it, B, N, d->bc_kind, d->n_layers, d->pre, d->post, check_every);
+  TRY(ws_ok(d->workspace, d->workspace_bytes, need));
+  cudaStream_t st = S(stream);
+  Bump b(d->workspace);
+  IterWs w;
+  w.carve(b, it, B, N, d->bc_kind, d->n_layers, d->pre, d->post);
+  SolveResult *res = reinterpret_cast<SolveResult *>(result);
+  float *err = w.stage_fd;  // (B) residual row of the current check
+  const bool conv_fast = it == NPDE_IT_CONV && npde::conv_stream_supported(d->bc_kind, d->n_layers, d->w_host);
+  const bool fast = conv_fast || it == NPDE_IT_JACOBI;  // stream kernels on pair-permuted fields
+  npde::FieldViewMut pad[2] = {{w.buf[0], w.pitch, w.bstride, 1}, {w.buf[1], w.pitch, w.bstride, 1}};
+  if (!fast) pad[0] = npde::ref_view_mut(w.buf[0], N), pad[1] = npde::ref_view_mut(w.buf[1], N);
+  npde::FieldView fv = npde::ref_view(d->f, N);
+  npde::BcFields bcf = npde::bc_fields(d->bc, d->bc_kind, N);
+  const float *wf = d->w, *wp = nullptr, *wsnd = nullptr;
+  if (it == NPDE_IT_UNET) {
+    wp = wf + 9 * (size_t)d->n_layers * d->pre;
+    wsnd = wp + 9 * (size_t)(d->n_layers - 1);
+  }
+  // prologue: x_in -> pad[0] (the source and the bc planes get their 128-bit layout once), residual of x_0
+  auto prologue = [&](cudaStream_t s) -> int {
+    if (fast && d->f) {
+      npde::FieldViewMut fp = {w.fpad, w.pitch, w.bstride, 1};
+      TRY(npde::copy_field(fv, fp, B, N, s));
+      fv = npde::as_const(fp);
+    }
+    if (fast && d->bc_kind == NPDE_BC_MASK) {
+      npde::FieldViewMut vp = {w.vpad, w.pitch, w.bstride, 1}, mp = {w.mpad, w.pitch, w.bstride, 1};
+      TRY(npde::copy_field(bcf.values, vp, B, N, s));
+      TRY(npde::copy_field(bcf.mask, mp, B, N, s));
+      bcf.values = npde::as_const(vp);
+      bcf.mask = npde::as_const(mp);
+    }
+    TRY(npde::copy_field(npde::ref_view(d->x_in, N), pad[0], B, N, s));
+    TRY(npde::reduce_ws_clear(w.red, w.red_bytes, B, N, s));
+    return npde::fd_error_view(npde::as_const(pad[0]), d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, err, B, N, w.red,
+                               w.red_bytes, s, true);
+  };
+  // one check interval: check_every applications pad[0] -> ... -> pad[0], then the residual row
+  auto body = [&](cudaStream_t s) -> int {
+    int cur = 0, left = check_every;
+    while (left > 0) {
+      int adv = 1;
+      if (it == NPDE_IT_JACOBI) adv = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+      const npde::FieldView src = npde::as_const(pad[cur]);
+      const npde::FieldViewMut &dst = pad[cur ^ 1];
+      if (it == NPDE_IT_JACOBI) TRY(npde::jacobi_stream(src, dst, bcf, fv, adv, B, N, s));
+      else if (conv_fast) TRY(npde::conv_stream(src, dst, bcf, fv, d->w_host, d->n_layers, d->act, B, N, s));
+      else if (it == NPDE_IT_CONV)
+        TRY(npde_conv_step_fwd(src.p, d->bc, d->bc_kind, d->f, d->w, d->w_host, d->n_layers, d->act, dst.p, B, N, w.step,
+                               w.step_bytes, s));
+      else if (it == NPDE_IT_MULTIGRID)
+        TRY(npde_mg_step(src.p, d->bc, d->bc_kind, d->f, d->n_layers, d->pre, d->post, dst.p, B, N, w.step, w.step_bytes, s));
+      else
+        TRY(npde_unet_step_fwd_hw(src.p, d->bc, d->bc_kind, d->f, wf, wp, wsnd, d->w_host, d->n_layers, d->pre, d->post,
+                                  d->act, dst.p, B, N, w.step, w.step_bytes, s));
+      left -= adv;
+      cur ^= 1;
+    }
+    if (cur != 0) TRY(npde::copy_field(npde::as_const(pad[1]), pad[0], B, N, s));
+    return npde::fd_error_view(npde::as_const(pad[0]), d->bc, d->bc_kind, d->f, NPDE_AGG_MAX, err, B, N, w.red,
+                               w.red_bytes, s, true);
+  };
+  auto epilogue = [&](cudaStream_t s) -> int {
+    return npde::copy_field(npde::as_const(pad[0]), npde::ref_view_mut(d->x_out, N), B, N, s);
+  };
+#ifdef NPDE_EMU
+  // host emulator: "device" memory is host memory, so the loop condition is simply read back
+  TRY(prologue(st));
+  NPDE_LAUNCH(k_solve_check, dim3(1), dim3(32), 0, st, err, B, tol, 0, max_iters, res, 1);
+  while (!res->converged && res->iterations < max_iters) {
+    TRY(body(st));
+    NPDE_LAUNCH(k_solve_check, dim3(1), dim3(32), 0, st, err, B, tol, check_every, max_iters, res, 0);
+  }
+  return epilogue(st);
+#else
+  // One graph: prologue -> WHILE(residual >= tol and iterations < max_iters) { body } -> epilogue.  The condition is
+  // written by k_solve_check on the device, so the host neither waits nor reads anything until the caller does.
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &status) != cudaSuccess || status != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return NPDE_ERR_ARG;  // cannot build a graph inside the caller's capture
+  }
+  struct Guard {
+    cudaStream_t cs = nullptr, cs2 = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaGraphExec_t ex = nullptr;
+    ~Guard() {
+      if (ex) cudaGraphExecDestroy(ex);  // an in-flight launch completes; resources are released afterwards
+      if (g) cudaGraphDestroy(g);
+      if (cs) cudaStreamDestroy(cs);
+      if (cs2) cudaStreamDestroy(cs2);
+    }
+  } G;
+#define CU(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { cudaGetLastError(); return (int)e__; } } while (0)
+  CU(cudaStreamCreateWithFlags(&G.cs, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&G.cs2, cudaStreamNonBlocking));
+  CU(cudaGraphCreate(&G.g, 0));
+  cudaGraphConditionalHandle handle;
+  CU(cudaGraphConditionalHandleCreate(&handle, G.g, 1, cudaGraphCondAssignDefault));
+  CU(cudaStreamBeginCaptureToGraph(G.cs, G.g, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  int rc = prologue(G.cs);
+  if (rc == NPDE_OK) {
+    NPDE_LAUNCH(k_solve_check, dim3(1), dim3(32), 0, G.cs, err, B, tol, 0, max_iters, res, 1, handle);
+    if (cudaGetLastError() != cudaSuccess) rc = NPDE_ERR_ARG;
+  }
+  cudaGraphNode_t cond = nullptr;
+  cudaGraph_t body_graph = nullptr;
+  if (rc == NPDE_OK) {
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n_deps = 0;
+    cudaGraph_t gq = nullptr;
+    unsigned long long id = 0;
+    cudaError_t e = cudaStreamGetCaptureInfo(G.cs, &status, &id, &gq, &deps, &n_deps);
+    cudaGraphNodeParams np = {};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    if (e == cudaSuccess) e = cudaGraphAddNode(&cond, G.g, deps, n_deps, &np);
+    if (e == cudaSuccess) {
+      body_graph = np.conditional.phGraph_out[0];
+      e = cudaStreamUpdateCaptureDependencies(G.cs, &cond, 1, cudaStreamSetCaptureDependencies);
+    }
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  if (rc == NPDE_OK) rc = epilogue(G.cs);
+  {
+    cudaGraph_t done = nullptr;
+    cudaError_t e = cudaStreamEndCapture(G.cs, &done);
+    if (rc == NPDE_OK && e != cudaSuccess) rc = (int)e;
+  }
+  if (rc != NPDE_OK) { cudaGetLastError(); return rc; }
+  CU(cudaStreamBeginCaptureToGraph(G.cs2, body_graph, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  rc = body(G.cs2);
+  if (rc == NPDE_OK) {
+    NPDE_LAUNCH(k_solve_check, dim3(1), dim3(32), 0, G.cs2, err, B, tol, check_every, max_iters, res, 0, handle);
+    if (cudaGetLastError() != cudaSuccess) rc = NPDE_ERR_ARG;
+  }
+  {
+    cudaError_t e = cudaStreamEndCapture(G.cs2, nullptr);
+    if (rc == NPDE_OK && e != cudaSuccess) rc = (int)e;
+  }
+  if (rc != NPDE_OK) { cudaGetLastError(); return rc; }
+  CU(cudaGraphInstantiate(&G.ex, G.g, 0));
+  CU(cudaGraphLaunch(G.ex, st));
+#undef CU
+  return NPDE_OK;
+#endif
 }
 
 size_t npde_packed_floats(int B, int N) { return (B > 0 && N > 0) ? npde::wide_field_floats(B, N) : 0; }

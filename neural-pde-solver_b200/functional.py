@@ -484,3 +484,35 @@ def iterate(iterator, x, bc, f, k, *, w=None, w_host=None, n_layers=0, pre=0, po
                     err_fd=None if efd is None else efd.data_ptr(), workspace=ws, workspace_bytes=wsb)
     check(lib().npde_iterate(ctypes.byref(d), _stream(x)), "npde_iterate")
     return y, e2, efd
+
+
+def solve(iterator, x, bc, f, tol, check_every, max_iters, *, w=None, w_host=None, n_layers=0, pre=0, post=0,
+          act="none"):
+    """generation.py:72-99 as one device-side loop (npde_solve): apply the iterator until max_b fd_error < tol,
+    checked every `check_every` applications, at most `max_iters`.  Only enqueues: returns (x_final, result) with
+    result a 4-element int32 DEVICE tensor [iterations, converged, bits(residual), bits(residual0)] that is valid once
+    the stream has run (read it with .cpu(): that is the only synchronisation)."""
+    x = _field(x)
+    bc = _require(bc, "bc")
+    f = _opt(f, "f")
+    w = None if w is None else _require(w, "w").reshape(-1)
+    for name, t in (("bc", bc), ("f", f), ("w", w)):
+        if t is not None and t.device != x.device:
+            raise RuntimeError("solve: %s is on %s, x on %s" % (name, t.device, x.device))
+    B, N, _ = x.shape
+    kind = bc_kind(x, bc)
+    y = torch.empty_like(x)
+    result = torch.zeros(4, dtype=torch.int32, device=x.device)
+    wh = None
+    if w_host is not None:
+        w_host = np.ascontiguousarray(w_host, dtype=np.float32).reshape(-1)
+        wh = w_host.ctypes.data_as(ctypes.c_void_p)
+    ws, wsb = _workspace(lib().npde_workspace_bytes(_lib.WS_ITERATE + iterator, B, N, kind, n_layers, pre, post,
+                                                    int(check_every)), x)
+    d = IterateDesc(iterator=iterator, B=B, N=N, bc_kind=kind, n_layers=n_layers, pre=pre, post=post, act=_act(act),
+                    k=int(check_every), temporal_depth=0, x_in=x.data_ptr(), x_out=y.data_ptr(), bc=bc.data_ptr(),
+                    f=None if f is None else f.data_ptr(), w=None if w is None else w.data_ptr(), w_host=wh,
+                    gt=None, err_l2=None, err_fd=None, workspace=ws, workspace_bytes=wsb)
+    check(lib().npde_solve(ctypes.byref(d), ctypes.c_float(tol), int(check_every), int(max_iters), _ptr(result),
+                           _stream(x)), "npde_solve")
+    return y, result

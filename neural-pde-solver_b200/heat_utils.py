@@ -178,7 +178,8 @@ def calculate_errors(x, bc, f, gt, iter_func, n_steps, starting_error, threshold
     return errors, x
 
 
-def solve_to_tolerance(iterator, x, bc, f, tol=1e-5, check_every=100, max_iters=8000, per_problem=False):
+def solve_to_tolerance(iterator, x, bc, f, tol=1e-5, check_every=100, max_iters=8000, per_problem=False,
+                       device_loop=True):
     """The residual-tolerance driver of generation.py:72-99 (`get_solution`) for any iterator of this
     package: apply `iterator` until max_b fd_error(x_b) < tol, looking at the residual every
     `check_every` iterations (the reference checks `(i + 1) % 100 == 0`, generation.py:89-93) and
@@ -191,10 +192,22 @@ def solve_to_tolerance(iterator, x, bc, f, tol=1e-5, check_every=100, max_iters=
     every single problem drops below `tol` is returned: this is BASELINE's "iterations to 1e-6 residual",
     identical to the reference's count because iterates are bit-identical and the criterion is a max.
 
+    device_loop (default, when per_problem is off and max_iters is a multiple of check_every): the whole loop is ONE
+    npde_solve call -- a CUDA graph with a WHILE node whose condition the residual kernel writes on the device -- so
+    the host does not wait for the device once per interval but exactly once, when it reads the result; `history`
+    then holds the first and the last residual only.
+
     Returns a dict: x (final iterate), iterations (applied), converged (bool), history (list of
     (iteration, largest residual)), and with per_problem: first_below (B,) int64 (-1 = never).
     """
     x = x.detach()
+    if device_loop and not per_problem and hasattr(iterator, "solve") and max_iters % check_every == 0:
+        y, result = iterator.solve(x, bc, f, tol, check_every, max_iters)
+        r = result.cpu()  # the one synchronisation of the solve
+        res0, resn = (float(v) for v in r[2:].view(torch.float32)[[1, 0]])
+        done = int(r[0])
+        history = [(0, res0)] + ([(done, resn)] if done else [])
+        return {"x": y, "iterations": done, "converged": bool(r[1]), "history": history}
     err = fd_error(x, bc, f)
     largest = float(err.max().item())
     history = [(0, largest)]

@@ -67,6 +67,10 @@ class JacobiIterator(Iterator):
         return F_.iterate(IT_JACOBI, x, bc, f, k, gt=gt, want_l2=want_l2, want_fd=want_fd,
                           temporal_depth=temporal_depth, out=out)
 
+    def solve(self, x, bc, f, tol, check_every, max_iters):
+        """generation.py:72-99 as one device-side loop (npde_solve): see functional.solve."""
+        return F_.solve(IT_JACOBI, x, bc, f, tol, check_every, max_iters)
+
     def name(self):
         return 'Jacobi'
 
@@ -87,6 +91,10 @@ class MultigridIterator(Iterator):
     def iterate(self, x, bc, f, k, gt=None, want_l2=False, want_fd=False, out=None):
         return F_.iterate(IT_MULTIGRID, x, bc, f, k, n_layers=self.n_layers, pre=self.pre_smoothing,
                           post=self.post_smoothing, gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+
+    def solve(self, x, bc, f, tol, check_every, max_iters):
+        return F_.solve(IT_MULTIGRID, x, bc, f, tol, check_every, max_iters, n_layers=self.n_layers,
+                        pre=self.pre_smoothing, post=self.post_smoothing)
 
     def name(self):
         return 'Multigrid'
@@ -181,17 +189,22 @@ class _WeightCache(object):
         self.dev = None
         self.host = None
 
-    def get(self, params):
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+    def get(self, params, device=None):
+        """Writes through `p.data` (old-style torch code) do not move the version counter: call `invalidate()`
+        (Iterator.invalidate_weight_cache) after such a write.  `device`: where an EMPTY stack lives (Conv0)."""
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params) + (str(device),)
         if key != self.key:
             with torch.no_grad():
                 if len(params):
                     self.dev = torch.stack([p.detach().reshape(3, 3) for p in params]).contiguous()
                 else:
-                    self.dev = torch.empty((0, 3, 3), device='cpu')
+                    self.dev = torch.empty((0, 3, 3), device=device if device is not None else 'cpu')
                 self.host = self.dev.cpu().numpy().copy()
             self.key = key
         return self.dev, self.host
+
+    def invalidate(self):
+        self.key = None
 
 
 class ConvIterator(Iterator):
@@ -217,14 +230,14 @@ class ConvIterator(Iterator):
 
     def H(self, r, bc):
         """r: (B,1,N-2,N-2) -> H(r), same shape (conv_iterator.py:19-31)."""
-        w, _ = self._cache.get(self._params())
+        w, _ = self._cache.get(self._params(), r.device)
         return F_.conv_H(r.squeeze(1), bc, w, self.is_bc_mask).unsqueeze(1)
 
     def forward(self, x, bc, f):
         self._check_act()
         self._consistent(x, bc)
         params = self._params()
-        w_dev, w_host = self._cache.get(params)
+        w_dev, w_host = self._cache.get(params, x.device)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params)):
             w = torch.stack([p.reshape(3, 3) for p in params]) if params else w_dev
             return F_.ConvStepFn.apply(x, bc, f, w, self.act, w_host)
@@ -248,9 +261,20 @@ class ConvIterator(Iterator):
         1 forces the streaming kernel (one launch per step)."""
         self._check_act()
         self._consistent(x, bc)
-        w_dev, w_host = self._cache.get(self._params())
+        w_dev, w_host = self._cache.get(self._params(), x.device)
         return F_.iterate(IT_CONV, x, bc, f, k, w=w_dev, w_host=w_host, n_layers=self.n_layers, act=self.act,
                           gt=gt, want_l2=want_l2, want_fd=want_fd, out=out, temporal_depth=temporal_depth)
+
+    def solve(self, x, bc, f, tol, check_every, max_iters):
+        self._check_act()
+        self._consistent(x, bc)
+        w_dev, w_host = self._cache.get(self._params(), x.device)
+        return F_.solve(IT_CONV, x, bc, f, tol, check_every, max_iters, w=w_dev, w_host=w_host,
+                        n_layers=self.n_layers, act=self.act)
+
+    def invalidate_weight_cache(self):
+        """Call after writing the weights through `.data` (which does not move torch's version counter)."""
+        self._cache.invalidate()
 
     def name(self):
         return 'Conv{}'.format(self.n_layers)
@@ -316,6 +340,15 @@ class UNetIterator(Iterator):
         w, w_host = self._cache.get(self._params())
         return F_.iterate(IT_UNET, x, bc, f, k, w=w, w_host=w_host, n_layers=self.n_layers, pre=self.pre_smoothing,
                           post=self.post_smoothing, act=self.act, gt=gt, want_l2=want_l2, want_fd=want_fd, out=out)
+
+    def solve(self, x, bc, f, tol, check_every, max_iters):
+        self._check_act()
+        w, w_host = self._cache.get(self._params())
+        return F_.solve(IT_UNET, x, bc, f, tol, check_every, max_iters, w=w, w_host=w_host, n_layers=self.n_layers,
+                        pre=self.pre_smoothing, post=self.post_smoothing, act=self.act)
+
+    def invalidate_weight_cache(self):
+        self._cache.invalidate()
 
     def name(self):
         return 'UNet{}'.format(self.n_layers)

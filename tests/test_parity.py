@@ -994,3 +994,56 @@ def test_iterations_to_1e6_match_the_oracle(oracle, B, N, kind):
     assert np.array_equal(res["first_below"].numpy(), first), (res["first_below"], first)
     assert rows[n].max() < 1e-6 and (n == every or rows[n - every].max() >= 1e-6), "stops at the same check"
     assert_bitwise(be.n(res["x"]), ref, "iterate at the stopping check")
+
+
+# ------------------------------------------------------- device-side solve loop (npde_solve) --
+@pytest.mark.parametrize("case", ["jacobi_square_f", "jacobi_mask", "conv_mask", "multigrid_cap", "unet_square",
+                                  "already_converged"])
+def test_device_side_solve_loop(be, oracle, case):
+    """npde_solve (one CUDA graph with a WHILE node; the residual kernel writes the loop condition on the device)
+    against the host-driven loop of solve_to_tolerance: same stopping check, same iteration count, same iterate
+    bit for bit, same residuals -- Jacobi / Conv / Multigrid / U-Net, square domain and mask geometry, with a source
+    term, a run that hits max_iters, and an input that already meets the tolerance."""
+    rng = np.random.RandomState(11)
+    B, N = 3, 33
+    npde = be.npde
+    f = None
+    tol, every, cap = 1e-4, 20, 4000
+    if case in ("jacobi_mask", "conv_mask"):
+        bc = _mask_geometry(rng, B, N)
+        x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    else:
+        bc = rng.rand(B, 4).astype(np.float32)
+        x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    if case == "jacobi_square_f":
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    if case.startswith("jacobi") or case == "already_converged":
+        it = npde.JacobiIterator()
+    elif case == "conv_mask":
+        it = npde.ConvIterator("clamp", 2)
+        with torch.no_grad():
+            it.layers[0].weight.zero_(); it.layers[1].weight.zero_()
+            it.layers[0].weight[0, 0, 1, 1] = 0.3; it.layers[1].weight[0, 0, 1, 1] = -0.3
+        it = it.to(be.device)
+    elif case == "multigrid_cap":
+        it, tol, every, cap = npde.MultigridIterator(3, 2, 2), 1e-7, 4, 40  # the interpolant keeps it above 1e-7
+    else:
+        g, model = _load_trained(be, "unet322")
+        it, tol, every, cap = model.iterator, 1e-5, 10, 2000
+    it.is_bc_mask = bc.ndim == 4
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    if case == "already_converged":
+        xd = be.utils.solve_to_tolerance(it, xd, bcd, fd, tol=tol, check_every=every, max_iters=cap,
+                                         device_loop=False)["x"]
+    with torch.no_grad():
+        host = be.utils.solve_to_tolerance(it, xd, bcd, fd, tol=tol, check_every=every, max_iters=cap, device_loop=False)
+        dev = be.utils.solve_to_tolerance(it, xd, bcd, fd, tol=tol, check_every=every, max_iters=cap)
+    assert dev["iterations"] == host["iterations"], (case, dev["iterations"], host["iterations"])
+    assert dev["converged"] == host["converged"] == (case != "multigrid_cap")
+    assert_bitwise(be.n(dev["x"]), be.n(host["x"]), "iterate at the stopping check")
+    assert dev["history"][0][1] == host["history"][0][1] and dev["history"][-1][1] == host["history"][-1][1]
+    if case == "already_converged":
+        assert dev["iterations"] == 0
+    if case == "multigrid_cap":
+        assert dev["iterations"] == cap
