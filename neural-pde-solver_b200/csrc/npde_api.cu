@@ -4,8 +4,12 @@
 // here synchronises or allocates.
 #include <stdlib.h>
 
+#include <string.h>
+
 #include <atomic>
+#include <mutex>
 #include <new>
+#include <vector>
 
 #include "npde_common.cuh"
 #include "npde_internal.h"
@@ -433,6 +437,8 @@ constexpr int ITER_SEG = 32;  // fused launches per captured segment of the Jaco
 struct IterWs {
   float *buf[2];
   float *stage_l2, *stage_fd;  // (ITER_SEG, B) error rows of one replayed segment
+  float *bc_copy;              // stable copy of the caller's bc (graph replay), or nullptr
+  size_t bc_floats;
   float *fpad;  // the source in the padded layout (Jacobi / Conv fast path)
   float *vpad, *mpad;  // mask geometry: the two bc planes in the padded layout (Conv fast path)
   int pitch;
@@ -459,6 +465,9 @@ struct IterWs {
     red = b.take_bytes(red_bytes);
     stage_l2 = b.take<float>((size_t)ITER_SEG * B);
     stage_fd = b.take<float>((size_t)ITER_SEG * B);
+    // graph-eligible sizes: the caller's bc is copied here so that cached segments never refer to caller memory
+    bc_floats = ((size_t)B * N * N <= ((size_t)8 << 20)) ? (bc_kind == NPDE_BC_MASK ? 2 * (size_t)B * N * N : 4 * (size_t)B) : 0;
+    bc_copy = bc_floats ? b.take<float>(bc_floats) : nullptr;
     step_bytes = 0;
     if (iterator == NPDE_IT_CONV) step_bytes = npde_workspace_bytes(NPDE_WS_CONV_FWD, B, N, bc_kind, L, 0, 0, 0);
     if (iterator == NPDE_IT_MULTIGRID) step_bytes = npde_workspace_bytes(NPDE_WS_MG, B, N, bc_kind, L, pre, post, 0);
@@ -473,12 +482,89 @@ struct IterWs {
 // from the host: the segment (an even number of steps, ping-pong buffers back where they started) is captured
 // once on a private stream, instantiated, and launched into the caller's stream as often as it fits.  The
 // caller's stream may be the legacy default stream, which cannot capture -- hence the private stream.
+// Instantiated segments are cached per (shape, iterator, every pointer and every by-value weight the captured
+// launches contain): the drivers call npde_iterate over and over with the same workspace (calculate_errors in chunks,
+// solve_to_tolerance per check interval, runtime.py once per problem), and capture + instantiation cost as much as a
+// few dozen small launches.  The caller's bc tensor is copied into the workspace first (see npde_iterate) so that
+// the segment only refers to memory that stays the same from call to call.
+struct GraphKey {
+  int dev, iterator, B, N, bc_kind, n_layers, pre, post, act, adv, want_l2, want_fd, n_whost;
+  const void *bc, *f, *w, *gt, *ws;
+  unsigned long long whost_hash;
+};
+#ifndef NPDE_EMU
+struct GraphCache {
+  struct Entry {
+    GraphKey key;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    unsigned long long stamp;
+  };
+  std::mutex mu;
+  std::vector<Entry> entries;
+  unsigned long long clock = 0;
+  static constexpr size_t kMax = 16;
+  cudaGraphExec_t find(const GraphKey &k) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &e : entries)
+      if (memcmp(&e.key, &k, sizeof(GraphKey)) == 0) {
+        e.stamp = ++clock;
+        return e.exec;
+      }
+    return nullptr;
+  }
+  void put(const GraphKey &k, cudaGraph_t g, cudaGraphExec_t ex) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (entries.size() >= kMax) {  // evict the least recently used (an in-flight launch completes first)
+      size_t lru = 0;
+      for (size_t i = 1; i < entries.size(); ++i)
+        if (entries[i].stamp < entries[lru].stamp) lru = i;
+      cudaGraphExecDestroy(entries[lru].exec);
+      cudaGraphDestroy(entries[lru].graph);
+      entries.erase(entries.begin() + lru);
+    }
+    entries.push_back(Entry{k, g, ex, ++clock});
+  }
+};
+GraphCache g_graphs;
+#endif
+
+inline GraphKey make_graph_key(const npde_iterate_desc *d, int adv, const void *ws, size_t n_whost) {
+  GraphKey k;
+  memset(&k, 0, sizeof(k));  // padding bytes take part in the comparison
+  int dev = 0;
+#ifndef NPDE_EMU
+  cudaGetDevice(&dev);
+#endif
+  k.dev = dev; k.iterator = d->iterator; k.B = d->B; k.N = d->N; k.bc_kind = d->bc_kind; k.n_layers = d->n_layers;
+  k.pre = d->pre; k.post = d->post; k.act = d->act; k.adv = adv;
+  k.want_l2 = d->err_l2 != nullptr; k.want_fd = d->err_fd != nullptr;
+  k.bc = d->bc; k.f = d->f; k.w = d->w; k.gt = d->err_l2 ? d->gt : nullptr; k.ws = ws;
+  k.n_whost = d->w_host ? (int)n_whost : -1;
+  unsigned long long h = 1469598103934665603ull;  // FNV-1a over the by-value weights
+  if (d->w_host) {
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(d->w_host);
+    for (size_t i = 0; i < n_whost * sizeof(float); ++i) h = (h ^ p[i]) * 1099511628211ull;
+  }
+  k.whost_hash = h;
+  return k;
+}
+
 struct StepGraph {
 #ifndef NPDE_EMU
   cudaStream_t cs = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
-  bool capturing = false;
+  bool capturing = false, cached = false, owned = true;
+  GraphKey key;
+  // true: a cached instantiation of this very segment exists -- nothing to capture
+  bool lookup(const GraphKey &k) {
+    key = k;
+    exec = g_graphs.find(k);
+    cached = exec != nullptr;
+    if (cached) owned = false;
+    return cached;
+  }
   // false: graphs are not usable here (caller is capturing itself, or stream creation failed) -> plain launches
   bool begin(cudaStream_t caller) {
     cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
@@ -495,26 +581,27 @@ struct StepGraph {
     if (capturing) { cudaStreamEndCapture(cs, &graph); capturing = false; cudaGetLastError(); }
     return NPDE_OK;
   }
+  // ends the capture, instantiates and hands the result to the cache; on failure the caller falls back to plain launches
   int finish() {
+    if (cached) return NPDE_OK;
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
     capturing = false;
-    if (e != cudaSuccess) return (int)e;
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    return e == cudaSuccess ? NPDE_OK : (int)e;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    g_graphs.put(key, graph, exec);
+    owned = false;
+    return NPDE_OK;
   }
   int launch_once(cudaStream_t caller) {
     cudaError_t e = cudaGraphLaunch(exec, caller);
     return e == cudaSuccess ? NPDE_OK : (int)e;
   }
-  int finish_and_launch(int times, cudaStream_t caller) {
-    int rc = finish();
-    for (int i = 0; i < times && rc == NPDE_OK; ++i) rc = launch_once(caller);
-    return rc;
-  }
   ~StepGraph() {
     abort_capture();
-    if (exec) cudaGraphExecDestroy(exec);  // in-flight launches complete; resources are released afterwards
-    if (graph) cudaGraphDestroy(graph);
+    if (owned) {
+      if (exec) cudaGraphExecDestroy(exec);
+      if (graph) cudaGraphDestroy(graph);
+    }
     if (cs) cudaStreamDestroy(cs);
   }
 #endif
@@ -1118,6 +1205,16 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   w.carve(b, it, B, N, d->bc_kind, d->n_layers, d->pre, d->post);
   const size_t cells = (size_t)B * N * N;
   const bool want_err = d->err_l2 || d->err_fd;
+  npde_iterate_desc dd = *d;
+#ifndef NPDE_EMU
+  if (w.bc_copy && graph_worthwhile(cells, d->k)) {
+    TRY(d2d(w.bc_copy, d->bc, sizeof(float) * w.bc_floats, st));
+    dd.bc = w.bc_copy;
+  }
+#endif
+  d = &dd;
+  const size_t n_whost = it == NPDE_IT_CONV ? 9 * (size_t)d->n_layers
+                        : it == NPDE_IT_UNET ? 9 * ((size_t)d->n_layers * (d->pre + d->post) + d->n_layers - 1) : 0;
 
   // ---- fast path: fused stream kernels on pair-permuted ping-pong buffers.  Error rows, if asked for,
   // come from the reduction kernels reading the same buffers (one launch per row, no host round trip);
@@ -1175,7 +1272,8 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
     constexpr int SEG = ITER_SEG;
     if (graph_worthwhile(cells, d->k) && left > full_adv * (SEG + 1)) {
       StepGraph sg;
-      if (sg.begin(st)) {
+      const bool hit = sg.lookup(make_graph_key(d, full_adv, d->workspace, n_whost));
+      if (hit || sg.begin(st)) {
         // error rows of a replayed segment land in staging rows (fixed addresses) and are copied to their place
         // in the caller's (k, B) / (k+1, B) arrays after every replay
         auto rows = [&](const npde::FieldView &v, float *l2_row, float *fd_row, cudaStream_t s) -> int {
@@ -1186,7 +1284,7 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
         };
         if (want_err) TRY(npde::reduce_ws_clear(w.red, w.red_bytes, B, N, st));  // once; reductions keep them clean
         int rc = NPDE_OK;
-        for (int i = 0; i < SEG && rc == NPDE_OK; ++i) {
+        for (int i = 0; i < SEG && rc == NPDE_OK && !hit; ++i) {
           rc = launch(npde::as_const(pad[i & 1]), pad[(i + 1) & 1], full_adv, sg.cs);
           if (rc == NPDE_OK && want_err)
             rc = rows(npde::as_const(pad[(i + 1) & 1]), w.stage_l2 + (size_t)i * B, w.stage_fd + (size_t)i * B, sg.cs);
@@ -1198,8 +1296,8 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
         if (want_err)
           TRY(rows(npde::as_const(pad[0]), d->err_l2 ? d->err_l2 + (size_t)(done - 1) * B : nullptr,
                    d->err_fd ? d->err_fd + (size_t)done * B : nullptr, st));
-        const int times = (left - 1) / (full_adv * SEG);
-        TRY(sg.finish());
+        int times = (left - 1) / (full_adv * SEG);
+        if (sg.finish() != NPDE_OK) times = 0;  // no graph after all: the plain loop below does the rest
         for (int r = 0; r < times; ++r) {
           TRY(sg.launch_once(st));
           if (d->err_l2)
@@ -1269,13 +1367,15 @@ int npde_iterate(const npde_iterate_desc *d, void *stream) {
   // launch-bound sizes: x_in -> A once, then replay the captured pair of steps A -> B -> A
   if (!want_err && graph_worthwhile(cells, d->k)) {
     StepGraph sg;
-    if (sg.begin(st)) {
-      int rc = step(bufA, bufB, sg.cs);
-      if (rc == NPDE_OK) rc = step(bufB, bufA, sg.cs);
+    const bool hit = sg.lookup(make_graph_key(d, 2, d->workspace, n_whost));
+    if (hit || sg.begin(st)) {
+      int rc = hit ? NPDE_OK : step(bufA, bufB, sg.cs);
+      if (rc == NPDE_OK && !hit) rc = step(bufB, bufA, sg.cs);
       if (rc != NPDE_OK) { sg.abort_capture(); return rc; }
       TRY(step(cur, bufA, stream));
       int times = (d->k - 1) / 2;
-      TRY(sg.finish_and_launch(times, st));
+      if (sg.finish() != NPDE_OK) times = 0;  // no graph after all: the plain loop below does the rest
+      for (int r = 0; r < times; ++r) TRY(sg.launch_once(st));
       cur = bufA;
       t = 1 + 2 * times;
     }
