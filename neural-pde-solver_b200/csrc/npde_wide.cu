@@ -40,6 +40,9 @@ constexpr int WSLOT = 1024;   // bytes of one row segment of a strip (32 lanes x
 // more rows); at L = 3 the depth does not matter.
 constexpr int WRING = NPDE_WRING;
 static_assert((WRING & (WRING - 1)) == 0 && WRING >= 2, "ring size: power of two");
+#ifndef NPDE_W_TMA
+#define NPDE_W_TMA 0  // 1: row segments arrive by TMA bulk copies (one elected lane, mbarrier completion), see wring_fill
+#endif
 #ifndef NPDE_WIDE_MIN_CTAS
 #define NPDE_WIDE_MIN_CTAS 8
 #endif
@@ -109,6 +112,40 @@ __device__ __forceinline__ void pin_reg(unsigned &v) { asm volatile("" : "+r"(v)
 __device__ __forceinline__ void pin_reg(unsigned &) {}
 #endif
 
+// ---- TMA (bulk asynchronous copy engine) primitives: mbarrier + cp.async.bulk global -> shared -------------------
+#ifdef NPDE_EMU
+__device__ __forceinline__ void mbar_init(void *, unsigned) {}
+__device__ __forceinline__ void mbar_fence_init() {}
+__device__ __forceinline__ void mbar_wait(void *, unsigned) {}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, void *) { memcpy(dst, src, bytes); }
+#else
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zero fill of the slots before the async writes
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+// one thread: announce `bytes` on the barrier and start the bulk copy that will complete them
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, void *bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"(b)
+               : "memory");
+}
+#endif
+
 __device__ __forceinline__ float wsel_bits(float v, unsigned keep, unsigned val) {
   return __uint_as_float((__float_as_uint(v) & keep) | val);
 }
@@ -153,6 +190,14 @@ struct WCtx {
   unsigned a_off, b_off;      // this lane's two 16-byte chunks inside a slot ({Q0,Q1} and {Q2,Q3}), swizzled
   unsigned fill_off;          // where chunk `lane` of a segment goes inside a slot (chunk lane+32: + 512)
   unsigned rslot;    // ring slot (byte offset) that holds x row it+1
+  // NPDE_W_TMA: the part of this strip's 1 KB segment that lies inside the virtual row (edge strips: the rest of a
+  // slot stays zero), the number of rows started / consumed so far (slot = n % WRING, barrier phase = n / WRING)
+  int tma_src, tma_dst, tma_bytes;
+  float wreg[4][9];  // NPDE_W_TMA: the weights in ordinary registers (the uniform registers serve the TMA operands;
+                     // with the weights there too ptxas re-loads them from the constant bank 19 times per two steps)
+  int pending;       // rows started and not yet consumed
+  unsigned phase;    // barrier phase of the slot `rslot` (flips when rslot wraps)
+  char *bars;        // WRING mbarriers behind the rings
   float top, bottom;
   int N, i0, i1, x_last, f_last, pitch, lane_l, lane_r;
 };
@@ -186,6 +231,14 @@ __device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, 
 // start the copy of one row segment (this strip's 32 groups = 1 KB) into a ring slot: lane l moves chunks l and l+32
 template <bool EDGE>
 __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const WCtx &x) {
+#if NPDE_W_TMA
+  // `chunk` is the (warp-uniform) start of the segment.  One bulk copy of its in-row part by an elected lane;
+  // completion is signalled on the slot's mbarrier (x and f rows share it).
+  if ((threadIdx.x & 31) == 0 && x.tma_bytes > 0)
+    tma_load_1d(slot + x.tma_dst, chunk + x.tma_src, (unsigned)x.tma_bytes,
+                x.bars + 8 * ((((unsigned)(slot - x.ring)) >> 10) & (unsigned)(WRING - 1)));
+  return;
+#endif
   __syncwarp();  // lanes write each other's bytes: everybody is done reading the slot's previous row
   if (EDGE) {
     // a chunk outside the virtual row is zero-filled (source size 0; the address passed is a valid one anyway)
@@ -233,7 +286,7 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
       for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
       if (MAIN) {
         // x.ffill points at f row it + WRING - 1: it joins the copy group of x row it + WRING below
-        if (it + WRING - 1 <= x.f_last) {
+        if (NPDE_W_TMA ? (it + WRING <= x.x_last) : (it + WRING - 1 <= x.f_last)) {  // TMA: x and f rows share a barrier
           wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
           x.ffill += x.pitch;
         }
@@ -262,8 +315,9 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
       if (it + WRING <= x.x_last) {  // x.fill points at row it + WRING: into the slot that was read one step ago
         wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
         x.fill += x.pitch;
+        if (NPDE_W_TMA) ++x.pending;
       }
-      cp_async_commit();
+      if (!NPDE_W_TMA) cp_async_commit();
     } else {
       // warm-up / drain / ring-row steps: a plain load (running these steps from the cp.async ring as well
       // measured 4% slower overall)
@@ -277,7 +331,11 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
 #pragma unroll
   for (int k = 1; k <= L; ++k) {
     const int rk = it - 1 - k;
+#if NPDE_W_TMA
+    const float *w = x.wreg[k - 1];
+#else
     const float *w = p.w[k - 1];
+#endif
     f2 (&mid)[4] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
     f2 (&top)[4] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
     NPDE_W_OPERANDS(rc, rl, rr);
@@ -315,8 +373,14 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
     }
   }
   if (MAIN) {  // row it+1 has landed (at most WRING - 1 younger groups pending): move it to registers
+#if NPDE_W_TMA
+    if (x.tma_bytes > 0) mbar_wait(x.bars + (x.rslot >> 7), x.phase);  // 8 bytes per barrier, 1 KB per slot
+    --x.pending;
+    if (x.rslot == (unsigned)(WRING - 1) * WSLOT) x.phase ^= 1u;  // the ring wraps after this slot
+#else
     cp_async_wait<WRING - 1>();
     __syncwarp();  // a lane's bytes were copied by other lanes
+#endif
     lds128(x.ring + x.rslot + x.a_off, s.X[P ^ 1][0], s.X[P ^ 1][1]);
     lds128(x.ring + x.rslot + x.b_off, s.X[P ^ 1][2], s.X[P ^ 1][3]);
     if (HASF) {  // f row `it` travelled in the same copy group
@@ -345,7 +409,7 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   x.delay = smem;
   x.ring = smem + DS * WSLOT;
   x.rslot = 0;
-  const int sw = (lane >> 2) & 1;
+  const int sw = NPDE_W_TMA ? 0 : (lane >> 2) & 1;  // a bulk copy lands linearly: no chunk swizzle
   x.a_off = 32u * lane + 16u * sw;
   x.b_off = 32u * lane + 16u * (1 - sw);
   x.fill_off = 16u * (lane ^ ((lane >> 3) & 1));
@@ -375,6 +439,26 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
     pin_reg(x.keep[c]);
     pin_reg(x.gval[c]);
   }
+  {
+    // in-row part of the strip's segment [v0, v0 + 32) groups of the virtual row [0, VG)
+    const int g_lo = max(v0, 0), g_hi = min(v0 + 32, p.VG);
+    x.tma_src = (g_lo - v0) * WCOLS;                 // floats from the segment start
+    x.tma_dst = (g_lo - v0) * WCOLS * 4;             // bytes from the slot start
+    x.tma_bytes = max(g_hi - g_lo, 0) * WCOLS * 4;
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        float v = l < L ? p.w[l][t] : 0.0f;
+#if NPDE_W_TMA && !defined(NPDE_EMU)
+        asm volatile("" : "+f"(v));  // opaque: a per-thread copy, not a uniform value
+#endif
+        x.wreg[l][t] = v;
+      }
+    x.pending = 0;
+    x.phase = 0;
+    x.bars = smem + (DS + (HASF ? 2 : 1) * WRING) * WSLOT;
+  }
   // uniform: the strip needs the EDGE code unless its 32 groups are interior groups of ONE image
   bool edge_strip = true;
   if (v0 >= 0 && v0 + 31 < p.VG) {
@@ -401,6 +485,13 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
     sts128(x.delay + d * WSLOT + x.a_off, zero2(), zero2());
     sts128(x.delay + d * WSLOT + x.b_off, zero2(), zero2());
   }
+#if NPDE_W_TMA
+#pragma unroll
+  for (int d = 0; d < (HASF ? 2 : 1) * WRING; ++d) {  // edge strips copy only the in-row part of a segment
+    sts128(x.ring + d * WSLOT + x.a_off, zero2(), zero2());
+    sts128(x.ring + d * WSLOT + x.b_off, zero2(), zero2());
+  }
+#endif
   __syncwarp();
 
   // input rows it = it_first .. it_last; the output row of a step is it - 1 - L
@@ -412,7 +503,7 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   const float *xin = p.in + lane_off;
   const float *fin_ = HASF ? p.f + lane_off : nullptr;
   // chunk `lane` of this strip's row segment; strip 0 starts one group left of the row (never dereferenced there)
-  const long seg_off = (long)v0 * WCOLS + 4 * lane;
+  const long seg_off = (long)v0 * WCOLS + (NPDE_W_TMA ? 0 : 4 * lane);  // TMA: the (warp-uniform) segment start
   // the first step runs with parity 0: slot 0 receives row it_first
   if (x.ld_ok) ld256(xin + (size_t)it_first * p.pitch, s.X[0]);
   if (HASF && it_first - 1 >= 1 && x.ld_ok) ld256(fin_ + (size_t)(it_first - 1) * p.pitch, s.pff);
@@ -431,6 +522,16 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
     if (it >= main_lo && it + 1 <= main_hi) {
       // fill the ring: x row `it` is in registers, rows it+1 .. it+WRING-1 start now (f: one row behind)
       x.rslot = 0;
+#if NPDE_W_TMA
+      // the slot numbering restarts at 0 with every main loop: bring the barrier phases along by re-initialising
+      // them (nothing is in flight here: the previous loop drained its copies)
+      if (lane == 0)
+        for (int d = 0; d < WRING; ++d) mbar_init(x.bars + 8 * d, HASF ? 2u : 1u);
+      mbar_fence_init();
+      __syncwarp();
+      x.pending = 0;
+      x.phase = 0;
+#endif
       x.fill = p.in + (size_t)(it + 1) * p.pitch + seg_off;
       if (HASF) x.ffill = p.f + (size_t)it * p.pitch + seg_off;
 #define NPDE_W_MAIN_LOOP(EDGE_)                                                     \
@@ -439,8 +540,9 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
       if (it + 1 + d <= x.x_last) {                                                 \
         wring_fill<EDGE_>(x.ring + d * WSLOT, x.fill, x);                           \
         x.fill += x.pitch;                                                          \
+        if (NPDE_W_TMA) ++x.pending;                                                \
       }                                                                             \
-      if (HASF && it + d <= x.f_last) {                                             \
+      if (HASF && (NPDE_W_TMA ? (it + 1 + d <= x.x_last) : (it + d <= x.f_last))) {  \
         wring_fill<EDGE_>(x.ring + (WRING + d) * WSLOT, x.ffill, x);                \
         x.ffill += x.pitch;                                                         \
       }                                                                             \
@@ -455,7 +557,18 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
       if (edge_strip) NPDE_W_MAIN_LOOP(true);
       else NPDE_W_MAIN_LOOP(false);
 #undef NPDE_W_MAIN_LOOP
+#if NPDE_W_TMA
+      // rows started but not consumed (the band ended first): their copies must land before the slots are reused
+      // or the CTA exits
+      while (x.pending > 0) {
+        if (x.tma_bytes > 0) mbar_wait(x.bars + (x.rslot >> 7), x.phase);
+        if (x.rslot == (unsigned)(WRING - 1) * WSLOT) x.phase ^= 1u;
+        x.rslot = (x.rslot + (unsigned)WSLOT) & (unsigned)(WRING * WSLOT - 1);
+        --x.pending;
+      }
+#else
       cp_async_wait<0>();
+#endif
       __syncwarp();
       // back to plain loads: row `it` is in registers (slot of parity 0)
       x.pin = xin + (size_t)(it + 1) * p.pitch;
@@ -549,7 +662,7 @@ WideGeom wide_geom(int B, int N) {
 
 template <int L>
 constexpr size_t wide_smem(bool hasf) {
-  return (size_t)WSLOT * (((L + 1 <= 4) ? 4 : 8) + (hasf ? 2 : 1) * WRING);
+  return (size_t)WSLOT * (((L + 1 <= 4) ? 4 : 8) + (hasf ? 2 : 1) * WRING) + (NPDE_W_TMA ? 8 * WRING : 0);
 }
 
 // resident warps of the kernel on the current device (cached per device)
