@@ -15,7 +15,38 @@ namespace {
 #else
 #define NPDE_GRID_CONSTANT __grid_constant__
 #endif
-#if defined(NPDE_EMU) || defined(NPDE_SCALAR_F2)
+#if !defined(NPDE_EMU) && defined(NPDE_F2_HALVES)
+// Tuning build: a pair is carried as two 32-bit values and packed only inside the packed instruction, so that every
+// loop-carried value is a 32-bit register for ptxas (which coalesces those across the back edge without copies).
+struct __align__(8) f2 { float x, y; };
+__device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; r.x = lo; r.y = hi; return r; }
+__device__ __forceinline__ float lo(f2 a) { return a.x; }
+__device__ __forceinline__ float hi(f2 a) { return a.y; }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%6, %7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "mul.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\n"
+      "sub.rn.f32x2 rd, ra, rb;\nmov.b64 {%0, %1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ f2 and2(f2 a, unsigned mlo, unsigned mhi) {
+  return mk2(__uint_as_float(__float_as_uint(a.x) & mlo), __uint_as_float(__float_as_uint(a.y) & mhi));
+}
+#elif defined(NPDE_EMU) || defined(NPDE_SCALAR_F2)
 struct __align__(8) f2 { float x, y; };
 __device__ __forceinline__ f2 mk2(float lo, float hi) { f2 r; r.x = lo; r.y = hi; return r; }
 __device__ __forceinline__ float lo(f2 a) { return a.x; }
@@ -86,7 +117,7 @@ __device__ __forceinline__ void cp_async_commit() {}
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() {}
 #else
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#ifdef NPDE_SCALAR_F2
+#if defined(NPDE_SCALAR_F2) || defined(NPDE_F2_HALVES)
 __device__ __forceinline__ void ld_pairs(const float *p, f2 &a, f2 &b) {
   const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
   a = mk2(v.x, v.y);

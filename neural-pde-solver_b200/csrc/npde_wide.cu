@@ -25,6 +25,11 @@
 #include "npde_common.cuh"
 #include "npde_internal.h"
 
+// Register pairs are carried as two 32-bit values in this translation unit (npde_f2.cuh): with 64-bit values ptxas
+// copies every loop-carried partial-sum row home at the end of the 2x unrolled loop (~80 MOVs per two row steps).
+#if !defined(NPDE_F2_PACKED64) && !defined(NPDE_SCALAR_F2) && !defined(NPDE_F2_HALVES)
+#define NPDE_F2_HALVES 1
+#endif
 #include "npde_f2.cuh"
 
 namespace {
@@ -32,6 +37,7 @@ namespace {
 constexpr int WCOLS = 8;      // columns per lane
 constexpr int WVALID = 30;    // lanes 1..30 of a strip store; lanes 0 and 31 are the halo (radius <= 8 columns)
 constexpr int WSLOT = 1024;   // bytes of one row segment of a strip (32 lanes x 8 columns x 4 bytes)
+constexpr int WMAX_EDGE = 1024;  // edge strips that can get their own band count (else: uniform bands)
 #ifndef NPDE_WRING
 #define NPDE_WRING 4
 #endif
@@ -46,6 +52,18 @@ static_assert((WRING & (WRING - 1)) == 0 && WRING >= 2, "ring size: power of two
 #ifndef NPDE_WIDE_MIN_CTAS
 #define NPDE_WIDE_MIN_CTAS 8
 #endif
+#ifndef NPDE_W_SKEW
+#define NPDE_W_SKEW 0
+#endif
+// NPDE_W_SKEW = 1: the stages of a step are SKEWED by one step -- conv stage k consumes the row that stage k-1
+// finished in the PREVIOUS step (kept in registers with its two halo values) instead of the row it finishes in the
+// same step.  Nothing computed in a step depends on anything else computed in that step, so the serial chain
+// Psi -> SHFL -> stage 1 -> SHFL -> ... -> stage L -> store (four shuffle latencies and four FFMA2 chains per row
+// step, with two resident warps per scheduler to hide them) disappears; the price is L more warm-up steps per band
+// and a y delay line of 2L instead of L rows.  Same arithmetic per cell, so results stay bit-identical.
+#if NPDE_W_SKEW && NPDE_W_TMA
+#error "NPDE_W_SKEW and NPDE_W_TMA are separate experiments"
+#endif
 
 struct WideParams {
   const float *in;
@@ -56,9 +74,24 @@ struct WideParams {
   int pitch;         // floats per virtual row = 8*VG
   int strips;        // ceil(VG / WVALID)
   int bands, band_rows;  // a CTA (one warp) takes rows [band*band_rows, (band+1)*band_rows) of one strip
+  // Edge strips (ring / padding columns inside: the masked loop costs ~1.24x the interior loop per row) are cut into
+  // bands_edge >= bands shorter bands so that every warp of the single wave finishes at the same time.  CTAs
+  // [0, strips*bands) are (strip, band < bands); the following n_edge*(bands_edge - bands) CTAs are the extra bands
+  // of the edge strips, listed in edge_strip[].
+  int bands_edge, band_rows_edge, n_edge;
   int act;
   float w[4][9];
+  unsigned short edge_strip[WMAX_EDGE];
 };
+
+// does the strip need the EDGE code?  (not if its 32 groups are interior groups of ONE image)
+__host__ __device__ __forceinline__ bool wide_strip_is_edge(int strip, int N, int G8, int VG) {
+  const int v0 = strip * WVALID - 1;
+  if (v0 < 0 || v0 + 31 >= VG) return true;
+  const int b0 = v0 / G8, g0 = v0 - b0 * G8;
+  const int g_hi = (N - 9) >= 0 ? (N - 9) / 8 : -1;  // last group whose eight columns are all interior
+  return !(g0 >= 1 && g0 + 31 <= g_hi);
+}
 
 // ---- 256-bit global and 128-bit shared accesses of a lane's row: pairs q[k] = {c_k, c_k+4} ----------------
 #ifdef NPDE_EMU
@@ -84,15 +117,35 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem, const float *g, boo
   else memset(smem, 0, 16);
 }
 #else
+#if defined(NPDE_SCALAR_F2) || defined(NPDE_F2_HALVES)
+__device__ __forceinline__ void ld256(const float *p, f2 (&q)[4]) {
+  float v[8];
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+#pragma unroll
+  for (int k = 0; k < 4; ++k) q[k] = mk2(v[2 * k], v[2 * k + 1]);
+}
+#else
 __device__ __forceinline__ void ld256(const float *p, f2 (&q)[4]) {
   asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];" : "=l"(q[0]), "=l"(q[1]), "=l"(q[2]), "=l"(q[3]) : "l"(p));
 }
+#endif
 // columns c0..c7 -> memory order (c0,c4,c1,c5,c2,c6,c3,c7), one STG.E.ENL2.256
 __device__ __forceinline__ void st256_cols(float *p, const float (&o)[8]) {
   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(o[0]), "f"(o[4]), "f"(o[1]),
                "f"(o[5]), "f"(o[2]), "f"(o[6]), "f"(o[3]), "f"(o[7])
                : "memory");
 }
+#if defined(NPDE_SCALAR_F2) || defined(NPDE_F2_HALVES)
+__device__ __forceinline__ void lds128(const char *s, f2 &a, f2 &b) {
+  const float4 v = *reinterpret_cast<const float4 *>(s);
+  a = mk2(v.x, v.y);
+  b = mk2(v.z, v.w);
+}
+__device__ __forceinline__ void sts128(char *s, f2 a, f2 b) {
+  *reinterpret_cast<float4 *>(s) = make_float4(a.x, a.y, b.x, b.y);
+}
+#else
 __device__ __forceinline__ void lds128(const char *s, f2 &a, f2 &b) {
   const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(s);
   a = v.x;
@@ -101,6 +154,7 @@ __device__ __forceinline__ void lds128(const char *s, f2 &a, f2 &b) {
 __device__ __forceinline__ void sts128(char *s, f2 a, f2 b) {
   *reinterpret_cast<ulonglong2 *>(s) = make_ulonglong2(a, b);
 }
+#endif
 __device__ __forceinline__ void cp_async16_zfill(void *smem, const float *g, bool valid) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g),
                "r"(valid ? 16 : 0)
@@ -174,6 +228,16 @@ struct WState {
   f2 S[L][2][4];   // S[k-1][P]: partial sums of stage k that have seen taps w0..w5 (this step finishes them),
                    // S[k-1][P^1]: taps w0..w2
   f2 pff[4];       // f row it-1, fetched one step earlier
+#if NPDE_W_SKEW
+  f2 R[L][4];          // R[k]: the row stage k finished in the previous step (k = 0: the residual r_0), masked
+  float Rl[L], Rr[L];  // its outer neighbours (columns c-1 and c8)
+#endif
+};
+
+// rows of the y delay line (power of two): y waits L steps, 2L with skewed stages (read before write when equal)
+template <int L>
+struct WDelay {
+  static constexpr int slots = NPDE_W_SKEW ? ((2 * L <= 4) ? 4 : 8) : ((L + 1 <= 4) ? 4 : 8);
 };
 
 struct WCtx {
@@ -202,26 +266,51 @@ struct WCtx {
   int N, i0, i1, x_last, f_last, pitch, lane_l, lane_r;
 };
 
-// left / right operand pairs of a row r[0..3] with outer neighbours hl (c-1) and hr (c8)
-#define NPDE_W_OPERANDS(r, hl, hr)            \
-  const f2 opl0 = mk2((hl), lo((r)[3]));      \
-  const f2 opr3 = mk2(hi((r)[0]), (hr))
+// Taps of a 3-wide stencil row on the four output pairs a[0..3] of a lane.  Operand row r[0..3] = pairs
+// {c_k, c_k+4}; hl / hr = the outer neighbours c-1 / c8.  Every tap whose left / right operand is a whole pair of
+// r is one packed FFMA2.  The two that are not -- the left tap of a[0] = {c0,c4} needs {c-1,c3}, the right tap of
+// a[3] = {c3,c7} needs {c4,c8} -- either build that pair (NPDE_W_OUTER_SCALAR = 0: register moves) or run as two
+// scalar FFMA on the halves (= 1; the halves representation of f2 makes that free of any packing).
+#ifndef NPDE_W_OUTER_SCALAR
+#define NPDE_W_OUTER_SCALAR 0
+#endif
+__device__ __forceinline__ f2 wtap_l(float w, float hl, const f2 (&r)[4], f2 acc) {
+#if NPDE_W_OUTER_SCALAR
+  return fma_lohi(w, hl, lo(r[3]), acc);
+#else
+  return fma2(bc2(w), mk2(hl, lo(r[3])), acc);
+#endif
+}
+__device__ __forceinline__ f2 wtap_r(float w, float hr, const f2 (&r)[4], f2 acc) {
+#if NPDE_W_OUTER_SCALAR
+  return fma_lohi(w, hi(r[0]), hr, acc);
+#else
+  return fma2(bc2(w), mk2(hi(r[0]), hr), acc);
+#endif
+}
+__device__ __forceinline__ f2 wtap_l_first(float w, float hl, const f2 (&r)[4]) {
+#if NPDE_W_OUTER_SCALAR
+  return mul_lohi(w, hl, lo(r[3]));
+#else
+  return mul2(bc2(w), mk2(hl, lo(r[3])));
+#endif
+}
 // three taps (wl, wc, wr) of one stencil row applied to the four output pairs a[0..3]
-__device__ __forceinline__ void wtaps(const f2 (&r)[4], f2 opl0, f2 opr3, float wl, float wc, float wr, f2 (&a)[4]) {
+__device__ __forceinline__ void wtaps(const f2 (&r)[4], float hl, float hr, float wl, float wc, float wr, f2 (&a)[4]) {
   const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
-  a[0] = fma2(l2, opl0, a[0]); a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[0] = wtap_l(wl, hl, r, a[0]);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
   a[1] = fma2(l2, r[0], a[1]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
   a[2] = fma2(l2, r[1], a[2]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
-  a[3] = fma2(l2, r[2], a[3]); a[3] = fma2(c2, r[3], a[3]); a[3] = fma2(r2, opr3, a[3]);
+  a[3] = fma2(l2, r[2], a[3]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r(wr, hr, r, a[3]);
 }
 // same for the first stencil row of an output: the first tap is a plain product (oracle conv3x3_img)
-__device__ __forceinline__ void wtaps_first(const f2 (&r)[4], f2 opl0, f2 opr3, float wl, float wc, float wr,
+__device__ __forceinline__ void wtaps_first(const f2 (&r)[4], float hl, float hr, float wl, float wc, float wr,
                                             f2 (&a)[4]) {
   const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
-  a[0] = mul2(l2, opl0); a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[0] = wtap_l_first(wl, hl, r);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
   a[1] = mul2(l2, r[0]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
   a[2] = mul2(l2, r[1]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
-  a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = fma2(r2, opr3, a[3]);
+  a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r(wr, hr, r, a[3]);
 }
 __device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, float &hl, float &hr) {
   hl = __shfl_sync(NPDE_FULL_MASK, hi(r[3]), lane_l);  // c7 of the left lane
@@ -250,8 +339,9 @@ __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const
   }
 }
 
-// One step: input row `it` is in s.X[P].  Stage 0 (Psi, residual) works on row it-1, conv stage k (1..L) on row
-// it-1-k, each consuming the row the previous stage produced in this step; the epilogue stores row it-1-L.
+// One step: input row `it` is in s.X[P].  Stage 0 (Psi, residual) works on row it-1; conv stage k (1..L) finishes row
+// it-1-k from the row stage k-1 produced in this step (NPDE_W_SKEW = 0), or row it-1-2k from the row stage k-1
+// produced in the previous step (NPDE_W_SKEW = 1); the epilogue stores the row stage L finished.
 // MAIN: every stage row is an interior row, the output row belongs to this piece and the rows to fetch exist
 //       (no row tests); x (and f) rows arrive through the cp.async ring.
 // EDGE: the strip contains ring / padding / out-of-range columns: stage outputs are masked to the interior
@@ -259,119 +349,138 @@ __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const
 // P:    step parity (the two x slots and the two partial-sum rows of a stage swap roles every step; a variant
 //       that rotates three slots per stage to avoid consume-then-overwrite register moves needs a 3x unrolled
 //       loop of 10 KB and measured 4% slower: instruction fetch).
+
+// ---- stage 0: y = Psi(x) - f and r_0 = y - x for row it-1 -> (rc, rl, rr); y into the delay line; fetch x row it+1
 template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P>
-__device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParams &p, int it, unsigned &woff) {
-  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
-  constexpr unsigned DMASK = DS * (unsigned)WSLOT - 1u;
+__device__ __forceinline__ void wide_stage0(WState<L> &s, WCtx &x, int it, unsigned woff, f2 (&rc)[4], float &rl,
+                                            float &rr) {
   constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
   const int N = x.N;
+  const f2 (&D)[4] = s.X[P];
+  f2 (&C)[4] = s.X[P ^ 1];
+  const int r0 = it - 1;
+  const f2 q = bc2(0.25f);
+  f2 y[4];  // taps in the oracle's order: up (in yu), left, right, down
+  y[0] = wtap_l(0.25f, s.xhl, C, s.yu[0]); y[0] = fma2(q, C[1], y[0]); y[0] = fma2(q, D[0], y[0]);
+  y[1] = fma2(q, C[0], s.yu[1]); y[1] = fma2(q, C[2], y[1]); y[1] = fma2(q, D[1], y[1]);
+  y[2] = fma2(q, C[1], s.yu[2]); y[2] = fma2(q, C[3], y[2]); y[2] = fma2(q, D[2], y[2]);
+  y[3] = fma2(q, C[2], s.yu[3]); y[3] = wtap_r(0.25f, s.xhr, C, y[3]); y[3] = fma2(q, D[3], y[3]);
+  if (HASF) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
+    if (MAIN) {
+      // x.ffill points at f row it + WRING - 1: it joins the copy group of x row it + WRING below
+      if (NPDE_W_TMA ? (it + WRING <= x.x_last) : (it + WRING - 1 <= x.f_last)) {  // TMA: x and f rows share a barrier
+        wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
+        x.ffill += x.pitch;
+      }
+    } else {
+      const int nf = it;  // f row used by stage 0 of the next step
+      if (nf <= x.x_last && nf >= 1 && nf <= N - 2 && x.ld_ok) ld256(x.pfin, s.pff);
+      else s.pff[0] = s.pff[1] = s.pff[2] = s.pff[3] = zero2();
+      x.pfin += x.pitch;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) rc[k] = sub2(y[k], C[k]);
+  if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc[0] = rc[1] = rc[2] = rc[3] = zero2();
+  if (EDGE) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rc[k] = and2(rc[k], x.keep[k], x.keep[k + 4]);
+  }
+  whalo(rc, x.lane_l, x.lane_r, rl, rr);
+  sts128(x.delay + woff + x.a_off, y[0], y[1]);  // y waits in the delay line
+  sts128(x.delay + woff + x.b_off, y[2], y[3]);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s.yu[k] = mul2(q, C[k]);  // first tap of the next output row: up = x[it-1]
+  whalo(D, x.lane_l, x.lane_r, s.xhl, s.xhr);           // row `it` is the next centre row
+  // ---- row it-1 is dead: fetch x row it+1 ----
+  if (MAIN) {
+    if (it + WRING <= x.x_last) {  // x.fill points at row it + WRING: into the slot that was read one step ago
+      wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
+      x.fill += x.pitch;
+      if (NPDE_W_TMA) ++x.pending;
+    }
+    if (!NPDE_W_TMA) cp_async_commit();
+  } else {
+    // warm-up / drain / ring-row steps: a plain load (running these steps from the cp.async ring as well
+    // measured 4% slower overall)
+    if (it + 1 <= x.x_last && x.ld_ok) ld256(x.pin, C);
+    else C[0] = C[1] = C[2] = C[3] = zero2();
+    x.pin += x.pitch;
+  }
+}
+
+// ---- conv stage k (1..L): consumes the row (in, il, ir) of stage k-1, finishes row rk.  k < L: the finished row
+// goes to (out, ol, orr) (may alias the input); k == L: epilogue with the y row at `roff` of the delay line.
+template <int L, int ACT, bool MAIN, bool EDGE, int P>
+__device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const WideParams &p, int k, int rk, unsigned roff,
+                                                const f2 (&in)[4], float il, float ir, f2 (&out)[4], float &ol,
+                                                float &orr) {
+  const int N = x.N;
+#if NPDE_W_TMA
+  const float *w = x.wreg[k - 1];
+#else
+  const float *w = p.w[k - 1];
+#endif
+  f2 (&mid)[4] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
+  f2 (&top)[4] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
+  f2 fin[4] = {mid[0], mid[1], mid[2], mid[3]};
+  wtaps(in, il, ir, w[6], w[7], w[8], fin);
+  wtaps(in, il, ir, w[3], w[4], w[5], top);        // becomes the "mid" row of the next step
+  wtaps_first(in, il, ir, w[0], w[1], w[2], mid);  // fresh "top" row of the next step
+  if (k < L) {
+    if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = fin[2] = fin[3] = zero2();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = EDGE ? and2(fin[j], x.keep[j], x.keep[j + 4]) : fin[j];
+    whalo(out, x.lane_l, x.lane_r, ol, orr);
+  } else {
+    if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+      float o[8];
+      if (MAIN || (rk >= 1 && rk <= N - 2)) {
+        f2 ya, yb, yc, yd;
+        lds128(x.delay + roff + x.a_off, ya, yb);
+        lds128(x.delay + roff + x.b_off, yc, yd);
+        o[0] = wadd_act<ACT>(lo(ya), lo(fin[0])); o[4] = wadd_act<ACT>(hi(ya), hi(fin[0]));
+        o[1] = wadd_act<ACT>(lo(yb), lo(fin[1])); o[5] = wadd_act<ACT>(hi(yb), hi(fin[1]));
+        o[2] = wadd_act<ACT>(lo(yc), lo(fin[2])); o[6] = wadd_act<ACT>(hi(yc), hi(fin[2]));
+        o[3] = wadd_act<ACT>(lo(yd), lo(fin[3])); o[7] = wadd_act<ACT>(hi(yd), hi(fin[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
+      }
+      if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value (or 0: padding)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = wsel_bits(o[c], x.keep[c], x.gval[c]);
+      }
+      if (x.st_ok) st256_cols(x.pout, o);
+    }
+    if (MAIN || rk >= 0) x.pout += x.pitch;  // invariant: pout points at row max(rk + 1, 0) afterwards
+  }
+}
+
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P>
+__device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParams &p, int it, unsigned &woff) {
+  constexpr int DS = WDelay<L>::slots;
+  constexpr unsigned DMASK = DS * (unsigned)WSLOT - 1u;
+  constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
+#if NPDE_W_SKEW
+  // y of row it-1-2L was written 2L steps ago (DS == 2L: the slot this step's stage 0 overwrites afterwards)
+  const unsigned roff = (woff + (DS - 2 * L) * (unsigned)WSLOT) & DMASK;
+  // last stage first: stage k reads what stage k-1 left in the previous step, then stage k-1 replaces it
+#pragma unroll
+  for (int k = L; k >= 1; --k)
+    wide_conv_stage<L, ACT, MAIN, EDGE, P>(s, x, p, k, it - 1 - 2 * k, roff, s.R[k - 1], s.Rl[k - 1], s.Rr[k - 1],
+                                           s.R[k < L ? k : 0], s.Rl[k < L ? k : 0], s.Rr[k < L ? k : 0]);
+  wide_stage0<L, ACT, HASF, MAIN, EDGE, P>(s, x, it, woff, s.R[0], s.Rl[0], s.Rr[0]);
+#else
   const unsigned roff = (woff + (DS - L) * (unsigned)WSLOT) & DMASK;  // y written L steps ago
   f2 rc[4];
   float rl, rr;
-
-  // ---- stage 0: y = Psi(x) - f and r_0 = y - x for row it-1 ----
-  {
-    const f2 (&D)[4] = s.X[P];
-    f2 (&C)[4] = s.X[P ^ 1];
-    const int r0 = it - 1;
-    const f2 q = bc2(0.25f);
-    NPDE_W_OPERANDS(C, s.xhl, s.xhr);
-    f2 y[4];  // taps in the oracle's order: up (in yu), left, right, down
-    y[0] = fma2(q, opl0, s.yu[0]); y[0] = fma2(q, C[1], y[0]); y[0] = fma2(q, D[0], y[0]);
-    y[1] = fma2(q, C[0], s.yu[1]); y[1] = fma2(q, C[2], y[1]); y[1] = fma2(q, D[1], y[1]);
-    y[2] = fma2(q, C[1], s.yu[2]); y[2] = fma2(q, C[3], y[2]); y[2] = fma2(q, D[2], y[2]);
-    y[3] = fma2(q, C[2], s.yu[3]); y[3] = fma2(q, opr3, y[3]); y[3] = fma2(q, D[3], y[3]);
-    if (HASF) {
+  wide_stage0<L, ACT, HASF, MAIN, EDGE, P>(s, x, it, woff, rc, rl, rr);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
-      if (MAIN) {
-        // x.ffill points at f row it + WRING - 1: it joins the copy group of x row it + WRING below
-        if (NPDE_W_TMA ? (it + WRING <= x.x_last) : (it + WRING - 1 <= x.f_last)) {  // TMA: x and f rows share a barrier
-          wring_fill<EDGE>(x.ring + WRING * WSLOT + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.ffill, x);
-          x.ffill += x.pitch;
-        }
-      } else {
-        const int nf = it;  // f row used by stage 0 of the next step
-        if (nf <= x.x_last && nf >= 1 && nf <= N - 2 && x.ld_ok) ld256(x.pfin, s.pff);
-        else s.pff[0] = s.pff[1] = s.pff[2] = s.pff[3] = zero2();
-        x.pfin += x.pitch;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) rc[k] = sub2(y[k], C[k]);
-    if (!MAIN && !(r0 >= 1 && r0 <= N - 2)) rc[0] = rc[1] = rc[2] = rc[3] = zero2();
-    if (EDGE) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) rc[k] = and2(rc[k], x.keep[k], x.keep[k + 4]);
-    }
-    whalo(rc, x.lane_l, x.lane_r, rl, rr);
-    sts128(x.delay + woff + x.a_off, y[0], y[1]);  // y waits L steps in the delay line
-    sts128(x.delay + woff + x.b_off, y[2], y[3]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) s.yu[k] = mul2(q, C[k]);  // first tap of the next output row: up = x[it-1]
-    whalo(D, x.lane_l, x.lane_r, s.xhl, s.xhr);           // row `it` is the next centre row
-    // ---- row it-1 is dead: fetch x row it+1 ----
-    if (MAIN) {
-      if (it + WRING <= x.x_last) {  // x.fill points at row it + WRING: into the slot that was read one step ago
-        wring_fill<EDGE>(x.ring + ((x.rslot + (WRING - 1) * (unsigned)WSLOT) & RMASK), x.fill, x);
-        x.fill += x.pitch;
-        if (NPDE_W_TMA) ++x.pending;
-      }
-      if (!NPDE_W_TMA) cp_async_commit();
-    } else {
-      // warm-up / drain / ring-row steps: a plain load (running these steps from the cp.async ring as well
-      // measured 4% slower overall)
-      if (it + 1 <= x.x_last && x.ld_ok) ld256(x.pin, C);
-      else C[0] = C[1] = C[2] = C[3] = zero2();
-      x.pin += x.pitch;
-    }
-  }
-
-  // ---- conv stages 1 .. L on rows it-2 .. it-1-L ----
-#pragma unroll
-  for (int k = 1; k <= L; ++k) {
-    const int rk = it - 1 - k;
-#if NPDE_W_TMA
-    const float *w = x.wreg[k - 1];
-#else
-    const float *w = p.w[k - 1];
+  for (int k = 1; k <= L; ++k) wide_conv_stage<L, ACT, MAIN, EDGE, P>(s, x, p, k, it - 1 - k, roff, rc, rl, rr, rc, rl, rr);
 #endif
-    f2 (&mid)[4] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
-    f2 (&top)[4] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
-    NPDE_W_OPERANDS(rc, rl, rr);
-    f2 fin[4] = {mid[0], mid[1], mid[2], mid[3]};
-    wtaps(rc, opl0, opr3, w[6], w[7], w[8], fin);
-    wtaps(rc, opl0, opr3, w[3], w[4], w[5], top);        // becomes the "mid" row of the next step
-    wtaps_first(rc, opl0, opr3, w[0], w[1], w[2], mid);  // fresh "top" row of the next step
-    if (k < L) {
-      if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = fin[2] = fin[3] = zero2();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rc[j] = EDGE ? and2(fin[j], x.keep[j], x.keep[j + 4]) : fin[j];
-      whalo(rc, x.lane_l, x.lane_r, rl, rr);
-    } else {
-      if (MAIN || (rk >= x.i0 && rk < x.i1)) {
-        float o[8];
-        if (MAIN || (rk >= 1 && rk <= N - 2)) {
-          f2 ya, yb, yc, yd;
-          lds128(x.delay + roff + x.a_off, ya, yb);
-          lds128(x.delay + roff + x.b_off, yc, yd);
-          o[0] = wadd_act<ACT>(lo(ya), lo(fin[0])); o[4] = wadd_act<ACT>(hi(ya), hi(fin[0]));
-          o[1] = wadd_act<ACT>(lo(yb), lo(fin[1])); o[5] = wadd_act<ACT>(hi(yb), hi(fin[1]));
-          o[2] = wadd_act<ACT>(lo(yc), lo(fin[2])); o[6] = wadd_act<ACT>(hi(yc), hi(fin[2]));
-          o[3] = wadd_act<ACT>(lo(yd), lo(fin[3])); o[7] = wadd_act<ACT>(hi(yd), hi(fin[3]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = (rk == 0 ? x.top : x.bottom);  // ring row: pad then G
-        }
-        if (EDGE) {  // pad + G on the columns: non-interior columns take the Dirichlet value (or 0: padding)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) o[c] = wsel_bits(o[c], x.keep[c], x.gval[c]);
-        }
-        if (x.st_ok) st256_cols(x.pout, o);
-      }
-      if (MAIN || rk >= 0) x.pout += x.pitch;  // invariant: pout points at row max(rk + 1, 0) afterwards
-    }
-  }
   if (MAIN) {  // row it+1 has landed (at most WRING - 1 younger groups pending): move it to registers
 #if NPDE_W_TMA
     if (x.tma_bytes > 0) mbar_wait(x.bars + (x.rslot >> 7), x.phase);  // 8 bytes per barrier, 1 KB per slot
@@ -396,7 +505,8 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
 template <int L, int ACT, bool HASF>
 __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i0, int i1, char *smem) {
   constexpr int R = L + 1;
-  constexpr int DS = (L + 1 <= 4) ? 4 : 8;
+  constexpr int DS = WDelay<L>::slots;
+  constexpr int LAT = NPDE_W_SKEW ? 2 * L : L;  // steps between the arrival of x row i+1 and the store of output row i
   WCtx x;
   const int lane = threadIdx.x & 31, N = p.N;
   x.lane_l = (lane + 31) & 31;
@@ -404,7 +514,11 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   x.N = N;
   x.i0 = i0;
   x.i1 = i1;
+#ifdef NPDE_W_NOMEM
+  x.pitch = 0;  // DEVELOPMENT: every row step touches the same row (compute-only timing; results are garbage)
+#else
   x.pitch = p.pitch;
+#endif
   x.safe = p.in;
   x.delay = smem;
   x.ring = smem + DS * WSLOT;
@@ -460,12 +574,7 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
     x.bars = smem + (DS + (HASF ? 2 : 1) * WRING) * WSLOT;
   }
   // uniform: the strip needs the EDGE code unless its 32 groups are interior groups of ONE image
-  bool edge_strip = true;
-  if (v0 >= 0 && v0 + 31 < p.VG) {
-    const int b0 = v0 / p.G8, g0 = v0 - b0 * p.G8;
-    const int g_hi = (N - 9) >= 0 ? (N - 9) / 8 : -1;  // last group whose eight columns are all interior
-    edge_strip = !(g0 >= 1 && g0 + 31 <= g_hi);
-  }
+  const bool edge_strip = wide_strip_is_edge(strip, N, p.G8, p.VG);
 
   WState<L> s;
 #pragma unroll
@@ -479,6 +588,14 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
 #pragma unroll
   for (int k = 0; k < 4; ++k) s.yu[k] = s.pff[k] = zero2();
   s.xhl = s.xhr = 0.0f;
+#if NPDE_W_SKEW
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    s.Rl[l] = s.Rr[l] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.R[l][k] = zero2();
+  }
+#endif
   __syncwarp();  // a previous piece of this warp is done with the shared memory
 #pragma unroll
   for (int d = 0; d < DS; ++d) {
@@ -494,9 +611,9 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
 #endif
   __syncwarp();
 
-  // input rows it = it_first .. it_last; the output row of a step is it - 1 - L
+  // input rows it = it_first .. it_last; the output row of a step is it - 1 - LAT
   const int it_first = max(i0 - R, 0);  // rows above the grid are zeros == the initial state
-  const int it_last = i1 + L;
+  const int it_last = i1 + LAT;
   x.x_last = min(i1 - 1 + R, N - 1);    // last input row that exists and matters
   x.f_last = min(x.x_last, N - 2);      // last row of f that is ever read
   const size_t lane_off = (size_t)max(vg, 0) * WCOLS;
@@ -511,11 +628,11 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   x.pin = xin + (size_t)(it_first + 1) * p.pitch;
   x.pfin = HASF ? fin_ + (size_t)it_first * p.pitch : nullptr;
   x.fill = x.ffill = nullptr;
-  x.pout = p.out + lane_off + (size_t)max(it_first - 1 - L, 0) * p.pitch;
+  x.pout = p.out + lane_off + (size_t)max(it_first - 1 - LAT, 0) * p.pitch;
   unsigned woff = 0;
 
-  // MAIN range of `it`: stage rows it-1-L .. it-1 interior, output row it-1-L inside the piece, x row it+1 exists
-  const int main_lo = max(L + 2, i0 + L + 1);
+  // MAIN range of `it`: stage rows it-1-LAT .. it-1 interior, output row it-1-LAT inside the piece, x row it+1 exists
+  const int main_lo = max(LAT + 2, i0 + LAT + 1);
   const int main_hi = min(N - 2, x.x_last - 1);
   int it = it_first;  // (it - it_first) is even at the top of this loop: parities 0, 1 per trip
   while (it <= it_last) {
@@ -589,8 +706,18 @@ k_conv_wide(const NPDE_GRID_CONSTANT WideParams p) {
   // are contiguous in memory (one long DRAM burst per row of the band).  The work item depends on blockIdx only:
   // ptxas can prove that the strip bookkeeping and the loop versioning are warp-uniform and keeps the weights in
   // uniform registers.
-  const int strip = (int)blockIdx.x % p.strips, band = (int)blockIdx.x / p.strips;
-  const int i0 = band * p.band_rows, i1 = min(i0 + p.band_rows, p.N);
+  int strip, band;
+  const int uniform_ctas = p.strips * p.bands;
+  if ((int)blockIdx.x < uniform_ctas) {
+    strip = (int)blockIdx.x % p.strips;
+    band = (int)blockIdx.x / p.strips;
+  } else {  // the extra bands of the edge strips
+    const int e = (int)blockIdx.x - uniform_ctas;
+    strip = p.edge_strip[e % p.n_edge];
+    band = p.bands + e / p.n_edge;
+  }
+  const int rows = (p.bands_edge > p.bands && wide_strip_is_edge(strip, p.N, p.G8, p.VG)) ? p.band_rows_edge : p.band_rows;
+  const int i0 = band * rows, i1 = min(i0 + rows, p.N);
   if (i0 < i1) wide_piece<L, ACT, HASF>(p, strip, i0, i1, reinterpret_cast<char *>(wsm));
 }
 
@@ -662,14 +789,14 @@ WideGeom wide_geom(int B, int N) {
 
 template <int L>
 constexpr size_t wide_smem(bool hasf) {
-  return (size_t)WSLOT * (((L + 1 <= 4) ? 4 : 8) + (hasf ? 2 : 1) * WRING) + (NPDE_W_TMA ? 8 * WRING : 0);
+  return (size_t)WSLOT * (WDelay<L>::slots + (hasf ? 2 : 1) * WRING) + (NPDE_W_TMA ? 8 * WRING : 0);
 }
 
 // resident warps of the kernel on the current device (cached per device)
 int wide_slots(const void *kernel, size_t smem, std::atomic<int> *cache /* one entry per device */) {
 #ifdef NPDE_EMU
   (void)kernel; (void)smem; (void)cache;
-  return 7;  // small on purpose: several bands per strip in the emulator
+  return 8;  // small on purpose: several bands per strip in the emulator
 #else
   int dev = 0, sms = 0, blocks = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
@@ -726,7 +853,34 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
   if (force_bands > 0) bands = force_bands;
   p.band_rows = (p.N + bands - 1) / bands;
   p.bands = (p.N + p.band_rows - 1) / p.band_rows;
-  dim3 grid((unsigned)((long)p.bands * p.strips)), block(npde::STREAM_THREADS);
+  // Edge strips: ~5/4 of the interior cost per row -> 5/4 as many (shorter) bands, if the wave has room for them.
+  p.bands_edge = p.bands;
+  p.band_rows_edge = p.band_rows;
+  p.n_edge = 0;
+  long ctas = (long)p.bands * p.strips;
+  if (force_bands <= 0 && p.strips <= 65535 && wide_env_int("NPDE_WIDE_EDGE_BANDS", 1) != 0) {
+    int n_edge = 0;
+    for (int s = 0; s < p.strips && n_edge <= WMAX_EDGE; ++s)
+      if (wide_strip_is_edge(s, p.N, p.G8, p.VG)) {
+        if (n_edge < WMAX_EDGE) p.edge_strip[n_edge] = (unsigned short)s;
+        ++n_edge;
+      }
+    if (n_edge > 0 && n_edge < p.strips && n_edge <= WMAX_EDGE) {
+      int want = (p.bands * 5 + 3) / 4;
+      while (want > p.bands && (ctas + (long)n_edge * (want - p.bands) > slots || p.N / want < minrows)) --want;
+      if (want > p.bands) {
+        const int rows = (p.N + want - 1) / want;
+        const int nb = (p.N + rows - 1) / rows;
+        if (nb > p.bands) {
+          p.bands_edge = nb;
+          p.band_rows_edge = rows;
+          p.n_edge = n_edge;
+          ctas += (long)n_edge * (nb - p.bands);
+        }
+      }
+    }
+  }
+  dim3 grid((unsigned)ctas), block(npde::STREAM_THREADS);
   NPDE_LAUNCH((k_conv_wide<L, ACT, HASF>), grid, block, smem, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;

@@ -833,10 +833,12 @@ def test_graph_replay_paths_vs_oracle(oracle, mask, has_f):
 @pytest.mark.parametrize("B,N,L,has_f,act,k", [(3, 129, 3, False, "clamp", 5), (2, 257, 3, True, "none", 4),
                                                (7, 33, 2, True, "clamp", 6), (13, 17, 1, False, "clamp", 3),
                                                (4, 9, 4, False, "none", 3), (1, 65, 3, False, "sigmoid", 3),
-                                               (31, 17, 3, True, "clamp", 4), (2, 12, 3, False, "clamp", 3)])
+                                               (31, 17, 3, True, "clamp", 4), (2, 12, 3, False, "clamp", 3),
+                                               (1, 513, 2, False, "clamp", 3)])
 def test_wide_kernel_vs_oracle(be, oracle, B, N, L, has_f, act, k, tmp_path, monkeypatch):
     """k_conv_wide: batch-interleaved W8 layout, eight columns per lane, strips that span several images and
-    pieces that straddle strips (the emulator build cuts the work into 5 pieces of >= 6 rows).  k fused steps
+    pieces that straddle strips (the emulator build has 8 warp slots: several bands per strip; 1 x 513^2 has an
+    interior strip between two edge strips, which get one band more than it).  k fused steps
     through npde_iterate (pack -> k launches -> unpack) against the CPU oracle, bit for bit (sigmoid: 1e-5)."""
     rng = np.random.RandomState(B * 1000 + N + L)
     bc = rng.rand(B, 4).astype(np.float32)
