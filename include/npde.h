@@ -257,6 +257,14 @@ int npde_unpack(const float *packed, float *x, int B, int N, void *stream);  /* 
  * 1 <= n_layers <= 4, w_host = HOST weights (n_layers,3,3); f_packed: packed source or NULL; in != out. */
 int npde_conv_step_packed(const float *in_packed, float *out_packed, const float *bc, const float *f_packed,
                           const float *w_host, int n_layers, int act, int B, int N, void *stream);
+/* k applications of Phi_H ping-ponging between two W8 fields: application t reads (t even ? a : b) and writes the
+ * other one, so the k-th iterate is in (k even ? a : b).  The k-step loop of heat_utils.py:163-181 / generation.py:
+ * 86-93 for a driver that keeps its iterate in the packed layout between residual checks (no layout pass per call). */
+int npde_conv_iterate_packed(float *a_packed, float *b_packed, const float *bc, const float *f_packed,
+                             const float *w_host, int n_layers, int act, int B, int N, int k, void *stream);
+/* fd_error(x, bc, f, aggregate='max') (utils/heat_utils.py:108-121, square domain) of a W8 field -> err[B];
+ * bit-identical to npde_fd_error on the unpacked field. */
+int npde_fd_error_packed(const float *packed, const float *f_packed, float *err, int B, int N, void *stream);
 
 #ifdef __cplusplus
 }

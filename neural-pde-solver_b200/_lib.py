@@ -75,6 +75,8 @@ PROTOTYPES = {
     "npde_pack": (_int, [_vp, _vp, _int, _int, _vp]),
     "npde_unpack": (_int, [_vp, _vp, _int, _int, _vp]),
     "npde_conv_step_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp]),
+    "npde_conv_iterate_packed": (_int, [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _vp]),
+    "npde_fd_error_packed": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
 }
 
 _lib = None

@@ -1586,4 +1586,22 @@ int npde_conv_step_packed(const float *in_packed, float *out_packed, const float
   return npde::conv_wide(in_packed, out_packed, bc, f_packed, w_host, n_layers, act, B, N, S(stream));
 }
 
+int npde_conv_iterate_packed(float *a_packed, float *b_packed, const float *bc, const float *f_packed,
+                             const float *w_host, int n_layers, int act, int B, int N, int k, void *stream) {
+  TRY(npde::check_common(a_packed, b_packed, B, N));
+  if (!bc || !w_host) return NPDE_ERR_NULL;
+  if (act < NPDE_ACT_NONE || act > NPDE_ACT_SIGMOID) return NPDE_ERR_ACT;
+  if (n_layers < 1 || n_layers > 4) return NPDE_ERR_LAYERS;
+  if (k < 0) return NPDE_ERR_ARG;
+  float *buf[2] = {a_packed, b_packed};
+  for (int t = 0; t < k; ++t)
+    TRY(npde::conv_wide(buf[t & 1], buf[(t + 1) & 1], bc, f_packed, w_host, n_layers, act, B, N, S(stream)));
+  return NPDE_OK;
+}
+
+int npde_fd_error_packed(const float *packed, const float *f_packed, float *err, int B, int N, void *stream) {
+  if (B < 1 || N < 1) return NPDE_ERR_SIZE;
+  return npde::wide_fd_error_max(packed, f_packed, err, B, N, S(stream));
+}
+
 }  // extern "C"

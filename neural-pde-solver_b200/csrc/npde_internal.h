@@ -147,6 +147,8 @@ size_t wide_field_floats(int B, int N);
 bool conv_wide_supported(int bc_kind, int n_layers, const float *w_host, int B, int N);
 int wide_pack(const float *x_ref, float *wide, int B, int N, cudaStream_t st);
 int wide_unpack(const float *wide, float *x_ref, int B, int N, cudaStream_t st);
+// fd_error('max') of a W8 field (f_wide: the source in the W8 layout or nullptr) -> err[B]
+int wide_fd_error_max(const float *wide, const float *f_wide, float *err, int B, int N, cudaStream_t st);
 // one Phi_H application W8 -> W8 (in != out, 32-byte aligned); f_wide: the source in the W8 layout or nullptr
 int conv_wide(const float *in, float *out, const float *bc4, const float *f_wide, const float *w_host, int n_layers,
               int act, int B, int N, cudaStream_t st);

@@ -20,6 +20,7 @@
 // explicit fma.rn / mul.rn / sub.rn only, so iterates stay bit-identical to k_conv_stream and the CPU oracle.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "npde_common.cuh"
@@ -200,6 +201,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 }
 #endif
 
+#ifdef NPDE_EMU
+__device__ __forceinline__ void pdl_wait_prior_grids() {}
+__device__ __forceinline__ void pdl_launch_dependents() {}
+#else
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 __device__ __forceinline__ float wsel_bits(float v, unsigned keep, unsigned val) {
   return __uint_as_float((__float_as_uint(v) & keep) | val);
 }
@@ -272,45 +281,42 @@ struct WCtx {
 // a[3] = {c3,c7} needs {c4,c8} -- either build that pair (NPDE_W_OUTER_SCALAR = 0: register moves) or run as two
 // scalar FFMA on the halves (= 1; the halves representation of f2 makes that free of any packing).
 #ifndef NPDE_W_OUTER_SCALAR
-#define NPDE_W_OUTER_SCALAR 0
+#define NPDE_W_OUTER_SCALAR 3  // the layer count L that runs the two outer taps as scalar FFMA (measured: L = 3
+                               // 116.3 vs 117.4 us sustained; L = 4 is 1% slower with it); 0: never
 #endif
+template <bool OS>
 __device__ __forceinline__ f2 wtap_l(float w, float hl, const f2 (&r)[4], f2 acc) {
-#if NPDE_W_OUTER_SCALAR
-  return fma_lohi(w, hl, lo(r[3]), acc);
-#else
+  if (OS) return fma_lohi(w, hl, lo(r[3]), acc);
   return fma2(bc2(w), mk2(hl, lo(r[3])), acc);
-#endif
 }
+template <bool OS>
 __device__ __forceinline__ f2 wtap_r(float w, float hr, const f2 (&r)[4], f2 acc) {
-#if NPDE_W_OUTER_SCALAR
-  return fma_lohi(w, hi(r[0]), hr, acc);
-#else
+  if (OS) return fma_lohi(w, hi(r[0]), hr, acc);
   return fma2(bc2(w), mk2(hi(r[0]), hr), acc);
-#endif
 }
+template <bool OS>
 __device__ __forceinline__ f2 wtap_l_first(float w, float hl, const f2 (&r)[4]) {
-#if NPDE_W_OUTER_SCALAR
-  return mul_lohi(w, hl, lo(r[3]));
-#else
+  if (OS) return mul_lohi(w, hl, lo(r[3]));
   return mul2(bc2(w), mk2(hl, lo(r[3])));
-#endif
 }
 // three taps (wl, wc, wr) of one stencil row applied to the four output pairs a[0..3]
+template <bool OS>
 __device__ __forceinline__ void wtaps(const f2 (&r)[4], float hl, float hr, float wl, float wc, float wr, f2 (&a)[4]) {
   const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
-  a[0] = wtap_l(wl, hl, r, a[0]);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[0] = wtap_l<OS>(wl, hl, r, a[0]);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
   a[1] = fma2(l2, r[0], a[1]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
   a[2] = fma2(l2, r[1], a[2]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
-  a[3] = fma2(l2, r[2], a[3]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r(wr, hr, r, a[3]);
+  a[3] = fma2(l2, r[2], a[3]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r<OS>(wr, hr, r, a[3]);
 }
 // same for the first stencil row of an output: the first tap is a plain product (oracle conv3x3_img)
+template <bool OS>
 __device__ __forceinline__ void wtaps_first(const f2 (&r)[4], float hl, float hr, float wl, float wc, float wr,
                                             f2 (&a)[4]) {
   const f2 l2 = bc2(wl), c2 = bc2(wc), r2 = bc2(wr);
-  a[0] = wtap_l_first(wl, hl, r);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
+  a[0] = wtap_l_first<OS>(wl, hl, r);  a[0] = fma2(c2, r[0], a[0]); a[0] = fma2(r2, r[1], a[0]);
   a[1] = mul2(l2, r[0]); a[1] = fma2(c2, r[1], a[1]); a[1] = fma2(r2, r[2], a[1]);
   a[2] = mul2(l2, r[1]); a[2] = fma2(c2, r[2], a[2]); a[2] = fma2(r2, r[3], a[2]);
-  a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r(wr, hr, r, a[3]);
+  a[3] = mul2(l2, r[2]); a[3] = fma2(c2, r[3], a[3]); a[3] = wtap_r<OS>(wr, hr, r, a[3]);
 }
 __device__ __forceinline__ void whalo(const f2 (&r)[4], int lane_l, int lane_r, float &hl, float &hr) {
   hl = __shfl_sync(NPDE_FULL_MASK, hi(r[3]), lane_l);  // c7 of the left lane
@@ -356,15 +362,16 @@ __device__ __forceinline__ void wide_stage0(WState<L> &s, WCtx &x, int it, unsig
                                             float &rr) {
   constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
   const int N = x.N;
+  constexpr bool OS = (L == NPDE_W_OUTER_SCALAR);
   const f2 (&D)[4] = s.X[P];
   f2 (&C)[4] = s.X[P ^ 1];
   const int r0 = it - 1;
   const f2 q = bc2(0.25f);
   f2 y[4];  // taps in the oracle's order: up (in yu), left, right, down
-  y[0] = wtap_l(0.25f, s.xhl, C, s.yu[0]); y[0] = fma2(q, C[1], y[0]); y[0] = fma2(q, D[0], y[0]);
+  y[0] = wtap_l<OS>(0.25f, s.xhl, C, s.yu[0]); y[0] = fma2(q, C[1], y[0]); y[0] = fma2(q, D[0], y[0]);
   y[1] = fma2(q, C[0], s.yu[1]); y[1] = fma2(q, C[2], y[1]); y[1] = fma2(q, D[1], y[1]);
   y[2] = fma2(q, C[1], s.yu[2]); y[2] = fma2(q, C[3], y[2]); y[2] = fma2(q, D[2], y[2]);
-  y[3] = fma2(q, C[2], s.yu[3]); y[3] = wtap_r(0.25f, s.xhr, C, y[3]); y[3] = fma2(q, D[3], y[3]);
+  y[3] = fma2(q, C[2], s.yu[3]); y[3] = wtap_r<OS>(0.25f, s.xhr, C, y[3]); y[3] = fma2(q, D[3], y[3]);
   if (HASF) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) y[k] = sub2(y[k], s.pff[k]);
@@ -426,9 +433,10 @@ __device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const Wid
   f2 (&mid)[4] = s.S[k - 1][P];      // taps w0..w5 done: finished by this row
   f2 (&top)[4] = s.S[k - 1][P ^ 1];  // taps w0..w2 done
   f2 fin[4] = {mid[0], mid[1], mid[2], mid[3]};
-  wtaps(in, il, ir, w[6], w[7], w[8], fin);
-  wtaps(in, il, ir, w[3], w[4], w[5], top);        // becomes the "mid" row of the next step
-  wtaps_first(in, il, ir, w[0], w[1], w[2], mid);  // fresh "top" row of the next step
+  constexpr bool OS = (L == NPDE_W_OUTER_SCALAR);
+  wtaps<OS>(in, il, ir, w[6], w[7], w[8], fin);
+  wtaps<OS>(in, il, ir, w[3], w[4], w[5], top);        // becomes the "mid" row of the next step
+  wtaps_first<OS>(in, il, ir, w[0], w[1], w[2], mid);  // fresh "top" row of the next step
   if (k < L) {
     if (!MAIN && !(rk >= 1 && rk <= N - 2)) fin[0] = fin[1] = fin[2] = fin[3] = zero2();
 #pragma unroll
@@ -706,6 +714,11 @@ k_conv_wide(const NPDE_GRID_CONSTANT WideParams p) {
   // are contiguous in memory (one long DRAM burst per row of the band).  The work item depends on blockIdx only:
   // ptxas can prove that the strip bookkeeping and the loop versioning are warp-uniform and keeps the weights in
   // uniform registers.
+  // Programmatic dependent launch: this grid may become resident while the previous Phi_H launch of the same stream
+  // is still draining (its launch latency and CTA ramp hide behind that tail); nothing of global memory is touched
+  // before the previous grid has completed and flushed, and the next launch may be scheduled from now on.
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   int strip, band;
   const int uniform_ctas = p.strips * p.bands;
   if ((int)blockIdx.x < uniform_ctas) {
@@ -775,6 +788,66 @@ k_wide_convert(const float *__restrict__ src, float *__restrict__ dst, int B, in
   }
 }
 
+// ---- fd_error('max') on a W8 field (utils/heat_utils.py:108-121, square domain): a solver loop that keeps its
+// iterate in the packed layout checks the residual without unpacking.  One thread per group of eight columns walks
+// down RES_ROWS rows with a three-row register window; the outer neighbours c-1 / c8 are the last / first element
+// of the adjacent groups of the same image (L1 hits: the neighbour threads load them as part of their own group).
+// Per cell the loss-kernel chain npde_residual (bit-identical to k_fd_error); maximum per image with an integer
+// atomicMax on the float bits (non-negative floats order like integers, a maximum is order independent).
+constexpr int RES_ROWS = 32, RES_THREADS = 128;
+__device__ __forceinline__ void res_load(const float *row, int g, int G8, float (&c)[10]) {
+  // c[1..8] = columns 0..7 of group g, c[0] = column -1, c[9] = column 8 (0 outside the image)
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(row + 8 * g)), b = __ldg(reinterpret_cast<const float4 *>(row + 8 * g + 4));
+  c[1] = a.x; c[5] = a.y; c[2] = a.z; c[6] = a.w; c[3] = b.x; c[7] = b.y; c[4] = b.z; c[8] = b.w;
+  c[0] = g > 0 ? __ldg(row + 8 * (g - 1) + 7) : 0.0f;
+  c[9] = g + 1 < G8 ? __ldg(row + 8 * (g + 1)) : 0.0f;
+}
+__global__ void __launch_bounds__(RES_THREADS)
+k_wide_resid(const float *__restrict__ x, const float *__restrict__ f, float *err, int B, int N, int G8, int VG) {
+  const int vg = blockIdx.x * RES_THREADS + threadIdx.x;
+  const int i0 = 1 + blockIdx.y * RES_ROWS, i1 = min(i0 + RES_ROWS, N - 1);
+  float vmax = 0.0f;
+  int b = min(vg, VG - 1) / G8;
+  if (vg < VG && i0 < i1) {
+    const int g = vg - b * G8;
+    const size_t pitch = (size_t)VG * 8;
+    const float *img = x + (size_t)b * G8 * 8;           // this image's first group in a virtual row
+    const float *fim = f ? f + (size_t)b * G8 * 8 : nullptr;
+    float up[10], ce[10], dn[10];
+    res_load(img + (size_t)(i0 - 1) * pitch, g, G8, up);
+    res_load(img + (size_t)i0 * pitch, g, G8, ce);
+    for (int i = i0; i < i1; ++i) {
+      res_load(img + (size_t)(i + 1) * pitch, g, G8, dn);
+      float fv[8];
+      if (fim) {
+        const float *fr = fim + (size_t)i * pitch + 8 * g;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(fr)), q = __ldg(reinterpret_cast<const float4 *>(fr + 4));
+        fv[0] = a.x; fv[4] = a.y; fv[1] = a.z; fv[5] = a.w; fv[2] = q.x; fv[6] = q.y; fv[3] = q.z; fv[7] = q.w;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int col = 8 * g + c;
+        if (col >= 1 && col <= N - 2) {
+          float v = npde_residual(up[c + 1], ce[c], ce[c + 1], ce[c + 2], dn[c + 1]);
+          if (fim) v = __fsub_rn(v, fv[c]);
+          vmax = fmaxf(vmax, fabsf(v));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 10; ++c) { up[c] = ce[c]; ce[c] = dn[c]; }
+    }
+  }
+  // lanes of a warp may belong to two images (an image boundary inside the warp; b grows with the lane)
+  const int b_first = __shfl_sync(NPDE_FULL_MASK, b, 0), b_last = __shfl_sync(NPDE_FULL_MASK, b, 31);
+  if (b_first == b_last) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(NPDE_FULL_MASK, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > 0.0f) atomicMax(reinterpret_cast<int *>(err) + b, __float_as_int(vmax));
+  } else if (vmax > 0.0f) {
+    atomicMax(reinterpret_cast<int *>(err) + b, __float_as_int(vmax));
+  }
+}
+
 struct WideGeom {
   int G8, VG, pitch, strips;
 };
@@ -812,6 +885,22 @@ int wide_slots(const void *kernel, size_t smem, std::atomic<int> *cache /* one e
 #endif
 }
 
+// 4 x SMs of the current device
+int wide_layer() {
+#ifdef NPDE_EMU
+  return 4;
+#else
+  static std::atomic<int> cache[64];
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 4 * 148;
+  const int hit = cache[dev].load(std::memory_order_relaxed);
+  if (hit > 0) return hit;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  cache[dev].store(4 * sms, std::memory_order_relaxed);
+  return 4 * sms;
+#endif
+}
+
 int wide_env_int(const char *name, int dflt) {
 #ifdef NPDE_EMU
   (void)name;
@@ -830,27 +919,73 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
 #ifndef NPDE_EMU
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  const int slots = wide_slots((const void *)kern, smem, cache);
-  // Work partition: bands x strips one-warp CTAs in ONE wave, as many whole bands per strip as there are resident
-  // warps for, the strips of a band in lock step.  The throughput of an SM sub-partition saturates with two resident
-  // warps (~430 cycles per warp and row step at L = 3 against 264 FMA-pipe cycles; a lone warp needs 545), so the
-  // launch time is (rows per band + warm-up) x that, whatever the number of strips: 118-121 us per launch for
-  // B = 60 .. 68 at 1025^2.  Everything tried to also use the resident warps that whole bands leave idle
-  // (64 x 1025^2: 276 strips x 4 bands = 1104 CTAs for 1184 warps) lost more on the memory side than it won:
-  // equal runs of the flattened (strip,row) space 126 us, the same with the strips ordered by the row offset of
-  // their piece boundaries ("diagonal lock step") 124 us, 4 bands + a flattened tail 137 us, two band heights
-  // (4 or 5 bands per strip) 120 us -- against 115-119 us for 4 whole bands (profiles/r2_wide_ab.txt).
-  // A piece pays L + R warm-up rows, so bands are kept >= minrows rows long.  NPDE_WIDE_BANDS=b (tuning) forces b.
+  int slots = wide_slots((const void *)kern, smem, cache);
+  // Work partition: bands x strips one-warp CTAs in ONE wave, the strips of a band in lock step.  How many bands?
+  // A piece of h rows costs h + warm-up row steps (2L + 4: halo rows and pipeline fill, in the slower generic code),
+  // and a row step of w = ceil(CTAs / (4 x SMs)) resident warps per SM sub-partition costs each of them 1.3 / 2.0 /
+  // 2.76 units for w = 1 / 2 / 3 (measured: a lone warp is latency bound, the third warp still adds throughput):
+  // the launch takes c(w) x (h + warm-up).  Minimising that over the band count picks 6 bands on three warps for
+  // 64 x 1025^2 (108 us; 4 bands on two warps: 115 us) and 33 bands of 32 rows on two warps for 8 x 1025^2
+  // (17.9 us; 41 bands of 25 rows on three warps: 21.8 us) -- profiles/r2_wide_ab.txt.
+  // Everything tried to also use the warp slots that whole bands leave idle lost more on the memory side than it
+  // won (flattened (strip,row) runs, diagonal lock step, a flattened tail), except one: more, shorter bands for the
+  // slower edge strips (below).  NPDE_WIDE_BANDS=b (tuning) forces b bands.
 #ifdef NPDE_EMU
   const int minrows = 6;
+  const int layer = 4;
 #else
-  const int minrows = wide_env_int("NPDE_WIDE_MINROWS", 24);
+  const int minrows = wide_env_int("NPDE_WIDE_MINROWS", 16);
+  const int layer = wide_layer();  // one-warp CTAs that put one warp on every SM sub-partition
 #endif
-  int bands = slots / (p.strips > 0 ? p.strips : 1);
-  if (bands > p.N / minrows) bands = p.N / minrows;
-  if (bands < 1) bands = 1;
+  const int nstrips = p.strips > 0 ? p.strips : 1;
+  int bmax = slots / nstrips;
+  if (bmax > p.N / minrows) bmax = p.N / minrows;
+  if (bmax < 1) bmax = 1;
+  int bands = 1;
+  {
+    const double warm = 1.3 * (2 * L + 4);
+    const int wcap = wide_env_int("NPDE_WIDE_W", 16);  // tuning: at most this many warps per sub-partition
+    double best = 0.0;
+    for (int b = 1; b <= bmax; ++b) {
+      const int h = (p.N + b - 1) / b;
+      const int nb = (p.N + h - 1) / h;  // bands that really exist with this height
+      if (nb != b) continue;
+      const int w = (int)(((long)nstrips * b + layer - 1) / layer);
+      if (w > wcap && b > 1) continue;
+      const double cost = (w < 2 ? 1.3 : 2.0 + 0.76 * (w - 2)) * (h + warm);
+      if (best == 0.0 || cost < best) {
+        best = cost;
+        bands = b;
+      }
+    }
+  }
   const int force_bands = wide_env_int("NPDE_WIDE_BANDS", 0);
   if (force_bands > 0) bands = force_bands;
+  // The block scheduler fills an SM to its occupancy limit before it moves on: a grid meant to put w warps on every
+  // sub-partition must not be ALLOWED more than 4w CTAs per SM, or it leaves whole SMs idle.  The limit is set
+  // through the shared-memory request (the unused part is never touched).
+  size_t smem_launch = smem;
+#ifndef NPDE_EMU
+  {
+    int w = (int)(((long)nstrips * bands + layer - 1) / layer);
+    const int wmax = slots / layer;
+    if (w < 1) w = 1;
+    if (w < wmax && force_bands <= 0) {
+      const size_t per_cta = (size_t)(228 * 1024) / (size_t)(4 * w) - 1024 - 256;  // 1 KB per CTA is the system's
+      if (per_cta > smem_launch) smem_launch = per_cta;
+      slots = 4 * w * (layer / 4);
+    }
+    if (smem_launch > 48 * 1024) {
+      static std::atomic<int> optin[64];
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev < 0 || dev >= 64 || optin[dev].load(std::memory_order_relaxed) < (int)smem_launch) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_launch);
+        if (dev >= 0 && dev < 64) optin[dev].store((int)smem_launch, std::memory_order_relaxed);
+      }
+    }
+  }
+#endif
   p.band_rows = (p.N + bands - 1) / bands;
   p.bands = (p.N + p.band_rows - 1) / p.band_rows;
   // Edge strips: ~5/4 of the interior cost per row -> 5/4 as many (shorter) bands, if the wave has room for them.
@@ -867,7 +1002,9 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
       }
     if (n_edge > 0 && n_edge < p.strips && n_edge <= WMAX_EDGE) {
       int want = (p.bands * 5 + 3) / 4;
-      while (want > p.bands && (ctas + (long)n_edge * (want - p.bands) > slots || p.N / want < minrows)) --want;
+      // stay inside the warps-per-sub-partition layer the band count was chosen for
+      const long cap = std::min<long>(slots, ((ctas + layer - 1) / layer) * (long)layer);
+      while (want > p.bands && (ctas + (long)n_edge * (want - p.bands) > cap || p.N / want < minrows)) --want;
       if (want > p.bands) {
         const int rows = (p.N + want - 1) / want;
         const int nb = (p.N + rows - 1) / rows;
@@ -881,7 +1018,28 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
     }
   }
   dim3 grid((unsigned)ctas), block(npde::STREAM_THREADS);
-  NPDE_LAUNCH((k_conv_wide<L, ACT, HASF>), grid, block, smem, st, p);
+#ifndef NPDE_EMU
+  // Programmatic stream serialization (see k_conv_wide); not inside a stream capture, where the plain edge is kept.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (wide_env_int("NPDE_WIDE_PDL", 1) != 0 && cudaStreamIsCapturing(st, &cap) == cudaSuccess &&
+      cap == cudaStreamCaptureStatusNone) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem_launch;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    npde_note_launch();
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return (int)e;
+    return NPDE_OK;
+  }
+#endif
+  NPDE_LAUNCH((k_conv_wide<L, ACT, HASF>), grid, block, smem_launch, st, p);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }
@@ -924,6 +1082,23 @@ int wide_unpack(const float *wide, float *x_ref, int B, int N, cudaStream_t st) 
   const WideGeom g = wide_geom(B, N);
   dim3 grid((unsigned)((g.VG + 32 * PACK_WARPS - 1) / (32 * PACK_WARPS)), (unsigned)N), block(32 * PACK_WARPS);
   NPDE_LAUNCH(k_wide_convert<false>, grid, block, 0, st, wide, x_ref, B, N, g.G8, g.VG);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
+}
+
+int wide_fd_error_max(const float *wide, const float *f_wide, float *err, int B, int N, cudaStream_t st) {
+  if (!wide || !err) return NPDE_ERR_NULL;
+  if (((uintptr_t)wide | (uintptr_t)f_wide) & 31) return NPDE_ERR_ARG;
+  const WideGeom g = wide_geom(B, N);
+#ifdef NPDE_EMU
+  memset(err, 0, sizeof(float) * (size_t)B);
+#else
+  const cudaError_t e = cudaMemsetAsync(err, 0, sizeof(float) * (size_t)B, st);
+  if (e != cudaSuccess) return (int)e;
+#endif
+  if (N < 3) return NPDE_OK;
+  dim3 grid((unsigned)((g.VG + RES_THREADS - 1) / RES_THREADS), (unsigned)((N - 2 + RES_ROWS - 1) / RES_ROWS)), block(RES_THREADS);
+  NPDE_LAUNCH(k_wide_resid, grid, block, 0, st, wide, f_wide, err, B, N, g.G8, g.VG);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -516,3 +516,60 @@ def solve(iterator, x, bc, f, tol, check_every, max_iters, *, w=None, w_host=Non
     check(lib().npde_solve(ctypes.byref(d), ctypes.c_float(tol), int(check_every), int(max_iters), _ptr(result),
                            _stream(x)), "npde_solve")
     return y, result
+
+
+# ---------------------------------------------------------------- packed (W8) fields: npde.h "persistent layout" --
+class PackedField(object):
+    """A batch of square-domain fields in the batch-interleaved W8 layout of the fused Phi_H kernel (npde.h).
+    A solver loop that packs its iterate once, runs `conv_iterate_packed` / `fd_error_packed` on it and unpacks the
+    solution at the end pays no layout pass per call (drop-in callers of `iterate` pay two per call)."""
+
+    def __init__(self, data, B, N):
+        self.data, self.B, self.N = data, int(B), int(N)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def empty_like(self):
+        return PackedField(torch.zeros_like(self.data), self.B, self.N)
+
+
+def pack(x):
+    """(B,N,N) -> PackedField (npde_pack)."""
+    x = _require(x, "x")
+    B, N = x.shape[0], x.shape[-1]
+    data = torch.empty(int(lib().npde_packed_floats(B, N)), dtype=torch.float32, device=x.device)
+    check(lib().npde_pack(_ptr(x), _ptr(data), B, N, _stream(x)), "npde_pack")
+    return PackedField(data, B, N)
+
+
+def unpack(p, out=None):
+    """PackedField -> (B,N,N) (npde_unpack)."""
+    if out is None:
+        out = torch.empty((p.B, p.N, p.N), dtype=torch.float32, device=p.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or tuple(out.shape) != (p.B, p.N, p.N) or out.device != p.device:
+        raise ValueError("out must be a contiguous float32 (B,N,N) tensor on the field's device")
+    check(lib().npde_unpack(_ptr(p.data), _ptr(out), p.B, p.N, _stream(out)), "npde_unpack")
+    return out
+
+
+def conv_iterate_packed(a, b, bc, f_packed, w_host, n_layers, act, k):
+    """k applications of Phi_H ping-ponging between the PackedFields a (input) and b (scratch); returns the one that
+    holds the k-th iterate.  w_host: (n_layers, 9) float32 numpy array (the weights travel as kernel parameters)."""
+    bc = _require(bc, "bc")
+    w = np.ascontiguousarray(w_host, dtype=np.float32).reshape(-1)
+    if w.size != 9 * n_layers:
+        raise ValueError("w_host must hold n_layers * 9 floats")
+    fp = None if f_packed is None else _ptr(f_packed.data)
+    check(lib().npde_conv_iterate_packed(_ptr(a.data), _ptr(b.data), _ptr(bc), fp, ctypes.c_void_p(w.ctypes.data), n_layers,
+                                         ACT[act], a.B, a.N, int(k), _stream(a.data)), "npde_conv_iterate_packed")
+    return a if k % 2 == 0 else b
+
+
+def fd_error_packed(p, f_packed=None):
+    """fd_error(x, bc, f, aggregate='max') of a PackedField -> (B,) (npde_fd_error_packed)."""
+    err = torch.empty(p.B, dtype=torch.float32, device=p.device)
+    fp = None if f_packed is None else _ptr(f_packed.data)
+    check(lib().npde_fd_error_packed(_ptr(p.data), fp, _ptr(err), p.B, p.N, _stream(err)), "npde_fd_error_packed")
+    return err

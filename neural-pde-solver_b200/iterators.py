@@ -272,6 +272,27 @@ class ConvIterator(Iterator):
         return F_.solve(IT_CONV, x, bc, f, tol, check_every, max_iters, w=w_dev, w_host=w_host,
                         n_layers=self.n_layers, act=self.act)
 
+    # -- persistent packed layout (square domain, 1..4 layers): pack once, iterate / check many times, unpack once --
+    def pack(self, x):
+        """(B,N,N) -> functional.PackedField in the layout of the fused kernel (npde_pack)."""
+        return F_.pack(x)
+
+    def unpack(self, p, out=None):
+        return F_.unpack(p, out=out)
+
+    def iterate_packed(self, a, b, bc, f_packed, k):
+        """k steps x <- Phi_H(x) from PackedField a, with PackedField b as the second buffer; returns the one holding
+        the result (heat_utils.py:163-181 / generation.py:86-93 without a layout pass per call)."""
+        self._check_act()
+        if not 1 <= self.n_layers <= 4 or tuple(bc.shape) != (a.B, 4):
+            raise NotImplementedError("packed fields: square domain, 1..4 layers")
+        _, w_host = self._cache.get(self._params(), a.device)
+        return F_.conv_iterate_packed(a, b, bc, f_packed, w_host, self.n_layers, self.act, k)
+
+    def fd_error_packed(self, p, f_packed=None):
+        """utils.fd_error(x, bc, f) ('max' over the interior) of a packed field, bit-identical to the unpacked one."""
+        return F_.fd_error_packed(p, f_packed)
+
     def invalidate_weight_cache(self):
         """Call after writing the weights through `.data` (which does not move torch's version counter)."""
         self._cache.invalidate()

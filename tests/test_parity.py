@@ -873,6 +873,40 @@ def test_wide_kernel_vs_oracle(be, oracle, B, N, L, has_f, act, k, tmp_path, mon
         assert sum("k_wide_convert" in n for n in names) == (3 if has_f else 2), names
 
 
+@pytest.mark.parametrize("B,N,L,has_f,k", [(3, 65, 3, False, 5), (2, 33, 2, True, 4), (5, 17, 1, False, 3)])
+def test_packed_solver_loop(be, oracle, B, N, L, has_f, k):
+    """The persistent packed layout (npde_pack / npde_conv_iterate_packed / npde_fd_error_packed / npde_unpack):
+    pack once, k steps, residual on the packed field, unpack -- iterate and residual bit-identical to the oracle's
+    and to the drop-in path on reference-layout tensors."""
+    rng = np.random.RandomState(77 + B + N)
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = oracle.set_boundary(rng.rand(B, N, N).astype(np.float32), bc)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-3
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.3).astype(np.float32)
+    it = be.npde.ConvIterator("clamp", L)
+    with torch.no_grad():
+        for l, wl in zip(it.layers, w):
+            l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+    it = it.to(be.device)
+    xd, bcd, fd = be.t(x), be.t(bc), be.t(f)
+    with torch.no_grad():
+        a = it.pack(xd)
+        fp = it.pack(fd) if has_f else None
+        b = a.empty_like()
+        assert_bitwise(be.n(it.unpack(a)), x, "pack -> unpack")
+        res = it.iterate_packed(a, b, bcd, fp, k)
+        assert res is (a if k % 2 == 0 else b)
+        err = it.fd_error_packed(res, fp)
+        y = it.unpack(res)
+    ref = oracle.iterate("conv", x, bc, f, w, "clamp", k)[0]
+    assert_bitwise(be.n(y), ref, "%d packed Phi_H steps" % k)
+    assert_bitwise(be.n(err), oracle.fd_error(ref, bc, f, "max"), "fd_error on the packed field")
+    assert_bitwise(be.n(err), be.n(be.utils.fd_error(y, bcd, fd)), "packed vs unpacked fd_error")
+
+
 # ----------------------------------------------------------------- initialize --
 @pytest.mark.parametrize("name", golden_names("init_"))
 def test_initialize_vs_reference(be, name):
