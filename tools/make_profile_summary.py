@@ -66,7 +66,7 @@ def main():
             fh.write(raw)
         get = lambda k: (r[hdr.index(k)], units[hdr.index(k)]) if k in hdr else ("n/a", "")
         lines = ["# ncu --set full: %s" % get("Kernel Name")[0].strip(), "",
-                 "Capture: `ncu --set full -k regex:k_conv_stream -s 150 -c 1 --clock-control none --import-source on "
+                 "Capture: `ncu --set full -k regex:k_conv_wide -s 150 -c 1 --clock-control none --import-source on "
                  "python bench.py --steps 1 --warmup 3 --no-cpu --no-ttr` on one B200 (workload conv3_jacobi_square_1025_b64: "
                  "64 x 1025^2, clamp, one Phi_H application per launch).", "", "| metric | value |", "|---|---|"]
         for k, label in KEYS:
