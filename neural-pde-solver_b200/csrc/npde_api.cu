@@ -135,7 +135,9 @@ struct ConvBwdWs {
     t = b.take<float>(n);
     for (int l = 0; l <= L; ++l) rs[l] = b.take<float>(n);
     size_t a = npde::weight_grad_ws_bytes(B, N - 2), c = npde::bwd_layer_ws_bytes(B, N - 2);
+    size_t d = npde::conv_bwd_stream_ws_bytes(B, N, 3);  // the fused streaming backward (npde_bwd_stream.cu)
     wg_bytes = a > c ? a : c;
+    if (d > wg_bytes) wg_bytes = d;
     wg = b.take_bytes(wg_bytes);
     counters = b.take<unsigned>(NPDE_MAX_CONV_LAYERS);
   }
@@ -636,6 +638,9 @@ inline bool wide_worthwhile(int B, int N) {
 int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kind, const float *f, const float *w,
                        int L, int act, const float *gout, float *gw, bool accumulate, float *gx, int B, int N,
                        cudaStream_t st) {
+  // square domain, up to three layers: recompute + adjoint + weight gradient in ONE streaming pass
+  if (gx && npde::conv_bwd_stream_supported(bc_kind, L) && !getenv("NPDE_BWD_LAYERED"))
+    return npde::conv_bwd_stream(x, f, w, L, act, gout, gw, accumulate, gx, B, N, c.wg, c.wg_bytes, st);
   int Sz = N - 2;
   size_t bytes = sizeof(float) * (size_t)B * Sz * Sz;
   const float *mask = mask0(bc, bc_kind, N);

@@ -140,6 +140,11 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
                   int B, int N, cudaStream_t st);
 
 
+// npde_bwd_stream.cu -- backward of one Conv step as one register-streaming pass (square domain, 1..3 layers)
+bool conv_bwd_stream_supported(int bc_kind, int n_layers);
+size_t conv_bwd_stream_ws_bytes(int B, int N, int n_layers);
+int conv_bwd_stream(const float *x, const float *f, const float *w_dev, int n_layers, int act, const float *gout,
+                    float *gw, bool accumulate, float *gx, int B, int N, void *ws, size_t ws_bytes, cudaStream_t st);
 // npde_wide.cu -- second-generation fused Phi_H kernel on the batch-interleaved "W8" layout (square domain):
 // element (b,i,c) of a (B,N,N) field lives at  i*pitch + (b*G8 + c/8)*8 + perm8(c%8),  G8 = ceil(N/8),
 // pitch = 8*B*G8, perm8 = (c0,c4,c1,c5,c2,c6,c3,c7); padding columns hold zeros.

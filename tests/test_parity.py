@@ -341,6 +341,41 @@ def test_conv_backward(be, name):
     assert rel_err(be.n(xg.grad), g["gx"]) <= 2e-5
 
 
+@pytest.mark.parametrize("B,N,L,act,has_f", [(3, 65, 3, "clamp", False), (5, 33, 2, "none", True),
+                                             (2, 129, 1, "sigmoid", False), (7, 17, 3, "clamp", True)])
+def test_streaming_backward_vs_layered(be, B, N, L, act, has_f, monkeypatch):
+    """k_bwd_stream (one fused pass: recompute + adjoint + weight gradient) against the layered backward kernels
+    (NPDE_BWD_LAYERED=1), which the reference's autograd goldens pin: several strips and bands per image, strips
+    that span images, an upstream gradient on every cell.  Same arithmetic per cell up to the summation order of
+    the transposed convolution and of the weight-gradient sums: 1e-5 of the largest entry."""
+    rng = np.random.RandomState(5 * B + N + L)
+    bc = rng.rand(B, 4).astype(np.float32)
+    x = rng.rand(B, N, N).astype(np.float32)
+    f = None
+    if has_f:
+        f = np.zeros((B, N, N), np.float32)
+        f[:, 1:-1, 1:-1] = (rng.rand(B, N - 2, N - 2) - 0.5) * 1e-2
+    gout = (rng.rand(B, N, N).astype(np.float32) - 0.5)
+    w = ((rng.rand(L, 3, 3) - 0.5) * 0.4).astype(np.float32)
+    res = {}
+    for mode in ("stream", "layered"):
+        if mode == "layered":
+            monkeypatch.setenv("NPDE_BWD_LAYERED", "1")
+        else:
+            monkeypatch.delenv("NPDE_BWD_LAYERED", raising=False)
+        it = be.npde.ConvIterator(act, L)
+        with torch.no_grad():
+            for l, wl in zip(it.layers, w):
+                l.weight.copy_(torch.from_numpy(wl).view(1, 1, 3, 3))
+        it = it.to(be.device)
+        xg = be.t(x).clone().requires_grad_(True)
+        y = it(xg, be.t(bc), be.t(f))
+        y.backward(be.t(gout))
+        res[mode] = (be.n(xg.grad).copy(), np.stack([be.n(l.weight.grad)[0, 0] for l in it.layers]))
+    assert rel_err(res["stream"][0], res["layered"][0]) <= 1e-5
+    assert rel_err(res["stream"][1], res["layered"][1]) <= 1e-5, (res["stream"][1], res["layered"][1])
+
+
 @pytest.mark.parametrize("name", golden_names("bwd_unet_"))
 def test_unet_backward(be, name):
     """One differentiable UNetIterator step + MSE vs the reference's autograd (square and cylinder geometries,
