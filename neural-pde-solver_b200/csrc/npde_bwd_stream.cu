@@ -142,10 +142,11 @@ k_bwd_stream(const BwdParams p) {
       const float z4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       bw_store4(mine4 + s * SLOT4, z4);
     }
-    auto load4 = [&](const float *base, int row, float (&v)[4]) {
+    // `rowp` points at this lane's first column of `row` (it is only dereferenced when the row exists)
+    auto load4 = [&](const float *rowp, int row, float (&v)[4]) {
       const bool ok = row >= 0 && row < N;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = (ok && exists[c]) ? __ldg(base + (size_t)row * N + c) : 0.0f;
+      for (int c = 0; c < 4; ++c) v[c] = (ok && exists[c]) ? __ldg(rowp + c) : 0.0f;
     };
 
     // register state
@@ -171,9 +172,15 @@ k_bwd_stream(const BwdParams p) {
 
     const int it_first = max(i0 - 2 * L - 2, 0), it_last = i1 + 2 * L + 1;
     float xnext[4], fnext[4], gnext[4];  // x row it, f row it-1, g' row it-1-L: loaded one step ahead
-    load4(px, it_first, xnext);
-    if (HASF) load4(pf, it_first - 1, fnext);
-    load4(pg, it_first - 1 - L, gnext);
+    // running row pointers of the three input streams and of the output (pointer arithmetic only: no dereference
+    // outside [0, N))
+    const float *rx = px + (ptrdiff_t)it_first * N;
+    const float *rf = HASF ? pf + (ptrdiff_t)(it_first - 1) * N : nullptr;
+    const float *rg = pg + (ptrdiff_t)(it_first - 1 - L) * N;
+    float *ro = po + (ptrdiff_t)(it_first - 2 * L - 2) * N;
+    load4(rx, it_first, xnext);
+    if (HASF) load4(rf, it_first - 1, fnext);
+    load4(rg, it_first - 1 - L, gnext);
 
     for (int it = it_first; it <= it_last; ++it) {
       // ---- inputs of this step; start the loads of the next one ----
@@ -187,9 +194,14 @@ k_bwd_stream(const BwdParams p) {
         fcur[c] = HASF ? fnext[c] : 0.0f;
         gcur[c] = gnext[c];
       }
-      load4(px, it + 1, xnext);
-      if (HASF) load4(pf, it, fnext);
-      load4(pg, it - L, gnext);
+      rx += N;
+      rg += N;
+      load4(rx, it + 1, xnext);
+      if (HASF) {
+        rf += N;
+        load4(rf, it, fnext);
+      }
+      load4(rg, it - L, gnext);
       bw_halo(xw[2], lane_l, lane_r);
 
       // ---- y = Psi(x) - f and r_0 = y - x for row a0 = it-1 (oracle psi_residual) ----
@@ -265,7 +277,10 @@ k_bwd_stream(const BwdParams p) {
         bw_store4(mine4 + (size_t)(LY::y_slots + (it + 4 * LY::g_slots) % LY::g_slots) * SLOT4, gl);
       }
 
-      // ---- adjoint layers l = L..1: g_l row n = it-2L-1+l enters its window; centre row ac = n-1 ----
+      // ---- adjoint layers l = L..1: g_l row n = it-2L-1+l enters its window; centre row ac = n-1.  The first row of
+      //      g_L that an owned output depends on is i0-1-L = the one of step i0: the adjoint (60 % of a step's work)
+      //      sleeps through the first half of the band's warm-up ----
+      if (it >= i0) {
 #pragma unroll
       for (int l = L; l >= 1; --l) {
         bw_halo(gnew, lane_l, lane_r);
@@ -324,11 +339,13 @@ k_bwd_stream(const BwdParams p) {
           v = __fmaf_rn(0.25f, gyw[1].v[c], v);
           v = __fmaf_rn(0.25f, gyw[0].v[c + 1], v);
           if (ao >= 1 && ao <= N - 2 && interior[c]) v = __fsub_rn(v, g0prev[c]);
-          if (exists[c]) po[(size_t)ao * N + c] = v;
+          if (exists[c]) ro[c] = v;
         }
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) g0prev[c] = gnew.v[c + 1];
+      }  // adjoint
+      ro += N;
     }
     if (!owner) {
 #pragma unroll
