@@ -639,7 +639,7 @@ int conv_step_bwd_impl(ConvBwdWs &c, const float *x, const float *bc, int bc_kin
                        int L, int act, const float *gout, float *gw, bool accumulate, float *gx, int B, int N,
                        cudaStream_t st) {
   // square domain, up to three layers: recompute + adjoint + weight gradient in ONE streaming pass
-  if (gx && npde::conv_bwd_stream_supported(bc_kind, L) && !getenv("NPDE_BWD_LAYERED"))
+  if (npde::conv_bwd_stream_supported(bc_kind, L) && !getenv("NPDE_BWD_LAYERED"))
     return npde::conv_bwd_stream(x, f, w, L, act, gout, gw, accumulate, gx, B, N, c.wg, c.wg_bytes, st);
   int Sz = N - 2;
   size_t bytes = sizeof(float) * (size_t)B * Sz * Sz;

@@ -129,7 +129,7 @@ k_bwd_stream(const BwdParams p) {
     }
     const size_t img = (size_t)b * N * N + col0;
     const float *px = p.x + img, *pg = p.gout + img, *pf = HASF ? p.f + img : nullptr;
-    float *po = p.gx + img;
+    float *po = p.gx ? p.gx + img : nullptr;
     char *mine = smem + (size_t)lane * BROW;  // r row slot s of this lane: mine + s * SLOT
     char *mine4 = smem + LY::r_bytes + (size_t)lane * BROW4;  // y slots, then g_L slots: mine4 + s * SLOT4
     constexpr size_t SLOT = 32 * BROW, SLOT4 = 32 * BROW4;
@@ -177,7 +177,7 @@ k_bwd_stream(const BwdParams p) {
     const float *rx = px + (ptrdiff_t)it_first * N;
     const float *rf = HASF ? pf + (ptrdiff_t)(it_first - 1) * N : nullptr;
     const float *rg = pg + (ptrdiff_t)(it_first - 1 - L) * N;
-    float *ro = po + (ptrdiff_t)(it_first - 2 * L - 2) * N;
+    ptrdiff_t ro = (ptrdiff_t)(it_first - 2 * L - 2) * N;  // offset of the output row of this step from po
     load4(rx, it_first, xnext);
     if (HASF) load4(rf, it_first - 1, fnext);
     load4(rg, it_first - 1 - L, gnext);
@@ -331,7 +331,7 @@ k_bwd_stream(const BwdParams p) {
         bw_halo(gyw[2], lane_l, lane_r);
       }
       const int ao = n0 - 1;
-      if (ao >= i0 && ao < i1 && owner) {
+      if (ao >= i0 && ao < i1 && owner && p.gx != nullptr) {  // gx == NULL: only the weight gradient is wanted
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float v = __fmul_rn(0.25f, gyw[2].v[c + 1]);
@@ -339,7 +339,7 @@ k_bwd_stream(const BwdParams p) {
           v = __fmaf_rn(0.25f, gyw[1].v[c], v);
           v = __fmaf_rn(0.25f, gyw[0].v[c + 1], v);
           if (ao >= 1 && ao <= N - 2 && interior[c]) v = __fsub_rn(v, g0prev[c]);
-          if (exists[c]) ro[c] = v;
+          if (exists[c]) po[ro + c] = v;
         }
       }
 #pragma unroll
@@ -453,7 +453,7 @@ size_t conv_bwd_stream_ws_bytes(int B, int N, int n_layers) {
 
 int conv_bwd_stream(const float *x, const float *f, const float *w_dev, int n_layers, int act, const float *gout,
                     float *gw, bool accumulate, float *gx, int B, int N, void *ws, size_t ws_bytes, cudaStream_t st) {
-  if (!x || !gout || !gw || !gx || !w_dev || !ws) return NPDE_ERR_NULL;
+  if (!x || !gout || !gw || !w_dev || !ws) return NPDE_ERR_NULL;
   if (ws_bytes < conv_bwd_stream_ws_bytes(B, N, n_layers)) return NPDE_ERR_WORKSPACE;
   const BwdGeom g = bwd_geom(B, N);
   BwdParams p;
