@@ -17,7 +17,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libnpde_b200.so")
-SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_wide.cu", "npde_bwd_stream.cu", "npde_cg.cu", "npde_small.cu", "npde_api.cu"]
+SOURCES = ["npde_grid_ops.cu", "npde_conv_ops.cu", "npde_stream.cu", "npde_wide.cu", "npde_bwd_stream.cu", "npde_unet_coarse.cu", "npde_cg.cu", "npde_small.cu", "npde_api.cu"]
 HEADERS = [os.path.join(CSRC, "npde_common.cuh"), os.path.join(CSRC, "npde_internal.h"), os.path.join(CSRC, "npde_f2.cuh"),
            os.path.join(ROOT, "include", "npde.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -362,6 +362,7 @@ int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const floa
                 int pre, int post, const float **result, int B, cudaStream_t st) {
   const float *cur = src;
   auto other = [&](const float *c) -> float * { return (c == u.t0) ? u.t1 : u.t0; };
+  int up_from = L - 1;  // the level the way up starts at
   for (int l = l0; l < L; ++l) {
     int s = u.s[l];
     for (int j = 0; j < pre; ++j) {
@@ -371,13 +372,23 @@ int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const floa
       cur = dst;
     }
     if (pre == 0) TRY(d2d(u.skip[l], cur, sizeof(float) * (size_t)B * s * s, st));
+    if (l < L - 1 && npde::unet_coarse_supported(u.s, L, l + 1, pre, post) && !getenv("NPDE_UNET_LAYERED")) {
+      // every deeper level fits in shared memory: pool, levels l+1 .. L-1 and the upsampling back to this level in
+      // ONE kernel (npde_unet_coarse.cu); cur = the upsampled correction of level l, as after the loop below
+      float *dst = other(cur);
+      TRY(npde::unet_coarse(ArrView{u.skip[l], s, (long)s * s, 0, 0}, s, ArrViewMut{dst, s, (long)s * s, 0, 0}, wf, wp,
+                            wsnd, u.mask, u.mbs, u.s, L, pre, post, l + 1, B, st));
+      cur = dst;
+      up_from = l;
+      break;
+    }
     if (l < L - 1) {
       float *dst = other(cur);
       TRY(npde::conv3x3(cur, s, wp + 9 * l, 2, 0, u.mask[l + 1], u.mbs[l + 1], dst, u.s[l + 1], B, st));  // :63-66
       cur = dst;
     }
   }
-  for (int i = 0; i < L - l0; ++i) {
+  for (int i = L - 1 - up_from; i < L - l0; ++i) {
     int l = L - 1 - i, s = u.s[l];
     for (int j = 0; j < post; ++j) {
       // the last post-smoothing conv adds the skip connection in its epilogue (:76)
@@ -1001,7 +1012,14 @@ int npde_unet_step_fwd_hw(const float *x, const float *bc, int bc_kind, const fl
   // head: x -> y (frame), skip_0 = pre-smoothed masked residual (frame)
   TRY(npde::conv_head_stream(npde::ref_view(x, N), bcf, npde::ref_view(f, N), wh_first, pre, skipv, fw.y0, B, N, st));
   npde::FieldView rin = npde::as_const(skipv);  // single level: the post convs start from skip_0 itself
-  if (L > 1) {
+  if (L > 1 && npde::unet_coarse_supported(u.s, L, 1, pre, post) && !getenv("NPDE_UNET_LAYERED")) {
+    // levels 1 .. L-1 fit on chip (N <= 257): pooling conv of level 0, all coarser levels and the upsampling into the
+    // level-0 frame in one kernel, one CTA per problem
+    TRY(npde::unet_coarse(ArrView{fw.skip0, fw.pitch, fw.bstride, 1, 1}, u.s[0],
+                          ArrViewMut{fw.up0, fw.pitch, fw.bstride, 1, 1}, w_first, w_pool, w_second, u.mask, u.mbs, u.s,
+                          L, pre, post, 1, B, st));
+    rin = npde::FieldView{fw.up0, fw.pitch, fw.bstride, 1};
+  } else if (L > 1) {
     // pooling conv of level 0 reads the skip frame, then levels 1 .. L-1 layer by layer
     float *lvl1 = u.t0;
     TRY(npde::conv3x3_view(ArrView{fw.skip0, fw.pitch, fw.bstride, 1, 1}, u.s[0], w_pool, 2, 0, u.mask[1], u.mbs[1], lvl1,

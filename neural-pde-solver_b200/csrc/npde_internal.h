@@ -140,6 +140,12 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
                   int B, int N, cudaStream_t st);
 
 
+// npde_unet_coarse.cu -- U-Net levels l0 .. L-1 (interiors <= 127^2) in one kernel, one CTA per problem, on chip:
+// pools `src` (the skip tensor of level l0-1), runs the deeper levels, writes the upsampled correction of level l0-1
+bool unet_coarse_supported(const int *s, int L, int l0, int pre, int post);
+int unet_coarse(const ArrView &src, int s_src, const ArrViewMut &up, const float *wf, const float *wp,
+                const float *wsnd, float *const *mask, const size_t *mbs, const int *s, int L, int pre, int post, int l0,
+                int B, cudaStream_t st);
 // npde_bwd_stream.cu -- backward of one Conv step as one register-streaming pass (square domain, 1..3 layers)
 bool conv_bwd_stream_supported(int bc_kind, int n_layers);
 size_t conv_bwd_stream_ws_bytes(int B, int N, int n_layers);
