@@ -372,7 +372,7 @@ int unet_levels(UnetWs &u, int l0, const float *src, const float *wf, const floa
       cur = dst;
     }
     if (pre == 0) TRY(d2d(u.skip[l], cur, sizeof(float) * (size_t)B * s * s, st));
-    if (l < L - 1 && npde::unet_coarse_supported(u.s, L, l + 1, pre, post) && !getenv("NPDE_UNET_LAYERED")) {
+    if (l < L - 1 && npde::unet_coarse_supported(u.s, L, l + 1, pre, post, B) && !getenv("NPDE_UNET_LAYERED")) {
       // every deeper level fits in shared memory: pool, levels l+1 .. L-1 and the upsampling back to this level in
       // ONE kernel (npde_unet_coarse.cu); cur = the upsampled correction of level l, as after the loop below
       float *dst = other(cur);
@@ -1012,7 +1012,7 @@ int npde_unet_step_fwd_hw(const float *x, const float *bc, int bc_kind, const fl
   // head: x -> y (frame), skip_0 = pre-smoothed masked residual (frame)
   TRY(npde::conv_head_stream(npde::ref_view(x, N), bcf, npde::ref_view(f, N), wh_first, pre, skipv, fw.y0, B, N, st));
   npde::FieldView rin = npde::as_const(skipv);  // single level: the post convs start from skip_0 itself
-  if (L > 1 && npde::unet_coarse_supported(u.s, L, 1, pre, post) && !getenv("NPDE_UNET_LAYERED")) {
+  if (L > 1 && npde::unet_coarse_supported(u.s, L, 1, pre, post, B) && !getenv("NPDE_UNET_LAYERED")) {
     // levels 1 .. L-1 fit on chip (N <= 257): pooling conv of level 0, all coarser levels and the upsampling into the
     // level-0 frame in one kernel, one CTA per problem
     TRY(npde::unet_coarse(ArrView{fw.skip0, fw.pitch, fw.bstride, 1, 1}, u.s[0],

@@ -142,7 +142,7 @@ int jacobi_stream(const FieldView &in, const FieldViewMut &out, const BcFields &
 
 // npde_unet_coarse.cu -- U-Net levels l0 .. L-1 (interiors <= 127^2) in one kernel, one CTA per problem, on chip:
 // pools `src` (the skip tensor of level l0-1), runs the deeper levels, writes the upsampled correction of level l0-1
-bool unet_coarse_supported(const int *s, int L, int l0, int pre, int post);
+bool unet_coarse_supported(const int *s, int L, int l0, int pre, int post, int B);
 int unet_coarse(const ArrView &src, int s_src, const ArrViewMut &up, const float *wf, const float *wp,
                 const float *wsnd, float *const *mask, const size_t *mbs, const int *s, int L, int pre, int post, int l0,
                 int B, cudaStream_t st);

@@ -302,13 +302,17 @@ size_t coarse_smem(const int *s, int l0) { return sizeof(float) * 3 * (size_t)(s
 namespace npde {
 
 // levels l0 .. L-1 fit on chip, nest, and have the smoothing convs the kernel assumes
-bool unet_coarse_supported(const int *s, int L, int l0, int pre, int post) {
+bool unet_coarse_supported(const int *s, int L, int l0, int pre, int post, int B) {
   if (l0 < 1 || l0 >= L || pre < 1 || post < 1 || pre > NPDE_MAX_UNET_SMOOTH || post > NPDE_MAX_UNET_SMOOTH ||
       L > NPDE_MAX_LEVELS)
     return false;
 #ifdef NPDE_EMU
   if (s[l0] > 127) return false;
+  (void)B;
 #else
+  // One CTA per problem, ~46 us whatever the batch: below ~16 problems the layered kernels, which spread a level over
+  // all SMs and replay from a CUDA graph, are faster (B = 1, 257^2: 42 vs 58 us per U-Net step).
+  if (B < 16) return false;
   if (coarse_smem(s, l0) + sizeof(float) * CW_MAX > 227 * 1024) return false;
 #endif
   for (int l = l0; l + 1 < L; ++l)
