@@ -420,7 +420,7 @@ __device__ __forceinline__ void wide_stage0(WState<L> &s, WCtx &x, int it, unsig
 
 // ---- conv stage k (1..L): consumes the row (in, il, ir) of stage k-1, finishes row rk.  k < L: the finished row
 // goes to (out, ol, orr) (may alias the input); k == L: epilogue with the y row at `roff` of the delay line.
-template <int L, int ACT, bool MAIN, bool EDGE, int P>
+template <int L, int ACT, bool MAIN, bool EDGE, int P, bool STORE = true>
 __device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const WideParams &p, int k, int rk, unsigned roff,
                                                 const f2 (&in)[4], float il, float ir, f2 (&out)[4], float &ol,
                                                 float &orr) {
@@ -443,7 +443,9 @@ __device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const Wid
     for (int j = 0; j < 4; ++j) out[j] = EDGE ? and2(fin[j], x.keep[j], x.keep[j + 4]) : fin[j];
     whalo(out, x.lane_l, x.lane_r, ol, orr);
   } else {
-    if (MAIN || (rk >= x.i0 && rk < x.i1)) {
+    // MAIN steps also run the band's warm-up (pipeline filling from the zero state, rows above the band) as
+    // STORE = false: those output rows are not this piece's, the whole epilogue is skipped
+    if (MAIN ? (STORE && (!NPDE_W_SKEW || rk >= x.i0)) : (rk >= x.i0 && rk < x.i1)) {
       float o[8];
       if (MAIN || (rk >= 1 && rk <= N - 2)) {
         f2 ya, yb, yc, yd;
@@ -467,7 +469,7 @@ __device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const Wid
   }
 }
 
-template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P>
+template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P, bool STORE = true>
 __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParams &p, int it, unsigned &woff) {
   constexpr int DS = WDelay<L>::slots;
   constexpr unsigned DMASK = DS * (unsigned)WSLOT - 1u;
@@ -478,7 +480,7 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
   // last stage first: stage k reads what stage k-1 left in the previous step, then stage k-1 replaces it
 #pragma unroll
   for (int k = L; k >= 1; --k)
-    wide_conv_stage<L, ACT, MAIN, EDGE, P>(s, x, p, k, it - 1 - 2 * k, roff, s.R[k - 1], s.Rl[k - 1], s.Rr[k - 1],
+    wide_conv_stage<L, ACT, MAIN, EDGE, P, STORE>(s, x, p, k, it - 1 - 2 * k, roff, s.R[k - 1], s.Rl[k - 1], s.Rr[k - 1],
                                            s.R[k < L ? k : 0], s.Rl[k < L ? k : 0], s.Rr[k < L ? k : 0]);
   wide_stage0<L, ACT, HASF, MAIN, EDGE, P>(s, x, it, woff, s.R[0], s.Rl[0], s.Rr[0]);
 #else
@@ -487,7 +489,8 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
   float rl, rr;
   wide_stage0<L, ACT, HASF, MAIN, EDGE, P>(s, x, it, woff, rc, rl, rr);
 #pragma unroll
-  for (int k = 1; k <= L; ++k) wide_conv_stage<L, ACT, MAIN, EDGE, P>(s, x, p, k, it - 1 - k, roff, rc, rl, rr, rc, rl, rr);
+  for (int k = 1; k <= L; ++k)
+    wide_conv_stage<L, ACT, MAIN, EDGE, P, STORE>(s, x, p, k, it - 1 - k, roff, rc, rl, rr, rc, rl, rr);
 #endif
   if (MAIN) {  // row it+1 has landed (at most WRING - 1 younger groups pending): move it to registers
 #if NPDE_W_TMA
@@ -622,7 +625,9 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   // input rows it = it_first .. it_last; the output row of a step is it - 1 - LAT
   const int it_first = max(i0 - R, 0);  // rows above the grid are zeros == the initial state
   const int it_last = i1 + LAT;
-  x.x_last = min(i1 - 1 + R, N - 1);    // last input row that exists and matters
+  // last input row that exists and matters, plus one (fetched, never used: it lets the row-test-free loop run the
+  // piece's last step as well)
+  x.x_last = min(i1 - 1 + R + 1, N - 1);
   x.f_last = min(x.x_last, N - 2);      // last row of f that is ever read
   const size_t lane_off = (size_t)max(vg, 0) * WCOLS;
   const float *xin = p.in + lane_off;
@@ -640,8 +645,14 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
   unsigned woff = 0;
 
   // MAIN range of `it`: stage rows it-1-LAT .. it-1 interior, output row it-1-LAT inside the piece, x row it+1 exists
-  const int main_lo = max(LAT + 2, i0 + LAT + 1);
+  // (the warm-up steps of a band that does not start at the top of the grid qualify too: their stores are suppressed)
+  const int main_lo = LAT + 2;
   const int main_hi = min(N - 2, x.x_last - 1);
+  // Steps up to i0 + LAT produce rows above the band: the store-free loop runs whole pairs of them.  From it_first
+  // (= i0 - R unless the band starts at the top, where nothing is suppressed) a band has LAT + R + 1 = 2L + 2 such
+  // steps, an even number, and `it` moves in pairs from it_first, so the first storing pair starts exactly at row i0.
+  // (With skewed stages the count is 3L + 2: the storing loop keeps a row test there, see wide_conv_stage.)
+  const int warm_hi = min(i0 + LAT, main_hi);
   int it = it_first;  // (it - it_first) is even at the top of this loop: parities 0, 1 per trip
   while (it <= it_last) {
     if (it >= main_lo && it + 1 <= main_hi) {
@@ -673,11 +684,16 @@ __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i
       }                                                                             \
       cp_async_commit();                                                            \
     }                                                                               \
-    do {                                                                            \
+    while (it + 1 <= warm_hi) { /* the band's warm-up: an even number of steps (2 LAT + 2), nothing stored */ \
+      wide_step<L, ACT, HASF, true, EDGE_, 0, false>(s, x, p, it, woff);            \
+      wide_step<L, ACT, HASF, true, EDGE_, 1, false>(s, x, p, it + 1, woff);        \
+      it += 2;                                                                      \
+    }                                                                               \
+    while (it + 1 <= main_hi) {                                                     \
       wide_step<L, ACT, HASF, true, EDGE_, 0>(s, x, p, it, woff);                   \
       wide_step<L, ACT, HASF, true, EDGE_, 1>(s, x, p, it + 1, woff);               \
       it += 2;                                                                      \
-    } while (it + 1 <= main_hi);                                                    \
+    }                                                                               \
   } while (0)
       if (edge_strip) NPDE_W_MAIN_LOOP(true);
       else NPDE_W_MAIN_LOOP(false);
