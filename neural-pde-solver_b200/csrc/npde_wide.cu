@@ -937,7 +937,7 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
 #endif
   int slots = wide_slots((const void *)kern, smem, cache);
   // Work partition: bands x strips one-warp CTAs in ONE wave, the strips of a band in lock step.  How many bands?
-  // A piece of h rows costs h + warm-up row steps (2L + 4: halo rows and pipeline fill, in the slower generic code),
+  // A piece of h rows costs h + warm-up row steps (2L + 3: halo rows and pipeline fill),
   // and a row step of w = ceil(CTAs / (4 x SMs)) resident warps per SM sub-partition costs each of them 1.3 / 2.0 /
   // 2.76 units for w = 1 / 2 / 3 (measured: a lone warp is latency bound, the third warp still adds throughput):
   // the launch takes c(w) x (h + warm-up).  Minimising that over the band count picks 6 bands on three warps for
@@ -954,42 +954,74 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
   const int layer = wide_layer();  // one-warp CTAs that put one warp on every SM sub-partition
 #endif
   const int nstrips = p.strips > 0 ? p.strips : 1;
-  int bmax = slots / nstrips;
-  if (bmax > p.N / minrows) bmax = p.N / minrows;
+  const int force_bands = wide_env_int("NPDE_WIDE_BANDS", 0);
+  // edge strips (a ring / padding column inside): the masked loop costs EDGE_COST x the interior loop per row step
+  const double EDGE_COST = 1.18;
+  int n_edge = 0;
+  if (force_bands <= 0 && p.strips <= 65535 && wide_env_int("NPDE_WIDE_EDGE_BANDS", 1) != 0) {
+    for (int s = 0; s < p.strips && n_edge <= WMAX_EDGE; ++s)
+      if (wide_strip_is_edge(s, p.N, p.G8, p.VG)) {
+        if (n_edge < WMAX_EDGE) p.edge_strip[n_edge] = (unsigned short)s;
+        ++n_edge;
+      }
+    if (n_edge >= p.strips || n_edge > WMAX_EDGE) n_edge = 0;  // all strips alike (or too many to list): uniform bands
+  }
+  const int n_int = nstrips - n_edge;
+  auto real_bands = [&](int b) {  // the bands that exist when N rows are cut into pieces of ceil(N / b) rows
+    const int h = (p.N + b - 1) / b;
+    return (p.N + h - 1) / h;
+  };
+  int bmax = p.N / minrows;
   if (bmax < 1) bmax = 1;
-  int bands = 1;
+  int bands = 1, bands_e = 1;
   {
-    const double warm = 1.3 * (2 * L + 4);
-    const int wcap = wide_env_int("NPDE_WIDE_W", 16);  // tuning: at most this many warps per sub-partition
+    // interior strips get b bands, edge strips as many (>= b) as still fit into the same warps-per-sub-partition layer:
+    // minimise c(w) x max(h_i + warm, EDGE_COST (h_e + warm)) over b
+    const double warm = 2 * L + 3;
+    const int wmax_dev = slots / layer > 0 ? slots / layer : 1;
+    const int wcap = std::min(wide_env_int("NPDE_WIDE_W", 16), wmax_dev);  // tuning: at most this many warps per sub-partition
     double best = 0.0;
     for (int b = 1; b <= bmax; ++b) {
-      const int h = (p.N + b - 1) / b;
-      const int nb = (p.N + h - 1) / h;  // bands that really exist with this height
-      if (nb != b) continue;
-      const int w = (int)(((long)nstrips * b + layer - 1) / layer);
-      if (w > wcap && b > 1) continue;
-      const double cost = (w < 2 ? 1.3 : 2.0 + 0.76 * (w - 2)) * (h + warm);
+      if (real_bands(b) != b) continue;
+      const long base = (long)nstrips * b;
+      int w = (int)((base + layer - 1) / layer);
+      if (w > wcap) {
+        if (b > 1) continue;
+        w = wcap;  // a single band that does not fit into one wave: nothing to choose
+      }
+      const long cap = std::min<long>(slots, (long)w * layer);
+      int be = b;
+      if (n_edge > 0) {
+        be = b + (int)((cap - base) / n_edge);
+        if (be > bmax) be = bmax;
+        while (be > b && real_bands(be) != be) --be;
+        // more edge bands than balance needs only add warm-up work
+        while (be > b && EDGE_COST * ((p.N + be - 2) / (be - 1) + warm) <= (p.N + b - 1) / b + warm &&
+               real_bands(be - 1) == be - 1)
+          --be;
+      }
+      const double hi = (p.N + b - 1) / b + warm, he = EDGE_COST * ((p.N + be - 1) / be + warm);
+      const double cost = (w < 2 ? 1.3 : 2.0 + 0.76 * (w - 2)) * (n_edge > 0 && he > hi ? he : hi);
       if (best == 0.0 || cost < best) {
         best = cost;
         bands = b;
+        bands_e = be;
       }
     }
   }
-  const int force_bands = wide_env_int("NPDE_WIDE_BANDS", 0);
-  if (force_bands > 0) bands = force_bands;
+  if (force_bands > 0) bands = bands_e = force_bands;
   // The block scheduler fills an SM to its occupancy limit before it moves on: a grid meant to put w warps on every
   // sub-partition must not be ALLOWED more than 4w CTAs per SM, or it leaves whole SMs idle.  The limit is set
   // through the shared-memory request (the unused part is never touched).
   size_t smem_launch = smem;
 #ifndef NPDE_EMU
   {
-    int w = (int)(((long)nstrips * bands + layer - 1) / layer);
+    int w = (int)(((long)n_int * bands + (long)n_edge * bands_e + layer - 1) / layer);
     const int wmax = slots / layer;
     if (w < 1) w = 1;
     if (w < wmax && force_bands <= 0) {
       const size_t per_cta = (size_t)(228 * 1024) / (size_t)(4 * w) - 1024 - 256;  // 1 KB per CTA is the system's
       if (per_cta > smem_launch) smem_launch = per_cta;
-      slots = 4 * w * (layer / 4);
     }
     if (smem_launch > 48 * 1024) {
       static std::atomic<int> optin[64];
@@ -1004,33 +1036,18 @@ int launch_wide_f(WideParams &p, cudaStream_t st) {
 #endif
   p.band_rows = (p.N + bands - 1) / bands;
   p.bands = (p.N + p.band_rows - 1) / p.band_rows;
-  // Edge strips: ~5/4 of the interior cost per row -> 5/4 as many (shorter) bands, if the wave has room for them.
   p.bands_edge = p.bands;
   p.band_rows_edge = p.band_rows;
   p.n_edge = 0;
   long ctas = (long)p.bands * p.strips;
-  if (force_bands <= 0 && p.strips <= 65535 && wide_env_int("NPDE_WIDE_EDGE_BANDS", 1) != 0) {
-    int n_edge = 0;
-    for (int s = 0; s < p.strips && n_edge <= WMAX_EDGE; ++s)
-      if (wide_strip_is_edge(s, p.N, p.G8, p.VG)) {
-        if (n_edge < WMAX_EDGE) p.edge_strip[n_edge] = (unsigned short)s;
-        ++n_edge;
-      }
-    if (n_edge > 0 && n_edge < p.strips && n_edge <= WMAX_EDGE) {
-      int want = (p.bands * 5 + 3) / 4;
-      // stay inside the warps-per-sub-partition layer the band count was chosen for
-      const long cap = std::min<long>(slots, ((ctas + layer - 1) / layer) * (long)layer);
-      while (want > p.bands && (ctas + (long)n_edge * (want - p.bands) > cap || p.N / want < minrows)) --want;
-      if (want > p.bands) {
-        const int rows = (p.N + want - 1) / want;
-        const int nb = (p.N + rows - 1) / rows;
-        if (nb > p.bands) {
-          p.bands_edge = nb;
-          p.band_rows_edge = rows;
-          p.n_edge = n_edge;
-          ctas += (long)n_edge * (nb - p.bands);
-        }
-      }
+  if (n_edge > 0 && bands_e > p.bands) {
+    const int rows = (p.N + bands_e - 1) / bands_e;
+    const int nb = (p.N + rows - 1) / rows;
+    if (nb > p.bands) {
+      p.bands_edge = nb;
+      p.band_rows_edge = rows;
+      p.n_edge = n_edge;
+      ctas += (long)n_edge * (nb - p.bands);
     }
   }
   dim3 grid((unsigned)ctas), block(npde::STREAM_THREADS);
