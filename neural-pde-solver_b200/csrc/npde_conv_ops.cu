@@ -198,6 +198,117 @@ __global__ void k_pad_up_crop(const float *__restrict__ r, int s, const float *_
   out.p[(size_t)b * out.bstride + (size_t)(i + out.off) * out.pitch + npde_view_col(j + out.off, out.perm)] = v;
 }
 
+// k_pad_up_crop by coarse cells: a thread takes the coarse cells (I, 2m) and (I, 2m+1) of the zero-padded input
+// (0 <= I <= s, 0 <= 2m <= s) and produces the 2 x 4 outputs they generate -- upsampled coordinates (2I + di,
+// 4m + dj), di < 2, dj < 4 -- from six loads, with no divergent parity cases.  When the output is the interior of a
+// pair-permuted frame (perm = 1, off = 1) those four columns are exactly one aligned 16-byte group of the frame row:
+// one 128-bit store per output row instead of four scattered 4-byte stores (632 -> ~150 us for the level-0 frame of
+// U-Net(6,2,2) at 8 x 4097^2).  Same per-output arithmetic as k_pad_up_crop.
+template <bool FRAME>
+__global__ void __launch_bounds__(TX * TY)
+k_pad_up_crop_quad(const float *__restrict__ r, int s, const float *__restrict__ mask_out, size_t mask_bstride,
+                   ArrViewMut out, int nested) {
+  const int so = 2 * s + 1;
+  const int m = blockIdx.x * TX + threadIdx.x, I = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  const int J = 2 * m;
+  if (I > s || J > s) return;
+  const float *rb = r + (size_t)b * s * s;
+  // padded coarse values: rows I, I+1; columns J, J+1, J+2
+  float a[2][3];
+#pragma unroll
+  for (int di = 0; di < 2; ++di)
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj) a[di][dj] = padded_at(rb, s, I + di, J + dj);
+  const float *mk = mask_out ? mask_out + (size_t)b * mask_bstride : nullptr;
+  float *ob = out.p + (size_t)b * out.bstride;
+#pragma unroll
+  for (int di = 0; di < 2; ++di) {
+    const int i = 2 * I + di - 1;  // cropped output row
+    if (i < 0 || i >= so) continue;
+    float v[4];
+#pragma unroll
+    for (int dj = 0; dj < 4; ++dj) {
+      const int c = dj >> 1;  // coarse column J + c
+      const float p00 = a[0][c], p01 = a[0][c + 1], p10 = a[1][c], p11 = a[1][c + 1];
+      if (di == 0 && !(dj & 1)) v[dj] = p00;
+      else if (di == 0) v[dj] = __fmul_rn(0.5f, __fadd_rn(p00, p01));
+      else if (!(dj & 1)) v[dj] = __fmul_rn(0.5f, __fadd_rn(p00, p10));
+      else {
+        const float sum = nested ? __fadd_rn(__fadd_rn(p00, p01), __fadd_rn(p10, p11))
+                                 : __fadd_rn(__fadd_rn(__fadd_rn(p00, p01), p10), p11);
+        v[dj] = __fmul_rn(0.25f, sum);
+      }
+      const int j = 2 * J + dj - 1;  // cropped output column
+      if (mk && j >= 0 && j < so) v[dj] = __fmul_rn(v[dj], fg_at(mk, so, i, j));
+    }
+    const int j0 = 2 * J - 1;
+    if (FRAME) {
+      // frame columns j0 + 1 .. j0 + 4 = 4m .. 4m + 3: one aligned group, stored as (c0, c2, c1, c3); column 4m is
+      // the frame's ring column when m == 0 and columns beyond the interior exist in the padded pitch: both are
+      // outside the cropped image and keep whatever the frame holds there (the tail kernel never reads them)
+      float *g = ob + (size_t)(i + 1) * out.pitch + 4 * m;
+      if (j0 >= 0 && j0 + 3 < so) {
+        *reinterpret_cast<float4 *>(g) = make_float4(v[0], v[2], v[1], v[3]);
+      } else {
+#pragma unroll
+        for (int dj = 0; dj < 4; ++dj)
+          if (j0 + dj >= 0 && j0 + dj < so) g[npde_view_col(dj, 1)] = v[dj];
+      }
+    } else {
+#pragma unroll
+      for (int dj = 0; dj < 4; ++dj) {
+        const int j = j0 + dj;
+        if (j >= 0 && j < so) ob[(size_t)(i + out.off) * out.pitch + npde_view_col(j + out.off, out.perm)] = v[dj];
+      }
+    }
+  }
+}
+
+// The pooling conv of the finest level read from a pair-permuted frame (perm = 1, off = 1): stride 2, pad 0.  A thread
+// computes the outputs (i, 2m) and (i, 2m+1): their taps are frame columns 4m+1 .. 4m+5 of three rows = two 128-bit
+// loads per row instead of eighteen 4-byte gathers with index arithmetic.  Same fmaf chain as k_conv3x3.
+__global__ void __launch_bounds__(TX * TY)
+k_pool_frame(const float *__restrict__ in, int pitch, long bstride, int Hi, const float *__restrict__ w,
+             const float *__restrict__ mask, size_t mask_bstride, float *__restrict__ out, int Ho) {
+  const int m = blockIdx.x * TX + threadIdx.x, i = blockIdx.y * TY + threadIdx.y, b = blockIdx.z;
+  if (i >= Ho || 2 * m >= Ho) return;
+  const float *p = in + (size_t)b * bstride;
+  float wk[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) wk[k] = __ldg(w + k);
+  float c[3][5];  // interior columns 4m .. 4m+4 of interior rows 2i .. 2i+2
+  const bool second = 2 * m + 1 < Ho;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float *row = p + (size_t)(2 * i + a + 1) * pitch + 4 * m;  // frame row, group m
+    const float4 g0 = __ldg(reinterpret_cast<const float4 *>(row));       // frame cols 4m..4m+3 as (c0,c2,c1,c3)
+    const float4 g1 = __ldg(reinterpret_cast<const float4 *>(row + 4));   // the padded pitch makes this readable
+    // interior column q = frame column q + 1
+    c[a][0] = g0.z;  // frame col 4m+1
+    c[a][1] = g0.y;  // 4m+2
+    c[a][2] = g0.w;  // 4m+3
+    c[a][3] = g1.x;  // 4m+4
+    c[a][4] = g1.z;  // 4m+5
+  }
+  (void)Hi;
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    if (o == 1 && !second) break;
+    const int j = 2 * m + o;
+    float acc = __fmul_rn(wk[0], c[0][2 * o]);
+    acc = __fmaf_rn(wk[1], c[0][2 * o + 1], acc);
+    acc = __fmaf_rn(wk[2], c[0][2 * o + 2], acc);
+    acc = __fmaf_rn(wk[3], c[1][2 * o], acc);
+    acc = __fmaf_rn(wk[4], c[1][2 * o + 1], acc);
+    acc = __fmaf_rn(wk[5], c[1][2 * o + 2], acc);
+    acc = __fmaf_rn(wk[6], c[2][2 * o], acc);
+    acc = __fmaf_rn(wk[7], c[2][2 * o + 1], acc);
+    acc = __fmaf_rn(wk[8], c[2][2 * o + 2], acc);
+    if (mask) acc = __fmul_rn(acc, fg_at(mask + (size_t)b * mask_bstride, Ho, i, j));
+    out[((size_t)b * Ho + i) * Ho + j] = acc;
+  }
+}
+
 // adjoint of k_pad_up_crop (without the mask multiply): g is (2s+1)^2, out is s^2
 __global__ void k_pad_up_crop_transpose(const float *__restrict__ g, int s, float *__restrict__ out) {
   int so = 2 * s + 1;
@@ -434,6 +545,15 @@ int conv3x3_view(const ArrView &in, int Hi, const float *w9, int stride, int pad
     NPDE_CHECK_LAUNCH();
     return NPDE_OK;
   }
+  // pooling conv read from a pair-permuted frame whose rows can be read one group past the interior
+  if (stride == 2 && pad == 0 && in.perm == 1 && in.off == 1 && !add && Ho == (Hi - 3) / 2 + 1 && (in.pitch & 3) == 0 &&
+      in.pitch >= ((Hi + 2 + 3) & ~3) && (in.bstride & 3) == 0 && (((uintptr_t)in.p) & 15) == 0 &&
+      4 * ((Ho - 1) / 2) + 8 <= in.pitch) {
+    NPDE_LAUNCH(k_pool_frame, grid2d((Ho + 1) / 2, Ho, B), dim3(TX, TY), 0, st, in.p, in.pitch, in.bstride, Hi, w9, mask,
+                mask_bstride, out, Ho);
+    NPDE_CHECK_LAUNCH();
+    return NPDE_OK;
+  }
   NPDE_LAUNCH(k_conv3x3, grid2d(Ho, Ho, B), dim3(TX, TY), 0, st, in, Hi, w9, stride, pad, mask, mask_bstride,
               out, Ho, add);
   NPDE_CHECK_LAUNCH();
@@ -487,7 +607,12 @@ int pad_up_crop_view(const float *r, int s, const float *mask_out, size_t mask_b
                      cudaStream_t st) {
   int M = s + 2, so = 2 * s + 1;
   int nested = ((long)M * M > 1024) ? 1 : 0;
-  NPDE_LAUNCH(k_pad_up_crop, grid2d(so, so, B), dim3(TX, TY), 0, st, r, s, mask_out, mask_bstride, out, nested);
+  // by coarse cells: (s + 1) rows x ceil((s + 1) / 2) column pairs
+  const bool frame = out.perm == 1 && out.off == 1 && (out.pitch & 3) == 0 && (out.bstride & 3) == 0 &&
+                     (((uintptr_t)out.p) & 15) == 0 && out.pitch >= ((so + 2 + 3) & ~3);
+  (void)so;
+  if (frame) NPDE_LAUNCH(k_pad_up_crop_quad<true>, grid2d(s / 2 + 1, s + 1, B), dim3(TX, TY), 0, st, r, s, mask_out, mask_bstride, out, nested);
+  else NPDE_LAUNCH(k_pad_up_crop_quad<false>, grid2d(s / 2 + 1, s + 1, B), dim3(TX, TY), 0, st, r, s, mask_out, mask_bstride, out, nested);
   NPDE_CHECK_LAUNCH();
   return NPDE_OK;
 }

@@ -15,7 +15,7 @@ rng = np.random.RandomState(0)
 x = torch.from_numpy(rng.rand(B, N, N).astype(np.float32)).cuda()
 bc = torch.from_numpy(rng.rand(B, 4).astype(np.float32)).cuda()
 x = npde.utils.set_boundary(x, bc)
-it = npde.UNetIterator("clamp", 3, 2, 2).cuda()
+it = npde.UNetIterator("clamp", int(os.environ.get("UP_L", 3)), 2, 2).cuda()
 with torch.no_grad():
     for p in it.parameters():
         p.copy_(torch.from_numpy(((rng.rand(1, 1, 3, 3) - 0.5) * 0.1).astype(np.float32)))
