@@ -39,17 +39,24 @@ constexpr int WCOLS = 8;      // columns per lane
 constexpr int WVALID = 30;    // lanes 1..30 of a strip store; lanes 0 and 31 are the halo (radius <= 8 columns)
 constexpr int WSLOT = 1024;   // bytes of one row segment of a strip (32 lanes x 8 columns x 4 bytes)
 constexpr int WMAX_EDGE = 1024;  // edge strips that can get their own band count (else: uniform bands)
-#ifndef NPDE_WRING
-#define NPDE_WRING 4
-#endif
-// Row segments in flight per warp (cp.async ring in shared memory).  4 measured best: at L = 1, where the kernel is
-// memory bound, 102-107 us per launch against 111 with 8 (a deeper ring scatters the DRAM accesses in flight over
-// more rows); at L = 3 the depth does not matter.
-constexpr int WRING = NPDE_WRING;
-static_assert((WRING & (WRING - 1)) == 0 && WRING >= 2, "ring size: power of two");
 #ifndef NPDE_W_TMA
 #define NPDE_W_TMA 0  // 1: row segments arrive by TMA bulk copies (one elected lane, mbarrier completion), see wring_fill
 #endif
+// Row segments in flight per warp (cp.async ring in shared memory), by layer count.  L >= 3 (fp32-pipe bound, three
+// warps per sub-partition): 8 -- 102.0 vs 106.3 us per launch at 64 x 1025^2, 0.758 vs 0.737 of the roofline sustained
+// on the same box; 16 halves the occupancy (141 us).  L <= 2 (memory bound): 4 -- a deeper ring scatters the DRAM
+// accesses in flight over more rows (L = 1: 111.3 vs 113.6 us, L = 2: 113.1 vs 115.9 us).  NPDE_WRING=n (tuning
+// builds) forces one depth for every L.
+template <int L>
+struct WRingOf {
+#ifdef NPDE_WRING
+  static constexpr int value = NPDE_WRING;
+#else
+  static constexpr int value = (L >= 3 && !NPDE_W_TMA) ? 8 : 4;
+#endif
+  static_assert((value & (value - 1)) == 0 && value >= 2, "ring size: power of two");
+};
+constexpr int WRING_TMA = 4;  // (NPDE_W_TMA builds: wring_fill is not templated on L)
 #ifndef NPDE_WIDE_MIN_CTAS
 #define NPDE_WIDE_MIN_CTAS 8
 #endif
@@ -331,7 +338,7 @@ __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const
   // completion is signalled on the slot's mbarrier (x and f rows share it).
   if ((threadIdx.x & 31) == 0 && x.tma_bytes > 0)
     tma_load_1d(slot + x.tma_dst, chunk + x.tma_src, (unsigned)x.tma_bytes,
-                x.bars + 8 * ((((unsigned)(slot - x.ring)) >> 10) & (unsigned)(WRING - 1)));
+                x.bars + 8 * ((((unsigned)(slot - x.ring)) >> 10) & (unsigned)(WRING_TMA - 1)));
   return;
 #endif
   __syncwarp();  // lanes write each other's bytes: everybody is done reading the slot's previous row
@@ -360,6 +367,7 @@ __device__ __forceinline__ void wring_fill(char *slot, const float *chunk, const
 template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P>
 __device__ __forceinline__ void wide_stage0(WState<L> &s, WCtx &x, int it, unsigned woff, f2 (&rc)[4], float &rl,
                                             float &rr) {
+  constexpr int WRING = WRingOf<L>::value;
   constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
   const int N = x.N;
   constexpr bool OS = (L == NPDE_W_OUTER_SCALAR);
@@ -471,6 +479,7 @@ __device__ __forceinline__ void wide_conv_stage(WState<L> &s, WCtx &x, const Wid
 
 template <int L, int ACT, bool HASF, bool MAIN, bool EDGE, int P, bool STORE = true>
 __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParams &p, int it, unsigned &woff) {
+  constexpr int WRING = WRingOf<L>::value;
   constexpr int DS = WDelay<L>::slots;
   constexpr unsigned DMASK = DS * (unsigned)WSLOT - 1u;
   constexpr unsigned RMASK = WRING * (unsigned)WSLOT - 1u;
@@ -515,6 +524,7 @@ __device__ __forceinline__ void wide_step(WState<L> &s, WCtx &x, const WideParam
 // rows [i0, i1) of one strip
 template <int L, int ACT, bool HASF>
 __device__ __forceinline__ void wide_piece(const WideParams &p, int strip, int i0, int i1, char *smem) {
+  constexpr int WRING = WRingOf<L>::value;
   constexpr int R = L + 1;
   constexpr int DS = WDelay<L>::slots;
   constexpr int LAT = NPDE_W_SKEW ? 2 * L : L;  // steps between the arrival of x row i+1 and the store of output row i
@@ -878,6 +888,7 @@ WideGeom wide_geom(int B, int N) {
 
 template <int L>
 constexpr size_t wide_smem(bool hasf) {
+  constexpr int WRING = WRingOf<L>::value;
   return (size_t)WSLOT * (WDelay<L>::slots + (hasf ? 2 : 1) * WRING) + (NPDE_W_TMA ? 8 * WRING : 0);
 }
 
