@@ -1,7 +1,7 @@
 // npde_wide.cu -- the k-step loop of Phi_H = ConvIterator.forward (models/iterators/conv_iterator.py:33-51)
 // on the square domain, second generation of the fused register-streaming kernel ("wide strips").
 //
-// What changed against k_conv_stream (npde_stream.cu), and why (DESIGN.md section 5.1b):
+// What changed against k_conv_stream (npde_stream.cu), and why (DESIGN.md section 5.1):
 //   * Batch-interleaved field layout "W8".  Row i of ALL images is one contiguous virtual row
 //         [ image 0 row i | image 1 row i | ... | image B-1 row i ],
 //     every image padded to G8 = ceil(N/8) groups of eight columns, and inside a group the columns are
@@ -15,7 +15,12 @@
 //     tap of every stage is one FFMA2; one SHFL pair serves eight columns instead of four; a lane moves its
 //     row with one 256-bit access (LDG/STG.E.ENL2.256, new on sm_100).  About 170 instructions per
 //     8-column row step instead of 2 x 129, for the same 264 FMA-pipe cycles.
-//   * Work partition: bands x strips one-warp CTAs in one wave, the strips of a band in lock step (launch_wide_f).
+//     (At L = 3 the two straddling taps run as scalar FFMA on the halves instead: NPDE_W_OUTER_SCALAR.)
+//   * Register pairs are carried as two 32-bit values (NPDE_F2_HALVES, npde_f2.cuh) and packed only inside the
+//     packed instruction: ptxas then keeps the loop-carried partial sums in place (no ~80 MOVs per two row steps).
+//   * Work partition: bands x strips one-warp CTAs in one wave, the strips of a band in lock step; band counts of
+//     interior and edge strips from a cost model, occupancy enforced through the shared-memory request, launches
+//     chained with programmatic dependent launch (launch_wide_f); the band warm-up runs store-free.
 // The arithmetic is unchanged: per output the oracle's order (oracle/npde_oracle.c conv3x3_img, orc_fd_step),
 // explicit fma.rn / mul.rn / sub.rn only, so iterates stay bit-identical to k_conv_stream and the CPU oracle.
 #include <stdlib.h>
