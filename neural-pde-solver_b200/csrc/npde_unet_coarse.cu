@@ -137,16 +137,18 @@ __device__ void pool_from_global(const float *pb, const ArrView &v, int s_in, fl
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
         const float *src = pb + (size_t)(2 * i + a + v.off) * v.pitch;
-        for (int c = tx; c < rowlen; c += 32) mine[a * rowlen + c] = __ldg(src + c);
+        // (the pair permutation of a frame row is undone here, once per element: it is its own inverse)
+        for (int c = tx; c < rowlen; c += 32) mine[a * rowlen + npde_view_col(c, v.perm)] = __ldg(src + c);
       }
       __syncwarp();
       for (int j = tx; j < s_out; j += 32) {
+        const float *t0 = mine + 2 * j + v.off;
         float acc = 0.0f;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            const float t = mine[a * rowlen + npde_view_col(2 * j + c + v.off, v.perm)];
+            const float t = t0[a * rowlen + c];
             acc = (a == 0 && c == 0) ? __fmul_rn(k[0], t) : __fmaf_rn(k[a * 3 + c], t, acc);
           }
         if (mask_plane) acc = __fmul_rn(acc, __fsub_rn(1.0f, __ldg(mask_plane + (size_t)(i + 1) * Po + (j + 1))));
@@ -288,10 +290,58 @@ k_unet_coarse(const CoarseParams p) {
     const float *m = p.mask[l0 - 1] ? p.mask[l0 - 1] + (size_t)b * p.mbs[l0 - 1] : nullptr;
     float *ob = p.up.p + (size_t)b * p.up.bstride;
     const ArrViewMut up = p.up;
-    up_plane(res, s, nested, [&](int i, int j, float v) {
-      if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + (i + 1) * (so + 2) + (j + 1))));
-      ob[(i + up.off) * up.pitch + npde_view_col(j + up.off, up.perm)] = v;
-    });
+    const bool frame = up.perm == 1 && up.off == 1 && (up.pitch & 3) == 0 && (up.bstride & 3) == 0 &&
+                       ((((uintptr_t)up.p) & 15) == 0) && up.pitch >= ((so + 2 + 3) & ~3);
+    if (frame) {
+      // by pairs of coarse cells (I, 2m), (I, 2m+1): their 2 x 4 outputs are one aligned 16-byte group of each of
+      // two frame rows (k_pad_up_crop_quad<true>) -- one 128-bit store per row instead of four 4-byte ones
+      const int P = s + 2, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+      for (int I = ty; I <= s; I += 32)
+        for (int mq = tx; 2 * mq <= s; mq += 32) {
+          const int J = 2 * mq;
+          const float *q = res + I * P + J;
+          float a[2][3];
+#pragma unroll
+          for (int di = 0; di < 2; ++di)
+#pragma unroll
+            for (int dj = 0; dj < 3; ++dj) a[di][dj] = (J + dj <= s + 1) ? q[di * P + dj] : 0.0f;
+#pragma unroll
+          for (int di = 0; di < 2; ++di) {
+            const int i = 2 * I + di - 1;
+            if (i < 0 || i >= so) continue;
+            float v[4];
+#pragma unroll
+            for (int dj = 0; dj < 4; ++dj) {
+              const int c = dj >> 1;
+              const float p00 = a[0][c], p01 = a[0][c + 1], p10 = a[1][c], p11 = a[1][c + 1];
+              if (di == 0 && !(dj & 1)) v[dj] = p00;
+              else if (di == 0) v[dj] = __fmul_rn(0.5f, __fadd_rn(p00, p01));
+              else if (!(dj & 1)) v[dj] = __fmul_rn(0.5f, __fadd_rn(p00, p10));
+              else {
+                const float sum = nested ? __fadd_rn(__fadd_rn(p00, p01), __fadd_rn(p10, p11))
+                                         : __fadd_rn(__fadd_rn(__fadd_rn(p00, p01), p10), p11);
+                v[dj] = __fmul_rn(0.25f, sum);
+              }
+              const int j = 2 * J + dj - 1;
+              if (m && j >= 0 && j < so) v[dj] = __fmul_rn(v[dj], __fsub_rn(1.0f, __ldg(m + (i + 1) * (so + 2) + (j + 1))));
+            }
+            const int j0 = 2 * J - 1;
+            float *g = ob + (size_t)(i + 1) * up.pitch + 4 * mq;
+            if (j0 >= 0 && j0 + 3 < so) {
+              *reinterpret_cast<float4 *>(g) = make_float4(v[0], v[2], v[1], v[3]);
+            } else {
+#pragma unroll
+              for (int dj = 0; dj < 4; ++dj)
+                if (j0 + dj >= 0 && j0 + dj < so) g[npde_view_col(dj, 1)] = v[dj];
+            }
+          }
+        }
+    } else {
+      up_plane(res, s, nested, [&](int i, int j, float v) {
+        if (m) v = __fmul_rn(v, __fsub_rn(1.0f, __ldg(m + (i + 1) * (so + 2) + (j + 1))));
+        ob[(i + up.off) * up.pitch + npde_view_col(j + up.off, up.perm)] = v;
+      });
+    }
   }
 }
 
