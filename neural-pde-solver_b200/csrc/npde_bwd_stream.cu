@@ -17,6 +17,8 @@
 //
 // Replaces, per step, the layered chain k_psi_residual + L x k_conv3x3 + k_bwd_gz + L x k_bwd_layer + k_bwd_gx
 // (npde_conv_ops.cu; still used for mask geometries and more than three layers).
+#include <stdlib.h>
+
 #include "npde_common.cuh"
 #include "npde_internal.h"
 
@@ -36,6 +38,19 @@ struct BwdParams {
   int strips, bands, band_rows;
   const float *w;  // (L, 9) weights in device memory
 };
+
+// Programmatic dependent launch (as in npde_wide.cu): a grid may become resident while its predecessor in the stream
+// drains; it touches global memory only after griddepcontrol.wait.  A backward pass is a chain
+// k_bwd_stream -> k_bwd_finish -> k_bwd_stream -> ...: every link waits for its predecessor, which itself completed
+// only after ITS predecessor, so step t+1 sees both the gradient field and the partial sums of step t.
+#ifdef NPDE_EMU
+__device__ __forceinline__ void bw_pdl_sync() {}
+#else
+__device__ __forceinline__ void bw_pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 
 struct Row6 {
   float v[6];  // v[0] = column -1 (left lane's last), v[1..4] = own columns, v[5] = column 4 (right lane's first)
@@ -101,6 +116,7 @@ __global__ void __launch_bounds__(32, 12)
 k_bwd_stream(const BwdParams p) {
   NPDE_DYN_SMEM(char, smem);
   using LY = BwdLayout<L>;
+  bw_pdl_sync();
   const int lane = threadIdx.x & 31, N = p.N;
   const int lane_l = (lane + 31) & 31, lane_r = (lane + 1) & 31;
   const int strip = (int)blockIdx.x % p.strips, band = (int)blockIdx.x / p.strips;
@@ -369,6 +385,7 @@ constexpr int FIN_THREADS = 128;
 __global__ void __launch_bounds__(FIN_THREADS)
 k_bwd_finish(const double *__restrict__ part, int ctas, int taps, float *gw, int accumulate) {
   __shared__ double sh[FIN_THREADS];
+  bw_pdl_sync();
   const int t = blockIdx.x;
   double v = 0.0;
   for (int k = threadIdx.x; k < ctas; k += FIN_THREADS) v += part[(size_t)k * taps + t];
@@ -379,6 +396,32 @@ k_bwd_finish(const double *__restrict__ part, int ctas, int taps, float *gw, int
     __syncthreads();
   }
   if (threadIdx.x == 0) gw[t] = accumulate ? __fadd_rn(gw[t], (float)sh[0]) : (float)sh[0];
+}
+
+// launch with programmatic stream serialization (plain launch in the emulator and inside a stream capture)
+template <class K, class... A>
+int bw_launch(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, A... args) {
+#ifndef NPDE_EMU
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone && !getenv("NPDE_BWD_NO_PDL")) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    npde_note_launch();
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+    return e == cudaSuccess ? NPDE_OK : (int)e;
+  }
+#endif
+  NPDE_LAUNCH(kern, grid, block, smem, st, args...);
+  NPDE_CHECK_LAUNCH();
+  return NPDE_OK;
 }
 
 struct BwdGeom {
@@ -421,9 +464,7 @@ int launch_bwd(BwdParams &p, cudaStream_t st) {
   if (smem > 48 * 1024) cudaFuncSetAttribute(k_bwd_stream<L, ACT, HASF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   dim3 grid((unsigned)((long)p.strips * p.bands)), block(32);
-  NPDE_LAUNCH((k_bwd_stream<L, ACT, HASF>), grid, block, smem, st, p);
-  NPDE_CHECK_LAUNCH();
-  return NPDE_OK;
+  return bw_launch(k_bwd_stream<L, ACT, HASF>, grid, block, smem, st, p);
 }
 
 template <int L>
@@ -473,10 +514,8 @@ int conv_bwd_stream(const float *x, const float *f, const float *w_dev, int n_la
   }
   if (rc != NPDE_OK) return rc;
   const int ctas = p.strips * p.bands, taps = 9 * n_layers;
-  NPDE_LAUNCH(k_bwd_finish, dim3((unsigned)taps), dim3(FIN_THREADS), 0, st, (const double *)p.part, ctas, taps, gw,
-              accumulate ? 1 : 0);
-  NPDE_CHECK_LAUNCH();
-  return NPDE_OK;
+  return bw_launch(k_bwd_finish, dim3((unsigned)taps), dim3(FIN_THREADS), 0, st, (const double *)p.part, ctas, taps, gw,
+                   accumulate ? 1 : 0);
 }
 
 }  // namespace npde
