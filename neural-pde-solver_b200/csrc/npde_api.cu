@@ -731,7 +731,7 @@ __global__ void k_solve_check(const float *err, int B, float tol, int add, int m
 // ======================================================================= C ABI
 extern "C" {
 
-int npde_version(void) { return 100; }
+int npde_version(void) { return 200; }  // major * 100 + minor: 2.0 = round 2 (packed solver loop, npde_solve, streaming backward)
 
 unsigned long long npde_debug_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
